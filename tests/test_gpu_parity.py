@@ -1,0 +1,431 @@
+"""GPU parity tests: the sm_100a path (through the C-ABI in vearch_b200/libgamma.so) against the
+CPU oracle on the same seeded inputs.
+
+Bars (north_star): integer/byte/index work bit-exact; floating point within 1e-4 relative.
+ * SIFT-shaped integer-valued data makes every fp32 partial sum exact, so scores must be
+   BIT-EQUAL and ids equal, except inside a group of exactly tied scores at the k-th boundary,
+   where the reference itself is scan-order dependent (DESIGN.md "tie rule").
+ * With shared index state (centroids, codebooks, list contents, probe lists, coarse distances)
+   the IVF-PQ ADC distances are bit-equal on float data too (same table arithmetic, same order).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from vearch_b200 import synth
+
+pytestmark = pytest.mark.gpu
+L2, IP = orc.METRIC_L2, orc.METRIC_IP
+FLT_MAX = np.finfo(np.float32).max
+
+
+def gi():
+    from vearch_b200 import index as gidx
+    return gidx
+
+
+def mt(metric):
+    return "L2" if metric == L2 else "InnerProduct"
+
+
+def assert_same_results(dg, ig, do, io, bit_exact=True, rtol=1e-4):
+    """scores equal (bitwise or rtol); ids equal except inside the tie group at the k-th boundary."""
+    assert dg.shape == do.shape and ig.shape == io.shape
+    if bit_exact:
+        assert np.array_equal(dg, do), f"score mismatch: max abs diff {np.abs(dg - do).max()}"
+    else:
+        ok = np.isclose(dg, do, rtol=rtol, atol=1e-6) | ((ig < 0) & (io < 0))
+        assert ok.all(), f"score mismatch beyond rtol={rtol}"
+    for q in range(dg.shape[0]):
+        if np.array_equal(ig[q], io[q]):
+            continue
+        valid = io[q] >= 0
+        assert np.array_equal(valid, ig[q] >= 0), "different number of results"
+        if not valid.any():
+            continue
+        boundary = do[q][valid][-1]
+        for v in np.unique(do[q][valid]):
+            grp = valid & (do[q] == v)
+            if v == boundary:
+                continue  # boundary tie group: membership is scan-order dependent in the reference
+            if bit_exact:
+                assert set(ig[q][grp]) == set(io[q][grp]), f"query {q}: ids differ at score {v}"
+        if not bit_exact:
+            # float data: allow swaps between near-equal neighbours only
+            common = len(set(ig[q][valid]) & set(io[q][valid]))
+            assert common >= valid.sum() - 1, f"query {q}: {valid.sum() - common} ids differ"
+
+
+def recall_1nn(ids, gt1, i):
+    return float(np.mean([(gt1[q] in ids[q, :i]) for q in range(ids.shape[0])]))
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 FLAT
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [L2, IP])
+@pytest.mark.parametrize("n,d,nq,k", [(5000, 128, 37, 10), (3000, 32, 5, 100), (777, 30, 3, 7), (40, 8, 2, 64)])
+def test_flat_matches_oracle(metric, n, d, nq, k):
+    db = synth.sift_like(n, d, seed=11)
+    xq = synth.sift_like(nq, d, seed=12)
+    idx = gi().GammaIndex("FLAT", d, {"metric_type": mt(metric)})
+    idx.add_vectors(db[: n // 2])
+    idx.add_vectors(db[n // 2:])
+    assert idx.ntotal == n
+    dg, ig = idx.search(xq, k)
+    do, io = orc.flat_search(db, xq, k, metric)
+    assert_same_results(dg, ig, do, io)
+    if metric == L2:
+        assert np.array_equal(ig, io)  # FLAT L2: ids bit-exact including order
+    idx.close()
+
+
+def test_flat_multi_chunk_and_filters():
+    n, d, nq, k = 300_000, 16, 16, 20  # > 131072 rows => several distance blocks + key merge
+    db = synth.sift_like(n, d, seed=21)
+    xq = synth.sift_like(nq, d, seed=22)
+    idx = gi().GammaIndex("FLAT", d, {"metric_type": "L2"})
+    idx.add_vectors(db)
+    dg, ig = idx.search(xq, k)
+    do, io = orc.flat_search(db, xq, k, L2)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    rng = np.random.default_rng(0)
+    deleted = rng.random(n) < 0.4
+    allowed = rng.random(n) < 0.5
+    delb, filb = np.packbits(deleted, bitorder="little"), np.packbits(allowed, bitorder="little")
+    dg, ig = idx.search(xq, k, del_bitmap=delb, filter_bitmap=filb)
+    do, io = orc.flat_search(db, xq, k, L2, del_bitmap=delb, filter_bitmap=filb)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    assert not deleted[ig[ig >= 0]].any() and allowed[ig[ig >= 0]].all()
+    lo, hi = float(do[0, 3]), float(do[0, 12])
+    dg, ig = idx.search(xq, k, min_score=lo, max_score=hi)
+    do, io = orc.flat_search(db, xq, k, L2, min_score=lo, max_score=hi)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    idx.close()
+
+
+def test_flat_empty_and_tiny():
+    idx = gi().GammaIndex("FLAT", 8, {"metric_type": "L2"})
+    xq = synth.sift_like(3, 8, seed=1)
+    dg, ig = idx.search(xq, 5)
+    assert (ig == -1).all() and (dg == FLT_MAX).all()
+    db = synth.sift_like(2, 8, seed=2)
+    idx.add_vectors(db)
+    dg, ig = idx.search(xq, 5)
+    do, io = orc.flat_search(db, xq, 5, L2)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    idx.close()
+
+
+def test_flat_float_data_and_reference_pins():
+    db = synth.embed_like(4000, 64, seed=3)
+    idx = gi().GammaIndex("FLAT", 64, {"metric_type": "InnerProduct"})
+    idx.add_vectors(db)
+    dg, ig = idx.search(db[:64], 10)
+    do, io = orc.flat_search(db, db[:64], 10, IP)
+    assert_same_results(dg, ig, do, io, bit_exact=False)
+    # self-query top-1 ~ 1.0 for normalised IP (internal/engine/tests/test.h:554-565)
+    assert np.array_equal(ig[:, 0], np.arange(64)) and np.abs(dg[:, 0] - 1).max() < 1e-5
+    # L2 score == sum (x-y)^2 within 0.01 (test/test_module_vector.py:337-364)
+    dl, il = idx.search(db[:8], 5, params={"metric_type": "L2"})
+    manual = ((db[:8, None, :] - db[il]) ** 2).sum(-1)
+    assert np.abs(manual - dl).max() < 0.01
+    idx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# K2 coarse quantiser, K6 k-means
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ivf_state():
+    d, n, nlist = 64, 20000, 64
+    db = synth.sift_like(n, d, seed=31)
+    xq = synth.sift_like(48, d, seed=32)
+    cent, _, _ = orc.kmeans(db[:8000], nlist, niter=6)
+    cent = np.rint(cent).astype(np.float32)  # integer-valued shared state => exact arithmetic
+    a = orc.assign(cent, db, L2)
+    off, order = orc.build_lists(a, nlist)
+    return dict(d=d, n=n, nlist=nlist, db=db, xq=xq, cent=cent, assign=a, off=off, order=order)
+
+
+@pytest.mark.parametrize("metric", [L2, IP])
+def test_coarse_search_exact(ivf_state, metric):
+    s = ivf_state
+    idx = gi().GammaIndex("IVFFLAT", s["d"], {"ncentroids": s["nlist"], "nprobe": 8, "metric_type": mt(metric)})
+    idx.set_centroids(s["cent"])
+    dg, ig = idx.coarse_search(s["xq"], 8)
+    do, io = orc.coarse_search(s["cent"], s["xq"], 8, metric)
+    assert_same_results(dg, ig, do, io)
+    idx.close()
+
+
+def test_kmeans_update_bit_exact(ivf_state):
+    s = ivf_state
+    x = synth.embed_like(5000, 48, seed=5)  # float data: order of summation matters
+    a = np.random.default_rng(1).integers(0, 37, size=5000)
+    a[a == 5] = 6  # leave one cluster empty
+    co, h = orc.kmeans_update(x, 37, a)
+    cg = gi().kmeans_update(x, 37, a)
+    assert np.array_equal(co, cg)
+
+
+def test_kmeans_device_quality():
+    x = synth.sift_like(8000, 32, seed=41)
+    cg, og = gi().kmeans(x, 32, niter=10)
+    co, _, oo = orc.kmeans(x, 32, niter=10)
+    # same seeded initialisation and integer data => identical first objective
+    assert og[0] == oo[0]
+    assert og[-1] <= og[0] and abs(og[-1] - oo[-1]) <= 0.02 * oo[-1]
+    ag = orc.assign(cg, x, L2)
+    ao = orc.assign(co, x, L2)
+    ig_, io_ = ((x - cg[ag]) ** 2).sum(), ((x - co[ao]) ** 2).sum()
+    assert abs(ig_ - io_) <= 0.02 * io_
+
+
+# ----------------------------------------------------------------------------------------------
+# K3 IVF-Flat
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ivfflat_index(ivf_state):
+    s = ivf_state
+    idx = gi().GammaIndex("IVFFLAT", s["d"], {"ncentroids": s["nlist"], "nprobe": 8, "metric_type": "L2"})
+    idx.set_centroids(s["cent"])
+    idx.add_vectors(s["db"][:12000])
+    idx.add_pending()
+    idx.add_vectors(s["db"][12000:])  # second batch exercises list growth (copy-on-grow)
+    idx.add_pending()
+    assert idx.indexed_count == s["n"]
+    yield idx
+    idx.close()
+
+
+def test_ivf_lists_match_oracle_layout(ivf_state, ivfflat_index):
+    s = ivf_state
+    off, codes, ids = ivfflat_index.export_lists()
+    assert np.array_equal(off, s["off"])  # same assignment
+    assert np.array_equal(ids, s["order"])  # insertion (vid) order inside each list
+    vecs = codes.view(np.float32).reshape(len(ids), -1)[:, : s["d"]]
+    assert np.array_equal(vecs, s["db"][s["order"]])
+
+
+@pytest.mark.parametrize("metric", [L2, IP])
+@pytest.mark.parametrize("k,nprobe", [(10, 8), (100, 16), (1, 1)])
+def test_ivfflat_search_preassigned_exact(ivf_state, ivfflat_index, metric, k, nprobe):
+    s = ivf_state
+    cd, keys = orc.coarse_search(s["cent"], s["xq"], nprobe, metric)
+    dg, ig = ivfflat_index.search_preassigned(s["xq"], k, keys, cd, params={"metric_type": mt(metric)})
+    do, io = orc.ivfflat_search_preassigned(s["off"], s["db"][s["order"]], s["order"], s["xq"], k, keys, metric)
+    assert_same_results(dg, ig, do, io)
+
+
+def test_ivfflat_search_end_to_end_and_filters(ivf_state, ivfflat_index):
+    s = ivf_state
+    nprobe, k = 8, 10
+    dg, ig = ivfflat_index.search(s["xq"], k, params={"nprobe": nprobe})
+    cd, keys = orc.coarse_search(s["cent"], s["xq"], nprobe, L2)
+    do, io = orc.ivfflat_search_preassigned(s["off"], s["db"][s["order"]], s["order"], s["xq"], k, keys, L2)
+    assert_same_results(dg, ig, do, io)
+    rng = np.random.default_rng(3)
+    deleted = rng.random(s["n"]) < 0.3
+    delb = np.packbits(deleted, bitorder="little")
+    dg, ig = ivfflat_index.search(s["xq"], k, params={"nprobe": nprobe}, del_bitmap=delb)
+    do, io = orc.ivfflat_search_preassigned(s["off"], s["db"][s["order"]], s["order"], s["xq"], k, keys, L2,
+                                            del_bitmap=delb)
+    assert_same_results(dg, ig, do, io)
+    lo, hi = float(do[0, 2]), float(do[0, 7])
+    dg, ig = ivfflat_index.search(s["xq"], k, params={"nprobe": nprobe}, min_score=lo, max_score=hi)
+    do, io = orc.ivfflat_search_preassigned(s["off"], s["db"][s["order"]], s["order"], s["xq"], k, keys, L2,
+                                            min_score=lo, max_score=hi)
+    assert_same_results(dg, ig, do, io)
+    # brute-force request on an IVF index == FLAT (gamma_index_ivfflat.cc:541-550)
+    dg, ig = ivfflat_index.search(s["xq"], k, brute_force=True)
+    do, io = orc.flat_search(s["db"], s["xq"], k, L2)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    # reference CI pins (test/test_vector_index_ivfflat.py:89-94)
+    dg, ig = ivfflat_index.search(s["xq"], 100, params={"nprobe": 16})
+    assert recall_1nn(ig, io[:, 0], 1) >= 0.8 and recall_1nn(ig, io[:, 0], 10) >= 0.9
+
+
+def test_ivfflat_tombstone_and_bad_keys(ivf_state):
+    s = ivf_state
+    idx = gi().GammaIndex("IVFFLAT", s["d"], {"ncentroids": s["nlist"], "nprobe": 4, "metric_type": "L2"})
+    idx.set_centroids(s["cent"])
+    idx.add_vectors(s["db"][:5000])
+    deleted = np.zeros(5000, bool)
+    deleted[::7] = True  # deleted before indexing => never enter the lists (ivfflat.cc:436)
+    idx.add_pending(del_bitmap=np.packbits(deleted, bitorder="little"))
+    off, codes, ids = idx.export_lists()
+    assert len(ids) == 5000 - deleted.sum() and not deleted[ids].any()
+    cd, keys = orc.coarse_search(s["cent"], s["xq"], 4, L2)
+    vecs = codes.view(np.float32).reshape(len(ids), -1)
+    d0, i0 = idx.search_preassigned(s["xq"], 5, keys, cd)
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids, s["xq"], 5, keys, L2)
+    assert_same_results(d0, i0, do, io)
+    # tombstone the best hit of query 0 (Update path, realtime_mem_data.cc:298-320)
+    victim = int(i0[0, 0])
+    pos_global = int(np.flatnonzero(ids == victim)[0])
+    l = int(np.searchsorted(off, pos_global, side="right") - 1)
+    idx.tombstone(l, pos_global - int(off[l]))
+    ids2 = ids.copy()
+    ids2[pos_global] |= orc.DEL_MASK
+    d1, i1 = idx.search_preassigned(s["xq"], 5, keys, cd)
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, s["xq"], 5, keys, L2)
+    assert_same_results(d1, i1, do, io)
+    assert victim not in i1[0]
+    keys2 = keys.copy()
+    keys2[:, 1] = -1  # "not enough centroids for multiprobe"
+    d2, i2 = idx.search_preassigned(s["xq"], 5, keys2, cd)
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, s["xq"], 5, keys2, L2)
+    assert_same_results(d2, i2, do, io)
+    idx.close()
+
+
+def test_ivfflat_train_on_device_recall():
+    d, n, nlist = 32, 30000, 64
+    db = synth.sift_like(n, d, seed=51)
+    xq = synth.sift_like(100, d, seed=52)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": 16, "metric_type": "L2",
+                                         "training_threshold": 10000})
+    idx.add_vectors(db)
+    assert not idx.is_trained
+    dg, ig = idx.search(xq, 10)  # untrained => FLAT fallback over all stored vectors
+    do, io = orc.flat_search(db, xq, 10, L2)
+    assert np.array_equal(dg, do) and np.array_equal(ig, io)
+    idx.train()
+    idx.add_pending()
+    assert idx.is_trained and idx.indexed_count == n
+    dg, ig = idx.search(xq, 10)
+    assert recall_1nn(ig, io[:, 0], 1) >= 0.8 and recall_1nn(ig, io[:, 0], 10) >= 0.9
+    # exact parity against the oracle on the index state the device produced
+    off, codes, ids = idx.export_lists()
+    cent = idx.get_centroids()
+    cd, keys = idx.coarse_search(xq, 16)
+    dref, iref = orc.ivfflat_search_preassigned(off, codes.view(np.float32).reshape(len(ids), -1), ids, xq, 10, keys, L2)
+    assert_same_results(dg, ig, dref, iref)
+    idx.close()
+
+
+def test_ivfflat_d768_inner_product():
+    d, n, nlist = 768, 6000, 16
+    db = synth.embed_like(n, d, seed=61)
+    xq = synth.embed_like(20, d, seed=62)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": 4, "metric_type": "InnerProduct",
+                                         "training_threshold": 2000})
+    idx.add_vectors(db)
+    idx.train()
+    idx.add_pending()
+    dg, ig = idx.search(xq, 10)
+    off, codes, ids = idx.export_lists()
+    cd, keys = idx.coarse_search(xq, 4)
+    dref, iref = orc.ivfflat_search_preassigned(off, codes.view(np.float32).reshape(len(ids), -1), ids, xq, 10, keys, IP)
+    assert_same_results(dg, ig, dref, iref, bit_exact=False)
+    idx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# K4 / K5 / K8 IVF-PQ
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def pq_state(ivf_state):
+    s = ivf_state
+    M = 8
+    resid = s["db"][:8000] - s["cent"][s["assign"][:8000]]
+    pqc = orc.pq_train(resid, M, niter=6)  # float codebooks
+    return dict(M=M, pqc=pqc)
+
+
+@pytest.mark.parametrize("metric", [L2, IP])
+def test_ivfpq_shared_state_bit_exact(ivf_state, pq_state, metric):
+    s, M, pqc = ivf_state, pq_state["M"], pq_state["pqc"]
+    idx = gi().GammaIndex("IVFPQ", s["d"], {"ncentroids": s["nlist"], "nprobe": 8, "nsubvector": M,
+                                            "metric_type": mt(metric)})
+    idx.set_centroids(s["cent"])
+    idx.set_pq_centroids(pqc)
+    idx.add_vectors(s["db"])
+    idx.add_pending()
+    a = orc.assign(s["cent"], s["db"], metric)
+    off_o, order = orc.build_lists(a, s["nlist"])
+    codes_o = orc.ivfpq_encode(s["cent"], pqc, s["db"], a)
+    # K8: codes byte-exact, list layout identical
+    assert np.array_equal(idx.pq_encode(s["db"][:3000], a[:3000]), codes_o[:3000])
+    off, codes, ids = idx.export_lists()
+    assert np.array_equal(off, off_o) and np.array_equal(ids, order) and np.array_equal(codes, codes_o[order])
+    T = None
+    if metric == L2:
+        T = orc.ivfpq_precompute_table(s["cent"], pqc)
+        assert np.array_equal(idx.get_precomputed_table(), T)  # K4 table bit-equal
+    for k, nprobe, recall_num in [(10, 8, 0), (50, 16, 0), (10, 8, 100), (10, 8, 5)]:
+        cd, keys = orc.coarse_search(s["cent"], s["xq"], nprobe, metric)
+        params = {"recall_num": recall_num} if recall_num else None
+        dg, ig = idx.search_preassigned(s["xq"], k, keys, cd, params=params)
+        do, io = orc.ivfpq_search_preassigned(off, codes, ids, s["cent"], pqc, T, s["xq"], k, keys, cd, metric,
+                                              recall_num=recall_num, raw=s["db"])
+        if metric == IP:
+            # oracle recomputes dis0 = <x, centroid> with its own summation order: integer data => same bits
+            pass
+        assert_same_results(dg, ig, do, io, bit_exact=(recall_num == 0 or True))
+    # filters
+    deleted = np.random.default_rng(5).random(s["n"]) < 0.25
+    delb = np.packbits(deleted, bitorder="little")
+    cd, keys = orc.coarse_search(s["cent"], s["xq"], 8, metric)
+    dg, ig = idx.search_preassigned(s["xq"], 10, keys, cd, del_bitmap=delb)
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids, s["cent"], pqc, T, s["xq"], 10, keys, cd, metric,
+                                          del_bitmap=delb)
+    assert_same_results(dg, ig, do, io)
+    idx.close()
+
+
+def test_ivfpq_train_on_device_recall():
+    d, n, nlist, M = 64, 40000, 64, 16
+    db = synth.sift_like(n, d, seed=71)
+    xq = synth.sift_like(100, d, seed=72)
+    idx = gi().GammaIndex("IVFPQ", d, {"ncentroids": nlist, "nprobe": 16, "nsubvector": M, "metric_type": "L2",
+                                       "training_threshold": 12800})
+    idx.add_vectors(db)
+    idx.train()
+    idx.add_pending()
+    assert idx.indexed_count == n
+    _, gt = orc.flat_search(db, xq, 1, L2)
+    dg, ig = idx.search(xq, 100)
+    # reference CI pins for IVFPQ (test/test_vector_index_ivfpq.py:105-111)
+    assert recall_1nn(ig, gt[:, 0], 10) >= 0.9 and recall_1nn(ig, gt[:, 0], 100) >= 0.95
+    dr, ir = idx.search(xq, 10, params={"recall_num": 100})
+    assert recall_1nn(ir, gt[:, 0], 1) >= 0.8
+    exact = ((xq[:, None, :] - db[ir]) ** 2).sum(-1)
+    assert np.array_equal(exact, dr)  # re-ranked scores are exact L2 (integer data)
+    # parity with the oracle on the device-built state (same probes & coarse distances)
+    off, codes, ids = idx.export_lists()
+    cent, pqc, T = idx.get_centroids(), idx.get_pq_centroids(), idx.get_precomputed_table()
+    assert np.array_equal(T, orc.ivfpq_precompute_table(cent, pqc))
+    cd, keys = idx.coarse_search(xq, 16)
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids, cent, pqc, T, xq, 100, keys, cd, L2)
+    assert_same_results(dg, ig, do, io)
+    idx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# K7 merge / multi-partition
+# ----------------------------------------------------------------------------------------------
+def test_merge_partitions_matches_router_order():
+    import torch
+    rng = np.random.default_rng(9)
+    nparts, nq, k = 4, 33, 10
+    for metric in (L2, IP):
+        dis = np.sort(rng.integers(0, 40, size=(nparts, nq, k)).astype(np.float32), axis=2)
+        if metric == IP:
+            dis = dis[:, :, ::-1].copy()
+        ids = rng.integers(0, 1000, size=(nparts, nq, k)).astype(np.int64)
+        ids[1, :, 7:] = -1
+        od, oi = orc.merge_partitions(dis, ids, metric)
+        gd, gi_ = gi().merge_partitions_device(torch.from_numpy(dis).cuda(), torch.from_numpy(ids).cuda(), metric)
+        assert np.array_equal(gd.cpu().numpy(), od) and np.array_equal(gi_.cpu().numpy(), oi)
+
+
+def test_search_device_resident_matches_host(ivf_state, ivfflat_index):
+    import torch
+    s = ivf_state
+    dg, ig = ivfflat_index.search(s["xq"], 10, params={"nprobe": 8})
+    xq_dev = torch.from_numpy(s["xq"]).cuda()
+    dd, di = ivfflat_index.search_device(xq_dev, 10, params={"nprobe": 8})
+    torch.cuda.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), dg) and np.array_equal(di.cpu().numpy(), ig)

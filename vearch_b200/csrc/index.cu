@@ -1,0 +1,1100 @@
+// Host orchestration of the hot path (see index.h).  Reference call sites are cited inline.
+#include "index.h"
+
+#include <float.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+
+#include "common.cuh"
+
+namespace gb {
+
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* last_error() { return g_last_error.c_str(); }
+
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+static cudaStream_t thread_stream(int device) {
+  static thread_local cudaStream_t st[64] = {nullptr};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!st[device]) {
+    cudaSetDevice(device);
+    cudaStreamCreateWithFlags(&st[device], cudaStreamNonBlocking);
+  }
+  return st[device];
+}
+
+// ------------------------------------------------------------------------------------------
+Scratch::~Scratch() {
+  for (void* p : ptrs_) cudaFreeAsync(p, st_);
+}
+void* Scratch::alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(&p, bytes, st_);
+  if (e != cudaSuccess) {
+    set_last_error(std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return nullptr;
+  }
+  ptrs_.push_back(p);
+  return p;
+}
+#define GB_ALLOC(var, T, n, s)                \
+  T* var = (s).alloc_n<T>((size_t)(n));       \
+  if (!var) return -1
+
+// ------------------------------------------------------------------------------------------
+RawStore::RawStore(int d, int seg_shift) : d_(d), dpad_((int)round_up(d, 4)), seg_shift_(seg_shift) {
+  cudaMalloc(&d_segs_, sizeof(float*) * kMaxSegs);
+}
+RawStore::~RawStore() {
+  for (float* p : segs_) cudaFree(p);
+  cudaFree(d_segs_);
+}
+int RawStore::ensure(int64_t n_total) {
+  while ((int64_t)segs_.size() * seg_rows() < n_total) {
+    if ((int)segs_.size() >= kMaxSegs) {
+      set_last_error("raw store: too many segments");
+      return -1;
+    }
+    float* p = nullptr;
+    size_t bytes = (size_t)seg_rows() * dpad_ * 4;
+    GB_CUDA(cudaMalloc(&p, bytes));
+    GB_CUDA(cudaMemset(p, 0, bytes));
+    segs_.push_back(p);
+    GB_CUDA(cudaMemcpy(d_segs_ + segs_.size() - 1, &p, sizeof(float*), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+int RawStore::append_host(const float* x, int64_t n, cudaStream_t st) {
+  if (ensure(n_ + n)) return -1;
+  int64_t done = 0;
+  while (done < n) {
+    int64_t vid = n_ + done;
+    int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
+    int64_t cnt = std::min(n - done, seg_rows() - off);
+    GB_CUDA(cudaMemcpy2DAsync(segs_[si] + off * dpad_, (size_t)dpad_ * 4, x + done * d_, (size_t)d_ * 4, (size_t)d_ * 4,
+                              (size_t)cnt, cudaMemcpyHostToDevice, st));
+    done += cnt;
+  }
+  GB_CUDA(cudaStreamSynchronize(st));
+  n_ += n;
+  return 0;
+}
+int RawStore::append_device(const float* x, int64_t ld, int64_t n, cudaStream_t st) {
+  if (ensure(n_ + n)) return -1;
+  int64_t done = 0;
+  while (done < n) {
+    int64_t vid = n_ + done;
+    int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
+    int64_t cnt = std::min(n - done, seg_rows() - off);
+    GB_CUDA(cudaMemcpy2DAsync(segs_[si] + off * dpad_, (size_t)dpad_ * 4, x + done * ld, (size_t)ld * 4,
+                              (size_t)d_ * 4, (size_t)cnt, cudaMemcpyDeviceToDevice, st));
+    done += cnt;
+  }
+  GB_CUDA(cudaStreamSynchronize(st));
+  n_ += n;
+  return 0;
+}
+int RawStore::update_host(int64_t vid, const float* x, cudaStream_t st) {
+  if (vid < 0 || vid >= n_) return -1;
+  int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
+  GB_CUDA(cudaMemcpyAsync(segs_[si] + off * dpad_, x, (size_t)d_ * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int RawStore::get_host(int64_t vid, float* out) const {
+  if (vid < 0 || vid >= n_) return -1;
+  int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
+  GB_CUDA(cudaMemcpy(out, segs_[si] + off * dpad_, (size_t)d_ * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+const float* RawStore::contiguous(int64_t n, Scratch& s) {
+  if (n <= seg_rows()) return segs_.empty() ? nullptr : segs_[0];
+  float* buf = s.alloc_n<float>((size_t)n * dpad_);
+  if (!buf) return nullptr;
+  int64_t done = 0;
+  while (done < n) {
+    int64_t si = done >> seg_shift_;
+    int64_t cnt = std::min(n - done, seg_rows());
+    if (cudaMemcpyAsync(buf + done * dpad_, segs_[si], (size_t)cnt * dpad_ * 4, cudaMemcpyDeviceToDevice,
+                        s.stream()) != cudaSuccess)
+      return nullptr;
+    done += cnt;
+  }
+  return buf;
+}
+
+// ------------------------------------------------------------------------------------------
+IvfLists::IvfLists(int nlist, int code_bytes) : nlist_(nlist), code_bytes_(code_bytes) {
+  h_data_.assign(nlist, nullptr);
+  h_ids_.assign(nlist, nullptr);
+  h_len_.assign(nlist, 0);
+  h_cap_.assign(nlist, 0);
+  cudaMalloc(&d_data_, sizeof(void*) * nlist);
+  cudaMalloc(&d_ids_, sizeof(int64_t*) * nlist);
+  cudaMalloc(&d_len_, sizeof(int) * nlist);
+  cudaMemset(d_data_, 0, sizeof(void*) * nlist);
+  cudaMemset(d_ids_, 0, sizeof(int64_t*) * nlist);
+  cudaMemset(d_len_, 0, sizeof(int) * nlist);
+}
+IvfLists::~IvfLists() {
+  for (void* p : slabs_) cudaFree(p);
+  cudaFree(d_data_);
+  cudaFree(d_ids_);
+  cudaFree(d_len_);
+}
+ListDirectory IvfLists::directory() const {
+  ListDirectory dir;
+  dir.vecs = reinterpret_cast<const float* const*>(d_data_);
+  dir.codes = reinterpret_cast<const uint8_t* const*>(d_data_);
+  dir.ids = reinterpret_cast<const int64_t* const*>(d_ids_);
+  dir.len = d_len_;
+  dir.nlist = nlist_;
+  return dir;
+}
+void* IvfLists::slab_alloc(size_t bytes) {
+  bytes = (size_t)round_up((int64_t)bytes, 256);
+  if (bytes > slab_left_) return nullptr;
+  void* p = slab_cur_;
+  slab_cur_ += bytes;
+  slab_left_ -= bytes;
+  return p;
+}
+int IvfLists::reserve(const std::vector<int>& add, cudaStream_t st) {
+  // pass 1: how many bytes do the growing lists need
+  std::vector<int> newcap(nlist_, 0);
+  size_t need_bytes = 0;
+  for (int l = 0; l < nlist_; l++) {
+    if (add[l] <= 0) continue;
+    int64_t need = (int64_t)h_len_[l] + add[l];
+    if (need <= h_cap_[l]) continue;
+    // growth policy: at least x1.5 (reference grows by 1.1 + pi/2 - atan(n), realtime_mem_data.cc:110-113)
+    int64_t nc = std::max<int64_t>(need, (int64_t)h_cap_[l] * 3 / 2);
+    nc = round_up(nc, 32);
+    if (nc > INT32_MAX) {
+      set_last_error("inverted list too long");
+      return -1;
+    }
+    newcap[l] = (int)nc;
+    need_bytes += (size_t)round_up(nc * code_bytes_ + 16, 256) + (size_t)round_up(nc * 8, 256);
+  }
+  if (need_bytes == 0) return 0;
+  if (need_bytes > slab_left_) {
+    size_t slab = std::max<size_t>(need_bytes, (size_t)64 << 20);
+    void* p = nullptr;
+    GB_CUDA(cudaMalloc(&p, slab));
+    slabs_.push_back(p);
+    slab_cur_ = static_cast<char*>(p);
+    slab_left_ = slab;
+    bytes_ += (int64_t)slab;
+  }
+  for (int l = 0; l < nlist_; l++) {
+    if (!newcap[l]) continue;
+    void* nd = slab_alloc((size_t)newcap[l] * code_bytes_ + 16);
+    int64_t* ni = static_cast<int64_t*>(slab_alloc((size_t)newcap[l] * 8));
+    if (!nd || !ni) {
+      set_last_error("slab exhausted");
+      return -1;
+    }
+    if (h_len_[l] > 0) {  // copy-on-grow; the old region stays valid for in-flight searches
+      GB_CUDA(cudaMemcpyAsync(nd, h_data_[l], (size_t)h_len_[l] * code_bytes_, cudaMemcpyDeviceToDevice, st));
+      GB_CUDA(cudaMemcpyAsync(ni, h_ids_[l], (size_t)h_len_[l] * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    h_data_[l] = nd;
+    h_ids_[l] = ni;
+    h_cap_[l] = newcap[l];
+  }
+  GB_CUDA(cudaMemcpyAsync(d_data_, h_data_.data(), sizeof(void*) * nlist_, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_ids_, h_ids_.data(), sizeof(int64_t*) * nlist_, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+int IvfLists::commit(const std::vector<int>& add, cudaStream_t st) {
+  for (int l = 0; l < nlist_; l++) {
+    h_len_[l] += add[l];
+    total_ += add[l];
+    if (h_len_[l] > max_len_) max_len_ = h_len_[l];
+  }
+  // length is published after the data (realtime_mem_data.cc:292-293): same stream, later op
+  GB_CUDA(cudaMemcpyAsync(d_len_, h_len_.data(), sizeof(int) * nlist_, cudaMemcpyHostToDevice, st));
+  return 0;
+}
+int IvfLists::tombstone(int list, int pos, cudaStream_t st) {
+  if (list < 0 || list >= nlist_ || pos < 0 || pos >= h_len_[list]) return -1;
+  int64_t v;
+  GB_CUDA(cudaMemcpyAsync(&v, h_ids_[list] + pos, 8, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  v |= kDelIdxMask;
+  GB_CUDA(cudaMemcpyAsync(h_ids_[list] + pos, &v, 8, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int IvfLists::download_list(int l, std::vector<uint8_t>* codes, std::vector<int64_t>* ids) const {
+  if (l < 0 || l >= nlist_) return -1;
+  int len = h_len_[l];
+  if (codes) {
+    codes->resize((size_t)len * code_bytes_);
+    if (len) GB_CUDA(cudaMemcpy(codes->data(), h_data_[l], codes->size(), cudaMemcpyDeviceToHost));
+  }
+  if (ids) {
+    ids->resize(len);
+    if (len) GB_CUDA(cudaMemcpy(ids->data(), h_ids_[l], (size_t)len * 8, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+Index::Index(const std::string& type, int d, const ModelParams& mp, int device, int seg_shift)
+    : type_(type), d_(d), dpad_((int)round_up(d, 4)), device_(device), mp_(mp) {
+  cudaSetDevice(device_);
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;  // keep scratch memory cached between searches
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  store_.reset(new RawStore(d, seg_shift));
+  cudaStreamCreateWithFlags(&build_stream_, cudaStreamNonBlocking);
+}
+Index::~Index() {
+  if (build_stream_) cudaStreamDestroy(build_stream_);
+}
+void Index::scan_timer_begin(cudaStream_t st) {
+  if (!time_scan_) return;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  std::lock_guard<std::mutex> g(ev_mu_);
+  scan_events_.emplace_back(e0, e1);
+}
+void Index::scan_timer_end(cudaStream_t st) {
+  if (!time_scan_) return;
+  std::lock_guard<std::mutex> g(ev_mu_);
+  if (!scan_events_.empty()) cudaEventRecord(scan_events_.back().second, st);
+}
+float Index::last_scan_ms() {
+  std::lock_guard<std::mutex> g(ev_mu_);
+  float total = 0.f;
+  for (auto& ev : scan_events_) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess)
+      total += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  scan_events_.clear();
+  return total;
+}
+int Index::add_vectors(const float* x, int64_t n) {
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  return store_->append_host(x, n, build_stream_);
+}
+int Index::add_vectors_device(const float* x, int64_t ld, int64_t n) {
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  return store_->append_device(x, ld, n, build_stream_);
+}
+
+int Index::upload_bitmaps(const SearchContext& ctx, FilterArgs* f, Scratch& s) {
+  f->del_bits = nullptr;
+  f->filter_bits = nullptr;
+  f->min_score = ctx.min_score;
+  f->max_score = ctx.max_score;
+  // the kernels index bitmaps by vid; pad to cover every stored vector
+  int64_t bits = std::max<int64_t>(ctx.bitmap_bits, store_->size());
+  size_t words = (size_t)((bits + 31) / 32) + 1;
+  size_t have = (size_t)((ctx.bitmap_bits + 7) / 8);
+  for (int which = 0; which < 2; which++) {
+    const uint8_t* src = which == 0 ? ctx.del_bitmap : ctx.filter_bitmap;
+    if (!src) continue;
+    uint32_t* dev = s.alloc_n<uint32_t>(words);
+    if (!dev) return -1;
+    // ids beyond the caller's bitmap: not deleted / not allowed
+    GB_CUDA(cudaMemsetAsync(dev, 0, words * 4, s.stream()));
+    GB_CUDA(cudaMemcpyAsync(dev, src, have, cudaMemcpyHostToDevice, s.stream()));
+    if (which == 0)
+      f->del_bits = dev;
+    else
+      f->filter_bits = dev;
+  }
+  return 0;
+}
+
+int Index::search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
+                         int64_t* out_ids_dev, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  if (k <= 0 || k > 4096) {
+    set_last_error("topK must be in [1, 4096]");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  Scratch s(st);
+  const float* xq = x_dev;
+  int64_t ldq = ldx;
+  if ((ldx & 3) || (reinterpret_cast<uintptr_t>(x_dev) & 15)) {  // re-pack into 16-byte aligned rows
+    float* buf = s.alloc_n<float>((size_t)nq * dpad_);
+    if (!buf) return -1;
+    GB_CUDA(cudaMemsetAsync(buf, 0, (size_t)nq * dpad_ * 4, st));
+    GB_CUDA(cudaMemcpy2DAsync(buf, (size_t)dpad_ * 4, x_dev, (size_t)ldx * 4, (size_t)d_ * 4, nq,
+                              cudaMemcpyDeviceToDevice, st));
+    xq = buf;
+    ldq = dpad_;
+  } else if (ldx < dpad_) {
+    set_last_error("query row stride smaller than padded dimension");
+    return -1;
+  }
+  FilterArgs f;
+  if (upload_bitmaps(ctx, &f, s)) return -1;
+  int metric = ctx.params.metric >= 0 ? ctx.params.metric : mp_.metric;
+  GB_ALLOC(keys, unsigned long long, (size_t)nq * k, s);
+  // the device kernels take a dense nq x dpad block
+  if (ldq != dpad_) {
+    float* buf = s.alloc_n<float>((size_t)nq * dpad_);
+    if (!buf) return -1;
+    GB_CUDA(cudaMemcpy2DAsync(buf, (size_t)dpad_ * 4, xq, (size_t)ldq * 4, (size_t)dpad_ * 4, nq,
+                              cudaMemcpyDeviceToDevice, st));
+    xq = buf;
+  }
+  int rc;
+  if (ctx.params.brute_force || !trained_) {
+    // brute-force fallback of the IVF models (gamma_index_ivfflat.cc:541-550, ivfpq.cc:561-570)
+    rc = flat_search_dev(ctx, f, metric, nq, xq, k, store_->size(), keys, s);
+  } else {
+    rc = search_keys_dev(ctx, f, metric, nq, xq, k, keys, s);
+  }
+  if (rc) return rc;
+  GB_CUDA(launch_decode_keys(keys, k, nq, k, metric, out_dis_dev, out_ids_dev, 0, st));
+  return 0;
+}
+
+int Index::search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids) {
+  if (nq <= 0) return 0;
+  cudaSetDevice(device_);
+  cudaStream_t st = thread_stream(device_);
+  float* dq = nullptr;
+  float* dd = nullptr;
+  int64_t* di = nullptr;
+  int rc = -1;
+  do {
+    if (cudaMallocAsync(&dq, (size_t)nq * dpad_ * 4, st) != cudaSuccess) break;
+    if (cudaMallocAsync(&dd, (size_t)nq * k * 4, st) != cudaSuccess) break;
+    if (cudaMallocAsync(&di, (size_t)nq * k * 8, st) != cudaSuccess) break;
+    if (d_ != dpad_ && cudaMemsetAsync(dq, 0, (size_t)nq * dpad_ * 4, st) != cudaSuccess) break;
+    if (cudaMemcpy2DAsync(dq, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, nq, cudaMemcpyHostToDevice, st) !=
+        cudaSuccess)
+      break;
+    rc = search_device(ctx, nq, dq, dpad_, k, dd, di, st);
+    if (rc) break;
+    rc = -1;
+    if (cudaMemcpyAsync(out_dis, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    if (cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) break;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      set_last_error(std::string("search: ") + cudaGetErrorString(e));
+      break;
+    }
+    rc = 0;
+  } while (0);
+  if (rc == -1 && !*last_error()) set_last_error(std::string("search: ") + cudaGetErrorString(cudaGetLastError()));
+  if (dq) cudaFreeAsync(dq, st);
+  if (dd) cudaFreeAsync(dd, st);
+  if (di) cudaFreeAsync(di, st);
+  return rc;
+}
+
+// GammaFLATIndex::Search (gamma_index_flat.cc:130-370): every stored row, filters before top-k.
+int Index::flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                           int64_t nrows, unsigned long long* out_keys, Scratch& s) {
+  (void)ctx;
+  cudaStream_t st = s.stream();
+  if (nrows <= 0) return launch_fill_u64(out_keys, (int64_t)nq * k, kKeySentinel, st) == cudaSuccess ? 0 : -1;
+  const int64_t CC = std::min<int64_t>(131072, store_->seg_rows());  // DB rows per distance block
+  struct Chunk {
+    const float* base;
+    int64_t id0;
+    int cnt;
+  };
+  std::vector<Chunk> chunks;
+  for (int64_t r = 0; r < nrows;) {
+    int64_t si = r >> store_->seg_shift(), off = r & (store_->seg_rows() - 1);
+    int64_t cnt = std::min<int64_t>(std::min(nrows - r, store_->seg_rows() - off), CC);
+    chunks.push_back({store_->seg((int)si) + off * dpad_, r, (int)cnt});
+    r += cnt;
+  }
+  const int nch = (int)chunks.size();
+  int64_t ldo = round_up(std::min<int64_t>(CC, nrows), 4);
+  int QB = (int)std::max<int64_t>(1, std::min<int64_t>(nq, ((int64_t)1 << 28) / ldo));  // <= 1 GiB of scores
+  GB_ALLOC(scores, float, (size_t)QB * ldo, s);
+  unsigned long long* partial = out_keys;
+  if (nch > 1) {
+    partial = s.alloc_n<unsigned long long>((size_t)nq * nch * k);
+    if (!partial) return -1;
+  }
+  scan_timer_begin(st);
+  for (int q0 = 0; q0 < nq; q0 += QB) {
+    int qb = std::min(QB, nq - q0);
+    for (int c = 0; c < nch; c++) {
+      GB_CUDA(launch_dist_matrix(xq + (int64_t)q0 * dpad_, dpad_, qb, chunks[c].base, dpad_, chunks[c].cnt, dpad_,
+                                 metric, scores, ldo, st));
+      GB_CUDA(launch_select_scores(scores, ldo, qb, chunks[c].cnt, chunks[c].id0, k, metric, f,
+                                   partial + ((int64_t)q0 * nch + c) * k, (int64_t)nch * k, st));
+    }
+  }
+  if (nch > 1) GB_CUDA(launch_select_keys(partial, (int64_t)nch * k, nq, nch * k, k, out_keys, k, st));
+  scan_timer_end(st);
+  return 0;
+}
+
+int FlatIndex::search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                               unsigned long long* out_keys, Scratch& s) {
+  return flat_search_dev(ctx, f, metric, nq, xq, k, store_->size(), out_keys, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// k-means (faiss::Clustering restated).  Assign runs on device (K2 kernel with
+// fused argmin), the centroid update is a deterministic segmented mean on device, the control
+// logic (seeded permutations, empty-cluster split) runs on host.
+static void rand_perm_mt(std::vector<int32_t>& perm, int64_t n, int64_t seed) {
+  perm.resize(n);
+  for (int64_t i = 0; i < n; i++) perm[i] = (int32_t)i;
+  std::mt19937 mt((unsigned)seed);
+  for (int64_t i = 0; i + 1 < n; i++) {
+    int64_t i2 = i + (int64_t)(mt() % (uint32_t)(n - i));
+    std::swap(perm[i], perm[i2]);
+  }
+}
+
+int kmeans_device(const float* x_in, int64_t ldx_in, int64_t n_in, int d, int k, const KMeansParams& kp,
+                  float* centroids, int64_t ldc, cudaStream_t st, std::vector<float>* obj) {
+  if (n_in < k) {
+    set_last_error("kmeans: fewer training points than centroids");
+    return -1;
+  }
+  if (n_in > INT32_MAX) {
+    set_last_error("kmeans: too many points");
+    return -1;
+  }
+  Scratch s(st);
+  const int dpad = (int)round_up(d, 4);
+  const float* x = x_in;
+  int64_t ldx = ldx_in, n = n_in;
+  std::vector<int32_t> perm;
+  if (kp.max_points_per_centroid > 0 && n_in > (int64_t)k * kp.max_points_per_centroid) {
+    n = (int64_t)k * kp.max_points_per_centroid;
+    rand_perm_mt(perm, n_in, kp.seed);
+    GB_ALLOC(d_idx, int32_t, n, s);
+    GB_CUDA(cudaMemcpyAsync(d_idx, perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GB_ALLOC(xs, float, (size_t)n * dpad, s);
+    GB_CUDA(launch_gather_rows(x_in, ldx_in, d_idx, n, d, xs, dpad, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    x = xs;
+    ldx = dpad;
+  }
+  // initial centroids = first k entries of a seeded permutation
+  rand_perm_mt(perm, n, kp.seed + 1);
+  GB_ALLOC(d_perm, int32_t, n, s);
+  GB_ALLOC(d_off, int32_t, k + 1, s);
+  GB_CUDA(cudaMemcpyAsync(d_perm, perm.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(launch_gather_rows(x, ldx, d_perm, k, d, centroids, ldc, st));
+  if (kp.spherical) GB_CUDA(launch_normalize_rows(centroids, ldc, k, d, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+
+  GB_ALLOC(best, unsigned long long, n, s);
+  std::vector<unsigned long long> h_best(n);
+  std::vector<int32_t> h_off(k + 1), h_perm(n), cursor(k);
+  std::vector<float> hassign(k), h_cent;
+  const int metric = kp.spherical ? kMetricIP : kMetricL2;  // gamma's quantizer is IndexFlat(d, metric)
+  for (int it = 0; it < kp.niter; it++) {
+    GB_CUDA(launch_fill_u64(best, n, kKeySentinel, st));
+    GB_CUDA(launch_dist_argmin(x, ldx, (int)n, centroids, ldc, k, dpad, metric, best, 0, st));
+    GB_CUDA(cudaMemcpyAsync(h_best.data(), best, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    // stable counting sort of the points by label (point order inside a cluster = faiss's sum order)
+    std::fill(h_off.begin(), h_off.end(), 0);
+    double o = 0;
+    for (int64_t i = 0; i < n; i++) {
+      if ((uint32_t)h_best[i] >= (uint32_t)k) h_best[i] &= 0xFFFFFFFF00000000ull;  // NaN rows -> cluster 0
+      h_off[(uint32_t)h_best[i] + 1]++;
+      if (obj) o += ord2score((uint32_t)(h_best[i] >> 32), metric);
+    }
+    if (obj) obj->push_back((float)o);
+    for (int c = 0; c < k; c++) {
+      hassign[c] = (float)h_off[c + 1];
+      h_off[c + 1] += h_off[c];
+      cursor[c] = h_off[c];
+    }
+    for (int64_t i = 0; i < n; i++) h_perm[cursor[(uint32_t)h_best[i]]++] = (int32_t)i;
+    GB_CUDA(cudaMemcpyAsync(d_perm, h_perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_off, h_off.data(), (size_t)(k + 1) * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(launch_segment_mean(x, ldx, d, d_perm, d_off, k, centroids, ldc, st));
+    // split_clusters: re-seed empty clusters from big ones (EPS = 1/1024, rng(1234))
+    bool any_empty = false;
+    for (int c = 0; c < k; c++) any_empty |= (hassign[c] == 0);
+    if (any_empty) {
+      h_cent.resize((size_t)k * ldc);
+      GB_CUDA(cudaMemcpyAsync(h_cent.data(), centroids, (size_t)k * ldc * 4, cudaMemcpyDeviceToHost, st));
+      GB_CUDA(cudaStreamSynchronize(st));
+      const float EPS = 1.0f / 1024.0f;
+      std::mt19937 rng(1234u);
+      for (int ci = 0; ci < k; ci++) {
+        if (hassign[ci] != 0) continue;
+        int cj;
+        for (cj = 0;; cj = (cj + 1) % k) {
+          float p = (hassign[cj] - 1.0f) / (float)(n - k);
+          float r = (float)rng() / (float)4294967295u;
+          if (r < p) break;
+        }
+        float* a = h_cent.data() + (size_t)ci * ldc;
+        float* b = h_cent.data() + (size_t)cj * ldc;
+        memcpy(a, b, sizeof(float) * d);
+        for (int j = 0; j < d; j++) {
+          if (j % 2 == 0) {
+            a[j] *= 1 + EPS;
+            b[j] *= 1 - EPS;
+          } else {
+            a[j] *= 1 - EPS;
+            b[j] *= 1 + EPS;
+          }
+        }
+        hassign[ci] = hassign[cj] / 2;
+        hassign[cj] -= hassign[ci];
+      }
+      GB_CUDA(cudaMemcpyAsync(centroids, h_cent.data(), (size_t)k * ldc * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (kp.spherical) GB_CUDA(launch_normalize_rows(centroids, ldc, k, d, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+IVFFlatIndex::IVFFlatIndex(int d, const ModelParams& mp, int device, int seg_shift, const std::string& type)
+    : Index(type, d, mp, device, seg_shift), nlist_(mp.ncentroids) {
+  cudaMalloc(&d_centroids_, (size_t)nlist_ * dpad_ * 4);
+  cudaMemset(d_centroids_, 0, (size_t)nlist_ * dpad_ * 4);
+}
+IVFFlatIndex::~IVFFlatIndex() { cudaFree(d_centroids_); }
+
+int IVFFlatIndex::training_threshold() const {
+  // gamma_index_ivfflat.cc:239: default nlist * 200 ; Indexing() clamps to [39, 256] * nlist (:350-375)
+  int64_t t = mp_.training_threshold ? mp_.training_threshold : (int64_t)nlist_ * 200;
+  if (t < nlist_)
+    t = (int64_t)nlist_ * 39;
+  else if (t > (int64_t)nlist_ * 256)
+    t = (int64_t)nlist_ * 256;
+  return (int)t;
+}
+int64_t IVFFlatIndex::index_mem_bytes() const {
+  return (int64_t)nlist_ * dpad_ * 4 + (lists_ ? lists_->mem_bytes() : 0);
+}
+int IVFFlatIndex::set_centroids(const float* host, int nlist) {
+  if (nlist != nlist_) {
+    set_last_error("set_centroids: nlist mismatch");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  GB_CUDA(cudaMemset(d_centroids_, 0, (size_t)nlist_ * dpad_ * 4));
+  GB_CUDA(cudaMemcpy2D(d_centroids_, (size_t)dpad_ * 4, host, (size_t)d_ * 4, (size_t)d_ * 4, nlist_,
+                       cudaMemcpyHostToDevice));
+  if (!lists_) lists_.reset(new IvfLists(nlist_, code_bytes()));
+  trained_ = true;
+  return 0;
+}
+int IVFFlatIndex::get_centroids(float* host) const {
+  cudaSetDevice(device_);
+  GB_CUDA(cudaMemcpy2D(host, (size_t)d_ * 4, d_centroids_, (size_t)dpad_ * 4, (size_t)d_ * 4, nlist_,
+                       cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// GammaIVFFlatIndex::Indexing (gamma_index_ivfflat.cc:342-411): train on the FIRST num vectors.
+int IVFFlatIndex::train() {
+  if (trained_) return 0;
+  cudaSetDevice(device_);
+  int64_t num = training_threshold();
+  if (num > store_->size()) {
+    set_last_error("vector total count less than training_threshold");
+    return -1;
+  }
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  cudaStream_t st = build_stream_;
+  Scratch s(st);
+  const float* xt = store_->contiguous(num, s);
+  if (!xt) return -1;
+  KMeansParams kp;
+  const bool is_pq = (type_ == "IVFPQ");
+  kp.niter = is_pq ? 10 : 25;                              // gamma_index_ivfpq.cc:188
+  kp.spherical = is_pq && mp_.metric == kMetricIP;          // gamma_index_ivfpq.cc:189-191
+  if (kmeans_device(xt, dpad_, num, d_, nlist_, kp, d_centroids_, dpad_, st, nullptr)) return -1;
+  if (train_extra(xt, num, s)) return -1;
+  GB_CUDA(cudaStreamSynchronize(st));
+  if (!lists_) lists_.reset(new IvfLists(nlist_, code_bytes()));
+  trained_ = true;
+  return 0;
+}
+
+int IVFFlatIndex::assign_dev(const float* x, int64_t ldx, int64_t n, int32_t* out, Scratch& s) {
+  cudaStream_t st = s.stream();
+  GB_ALLOC(best, unsigned long long, n, s);
+  GB_CUDA(launch_fill_u64(best, n, kKeySentinel, st));
+  GB_CUDA(launch_dist_argmin(x, ldx, (int)n, d_centroids_, dpad_, nlist_, dpad_, mp_.metric, best, 0, st));
+  GB_CUDA(launch_split_keys(best, n, mp_.metric, nullptr, out, st));
+  return 0;
+}
+
+int IVFFlatIndex::append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
+                               const int32_t* d_assign, Scratch& s) {
+  (void)d_assign;
+  GB_CUDA(launch_ivf_append_vecs(x, dpad_, n, dpad_, d_list, d_pos, reinterpret_cast<float* const*>(lists_->d_data()),
+                                 lists_->d_ids(), vid0, s.stream()));
+  return 0;
+}
+
+// GammaIVFFlatIndex::Add (gamma_index_ivfflat.cc:413-474) driven like
+// VectorManager::AddRTVecsToIndex (vector_manager.cc:572-702), in large device batches.
+int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
+  if (!trained_) return 0;
+  cudaSetDevice(device_);
+  cudaStream_t st = build_stream_;
+  const int64_t BATCH = 1 << 20;
+  while (indexed_count_ < store_->size()) {
+    int64_t vid0 = indexed_count_;
+    int64_t si = vid0 >> store_->seg_shift(), off = vid0 & (store_->seg_rows() - 1);
+    int64_t n = std::min<int64_t>(std::min(store_->size() - vid0, store_->seg_rows() - off), BATCH);
+    const float* x = store_->seg((int)si) + off * dpad_;
+    Scratch s(st);
+    GB_ALLOC(d_assign, int32_t, n, s);
+    if (assign_dev(x, dpad_, n, d_assign, s)) return -1;
+    std::vector<int32_t> h_list(n), h_pos(n);
+    GB_CUDA(cudaMemcpyAsync(h_list.data(), d_assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> add(nlist_, 0);
+    const std::vector<int>& lens = lists_->lens();
+    for (int64_t i = 0; i < n; i++) {
+      int64_t vid = vid0 + i;
+      int l = h_list[i];
+      if (del_bitmap && ((del_bitmap[vid >> 3] >> (vid & 7)) & 1)) {  // ivfflat.cc:436: deleted before indexing
+        h_list[i] = -1;
+        h_pos[i] = 0;
+        continue;
+      }
+      if (l < 0 || l >= nlist_) l = (int)(vid % nlist_);  // ivfflat.cc:443-446
+      h_list[i] = l;
+      h_pos[i] = lens[l] + add[l]++;  // insertion (vid) order inside the list
+    }
+    GB_ALLOC(d_list, int32_t, n, s);
+    GB_ALLOC(d_pos, int32_t, n, s);
+    GB_CUDA(cudaMemcpyAsync(d_list, h_list.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(d_pos, h_pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    {
+      std::unique_lock<std::shared_mutex> lk(mu_);
+      if (lists_->reserve(add, st)) return -1;
+      if (append_batch(x, n, vid0, d_list, d_pos, d_assign, s)) return -1;
+      if (lists_->commit(add, st)) return -1;
+      GB_CUDA(cudaStreamSynchronize(st));
+      indexed_count_ += n;
+    }
+  }
+  return 0;
+}
+
+int IVFFlatIndex::resolve_nprobe(const SearchContext& ctx) const {
+  int nprobe = mp_.nprobe;
+  if (ctx.params.nprobe > 0 && ctx.params.nprobe <= nlist_) nprobe = ctx.params.nprobe;  // ivfflat.cc:551-559
+  if (nprobe > nlist_) nprobe = nlist_;
+  if (nprobe > 4096) nprobe = 4096;
+  return nprobe;
+}
+
+// quantizer->search (gamma_index_ivfflat.cc:568 / gamma_index_ivfpq.cc:595)
+int IVFFlatIndex::coarse_dev(int nq, const float* xq, int nprobe, int metric, int32_t* probe_ids, float* coarse_dis,
+                             Scratch& s) {
+  cudaStream_t st = s.stream();
+  int64_t ldo = round_up(nlist_, 4);
+  GB_ALLOC(scores, float, (size_t)nq * ldo, s);
+  GB_ALLOC(keys, unsigned long long, (size_t)nq * nprobe, s);
+  GB_CUDA(launch_dist_matrix(xq, dpad_, nq, d_centroids_, dpad_, nlist_, dpad_, metric, scores, ldo, st));
+  FilterArgs nf{nullptr, nullptr, -FLT_MAX, FLT_MAX};
+  GB_CUDA(launch_select_scores(scores, ldo, nq, nlist_, 0, nprobe, metric, nf, keys, nprobe, st));
+  GB_CUDA(launch_split_keys(keys, (int64_t)nq * nprobe, metric, coarse_dis, probe_ids, st));
+  return 0;
+}
+
+int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                           const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
+                           Scratch& s) {
+  (void)ctx;
+  (void)coarse_dis;
+  cudaStream_t st = s.stream();
+  int nparts = ivfflat_scan_nparts(nprobe, lists_->max_len());
+  GB_ALLOC(partial, unsigned long long, (size_t)nq * nparts * k, s);
+  scan_timer_begin(st);
+  GB_CUDA(launch_ivfflat_scan(xq, dpad_, nq, dpad_, probe_ids, nprobe, lists_->directory(), lists_->max_len(), k, metric,
+                              f, partial, nullptr, st));
+  scan_timer_end(st);
+  GB_CUDA(launch_select_keys(partial, (int64_t)nparts * k, nq, nparts * k, k, out_keys, k, st));
+  return 0;
+}
+
+// GammaIVFFlatIndex::Search (gamma_index_ivfflat.cc:524-577)
+int IVFFlatIndex::search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq,
+                                  int k, unsigned long long* out_keys, Scratch& s) {
+  const int nprobe = resolve_nprobe(ctx);
+  const int QB = 16384;
+  for (int q0 = 0; q0 < nq; q0 += QB) {
+    int qb = std::min(QB, nq - q0);
+    Scratch sb(s.stream());
+    GB_ALLOC(probe_ids, int32_t, (size_t)qb * nprobe, sb);
+    GB_ALLOC(coarse_dis, float, (size_t)qb * nprobe, sb);
+    if (coarse_dev(qb, xq + (int64_t)q0 * dpad_, nprobe, metric, probe_ids, coarse_dis, sb)) return -1;
+    if (scan_dev(ctx, f, metric, qb, xq + (int64_t)q0 * dpad_, k, probe_ids, coarse_dis, nprobe,
+                 out_keys + (int64_t)q0 * k, sb))
+      return -1;
+  }
+  return 0;
+}
+
+int IVFFlatIndex::coarse_search_host(int nq, const float* x, int nprobe, float* out_dis, int64_t* out_ids) {
+  cudaSetDevice(device_);
+  cudaStream_t st = thread_stream(device_);
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  Scratch s(st);
+  GB_ALLOC(dq, float, (size_t)nq * dpad_, s);
+  GB_CUDA(cudaMemsetAsync(dq, 0, (size_t)nq * dpad_ * 4, st));
+  GB_CUDA(cudaMemcpy2DAsync(dq, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, nq, cudaMemcpyHostToDevice, st));
+  GB_ALLOC(ids, int32_t, (size_t)nq * nprobe, s);
+  GB_ALLOC(dis, float, (size_t)nq * nprobe, s);
+  if (coarse_dev(nq, dq, nprobe, mp_.metric, ids, dis, s)) return -1;
+  std::vector<int32_t> h((size_t)nq * nprobe);
+  GB_CUDA(cudaMemcpyAsync(h.data(), ids, h.size() * 4, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaMemcpyAsync(out_dis, dis, h.size() * 4, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < h.size(); i++) out_ids[i] = h[i];
+  return 0;
+}
+
+int IVFFlatIndex::search_preassigned_host(const SearchContext& ctx, int nq, const float* x, int k, const int64_t* keys,
+                                          const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids) {
+  if (!trained_ || !lists_) {
+    set_last_error("index not trained");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  cudaStream_t st = thread_stream(device_);
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  Scratch s(st);
+  GB_ALLOC(dq, float, (size_t)nq * dpad_, s);
+  GB_CUDA(cudaMemsetAsync(dq, 0, (size_t)nq * dpad_ * 4, st));
+  GB_CUDA(cudaMemcpy2DAsync(dq, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, nq, cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> h((size_t)nq * nprobe);
+  for (size_t i = 0; i < h.size(); i++) h[i] = (int32_t)keys[i];
+  GB_ALLOC(ids, int32_t, h.size(), s);
+  GB_ALLOC(dis, float, h.size(), s);
+  GB_CUDA(cudaMemcpyAsync(ids, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(dis, coarse_dis, h.size() * 4, cudaMemcpyHostToDevice, st));
+  FilterArgs f;
+  if (upload_bitmaps(ctx, &f, s)) return -1;
+  int metric = ctx.params.metric >= 0 ? ctx.params.metric : mp_.metric;
+  GB_ALLOC(okeys, unsigned long long, (size_t)nq * k, s);
+  if (scan_dev(ctx, f, metric, nq, dq, k, ids, dis, nprobe, okeys, s)) return -1;
+  GB_ALLOC(dd, float, (size_t)nq * k, s);
+  GB_ALLOC(di, int64_t, (size_t)nq * k, s);
+  GB_CUDA(launch_decode_keys(okeys, k, nq, k, metric, dd, di, 0, st));
+  GB_CUDA(cudaMemcpyAsync(out_dis, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+IVFPQIndex::IVFPQIndex(int d, const ModelParams& mp, int device, int seg_shift)
+    : IVFFlatIndex(d, mp, device, seg_shift, "IVFPQ") {
+  M_ = mp.nsubvector > 0 ? mp.nsubvector : d / 2;  // gamma_index_ivfpq.cc:122-124
+  if (M_ < 1) M_ = 1;
+  dsub_ = d / M_;
+  cudaMalloc(&d_pq_, (size_t)M_ * 256 * dsub_ * 4);
+  cudaMemset(d_pq_, 0, (size_t)M_ * 256 * dsub_ * 4);
+}
+IVFPQIndex::~IVFPQIndex() {
+  cudaFree(d_pq_);
+  cudaFree(d_table_);
+}
+int IVFPQIndex::training_threshold() const {
+  // gamma_index_ivfpq.cc:139-144: default max(nlist*200, 256); Indexing() clamps like IVFFLAT (:304-329)
+  int64_t t = mp_.training_threshold ? mp_.training_threshold : std::max<int64_t>((int64_t)nlist_ * 200, 256);
+  if (t < nlist_)
+    t = (int64_t)nlist_ * 39;
+  else if (t > (int64_t)nlist_ * 256)
+    t = (int64_t)nlist_ * 256;
+  return (int)t;
+}
+int64_t IVFPQIndex::index_mem_bytes() const {
+  return IVFFlatIndex::index_mem_bytes() + (int64_t)M_ * 256 * dsub_ * 4 +
+         (d_table_ ? (int64_t)nlist_ * M_ * 256 * 4 : 0);
+}
+int IVFPQIndex::rebuild_table(cudaStream_t st) {
+  if (mp_.metric != kMetricL2) return 0;  // IP: tab = ip table, dis0 = <x, centroid>
+  if (!d_table_) GB_CUDA(cudaMalloc(&d_table_, (size_t)nlist_ * M_ * 256 * 4));
+  GB_CUDA(launch_pq_precompute_table(d_centroids_, dpad_, nlist_, d_pq_, M_, dsub_, d_table_, st));
+  return 0;
+}
+int IVFPQIndex::set_pq_centroids(const float* host) {
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  GB_CUDA(cudaMemcpy(d_pq_, host, (size_t)M_ * 256 * dsub_ * 4, cudaMemcpyHostToDevice));
+  if (rebuild_table(build_stream_)) return -1;
+  GB_CUDA(cudaStreamSynchronize(build_stream_));
+  return 0;
+}
+int IVFPQIndex::get_pq_centroids(float* host) const {
+  cudaSetDevice(device_);
+  GB_CUDA(cudaMemcpy(host, d_pq_, (size_t)M_ * 256 * dsub_ * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int IVFPQIndex::get_precomputed_table(float* host) const {
+  if (!d_table_) {
+    set_last_error("no precomputed table (IP metric or untrained)");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  GB_CUDA(cudaMemcpy(host, d_table_, (size_t)nlist_ * M_ * 256 * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// faiss IndexIVFPQ::train_residual restated: residuals of (a subsample of <= 256*ksub) training
+// vectors -> ProductQuantizer::train = M independent 256-means on the dsub-wide slices.
+int IVFPQIndex::train_extra(const float* xtrain, int64_t n, Scratch& s) {
+  cudaStream_t st = s.stream();
+  if (d_ % M_ != 0) {
+    set_last_error("dimension not divisible by nsubvector");
+    return -1;
+  }
+  int64_t npq = std::min<int64_t>(n, 256 * 256);
+  const float* xs = xtrain;
+  if (npq < n) {
+    std::vector<int32_t> perm;
+    rand_perm_mt(perm, n, 1234);
+    GB_ALLOC(d_idx, int32_t, npq, s);
+    GB_CUDA(cudaMemcpyAsync(d_idx, perm.data(), (size_t)npq * 4, cudaMemcpyHostToDevice, st));
+    GB_ALLOC(sub, float, (size_t)npq * dpad_, s);
+    GB_CUDA(launch_gather_rows(xtrain, dpad_, d_idx, npq, dpad_, sub, dpad_, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    xs = sub;
+  }
+  GB_ALLOC(assign, int32_t, npq, s);
+  if (assign_dev(xs, dpad_, npq, assign, s)) return -1;
+  GB_ALLOC(resid, float, (size_t)npq * dpad_, s);
+  GB_CUDA(launch_residual(xs, dpad_, npq, d_, d_centroids_, dpad_, assign, resid, dpad_, st));
+  const int dsp = (int)round_up(dsub_, 4);
+  GB_ALLOC(slice, float, (size_t)npq * dsp, s);
+  GB_ALLOC(cent, float, (size_t)256 * dsp, s);
+  KMeansParams kp;  // ClusteringParameters defaults: niter 25, seed 1234, max 256 points per centroid
+  for (int m = 0; m < M_; m++) {
+    GB_CUDA(launch_slice_cols(resid, dpad_, npq, m * dsub_, dsub_, slice, dsp, st));
+    if (kmeans_device(slice, dsp, npq, dsub_, 256, kp, cent, dsp, st, nullptr)) return -1;
+    GB_CUDA(cudaMemcpy2DAsync(d_pq_ + (size_t)m * 256 * dsub_, (size_t)dsub_ * 4, cent, (size_t)dsp * 4,
+                              (size_t)dsub_ * 4, 256, cudaMemcpyDeviceToDevice, st));
+  }
+  return rebuild_table(st);
+}
+
+// GammaIVFPQIndex::Add (gamma_index_ivfpq.cc:455-540): residual -> pq.compute_codes -> AddKeys
+int IVFPQIndex::append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
+                             const int32_t* d_assign, Scratch& s) {
+  cudaStream_t st = s.stream();
+  GB_ALLOC(codes, uint8_t, (size_t)n * M_, s);
+  // residual is taken w.r.t. the assigned list (d_list == d_assign except for skipped rows)
+  (void)d_assign;
+  GB_CUDA(launch_pq_encode(x, dpad_, n, d_centroids_, dpad_, d_list, d_pq_, M_, dsub_, codes, st));
+  GB_CUDA(launch_ivf_append_codes(codes, n, M_, d_list, d_pos, reinterpret_cast<uint8_t* const*>(lists_->d_data()),
+                                  lists_->d_ids(), vid0, st));
+  return 0;
+}
+
+int IVFPQIndex::encode_host(const float* x, int64_t n, const int64_t* assign, uint8_t* codes_out) {
+  cudaSetDevice(device_);
+  cudaStream_t st = thread_stream(device_);
+  Scratch s(st);
+  GB_ALLOC(dx, float, (size_t)n * dpad_, s);
+  GB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * dpad_ * 4, st));
+  GB_CUDA(cudaMemcpy2DAsync(dx, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, n, cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> h(n);
+  for (int64_t i = 0; i < n; i++) h[i] = (int32_t)assign[i];
+  GB_ALLOC(da, int32_t, n, s);
+  GB_CUDA(cudaMemcpyAsync(da, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  GB_ALLOC(codes, uint8_t, (size_t)n * M_, s);
+  GB_CUDA(launch_pq_encode(dx, dpad_, n, d_centroids_, dpad_, da, d_pq_, M_, dsub_, codes, st));
+  GB_CUDA(cudaMemcpyAsync(codes_out, codes, (size_t)n * M_, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// GammaIVFPQIndex::search_preassigned (gamma_index_ivfpq.cc:730-947)
+int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                         const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
+                         Scratch& s) {
+  cudaStream_t st = s.stream();
+  if (metric != mp_.metric) {
+    set_last_error("IVFPQ: per-request metric must equal the trained metric");
+    return -1;
+  }
+  // recall_num / re-rank semantics: gamma_index_ivfpq.cc:764-770
+  const bool rerank = ctx.params.recall_num > 0;
+  int kk = k;
+  if (ctx.params.recall_num > k) kk = ctx.params.recall_num;
+  if (kk > 4096) kk = 4096;
+  GB_ALLOC(ip, float, (size_t)nq * M_ * 256, s);
+  GB_CUDA(launch_pq_ip_table(xq, dpad_, nq, d_pq_, M_, dsub_, ip, st));
+  int pg = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)nprobe * nq / (148 * 32)));
+  int ngroups = (nprobe + pg - 1) / pg;
+  GB_ALLOC(partial, unsigned long long, (size_t)nq * ngroups * kk, s);
+  scan_timer_begin(st);
+  GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, pg, lists_->directory(), M_, d_table_, kk, metric, f,
+                            partial, st));
+  scan_timer_end(st);
+  unsigned long long* adc = out_keys;
+  if (rerank || ngroups > 1) {
+    if (rerank) {
+      adc = s.alloc_n<unsigned long long>((size_t)nq * kk);
+      if (!adc) return -1;
+    }
+    GB_CUDA(launch_select_keys(partial, (int64_t)ngroups * kk, nq, ngroups * kk, kk, adc, kk, st));
+  } else {
+    GB_CUDA(cudaMemcpyAsync(out_keys, partial, (size_t)nq * kk * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  if (rerank) {
+    GB_CUDA(launch_rerank(adc, kk, nq, xq, dpad_, dpad_, store_->d_segs(), store_->seg_shift(), dpad_, k, metric, f,
+                          out_keys, st));
+  }
+  return 0;
+}
+
+int IVFPQIndex::search_preassigned_host(const SearchContext& ctx, int nq, const float* x, int k, const int64_t* keys,
+                                        const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids) {
+  return IVFFlatIndex::search_preassigned_host(ctx, nq, x, k, keys, coarse_dis, nprobe, out_dis, out_ids);
+}
+
+// ------------------------------------------------------------------------------------------
+Index* create_index(const std::string& type, int d, const ModelParams& mp, int device, int seg_shift) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    set_last_error("no CUDA device " + std::to_string(device) + " (this engine has no CPU path)");
+    return nullptr;
+  }
+  if (d <= 0) {
+    set_last_error("invalid dimension");
+    return nullptr;
+  }
+  if (type == "FLAT") return new FlatIndex(d, mp, device, seg_shift);
+  if (type == "IVFFLAT") {
+    if (mp.ncentroids <= 0 || mp.nprobe > mp.ncentroids) {  // gamma_index_ivfflat.cc:277-286
+      set_last_error("nprobe should be less than ncentroids");
+      return nullptr;
+    }
+    return new IVFFlatIndex(d, mp, device, seg_shift);
+  }
+  if (type == "IVFPQ") {
+    int M = mp.nsubvector > 0 ? mp.nsubvector : d / 2;
+    if (M <= 0 || d % M != 0) {  // gamma_index_ivfpq.cc:125-133
+      set_last_error("Dimension [" + std::to_string(d) + "] cannot divide by nsubvector [" + std::to_string(M) + "].");
+      return nullptr;
+    }
+    if (mp.nbits != 8) {
+      set_last_error("only nbits_per_idx = 8 is supported");
+      return nullptr;
+    }
+    if (mp.ncentroids <= 0 || mp.nprobe > mp.ncentroids) {
+      set_last_error("nprobe should be less than ncentroids");
+      return nullptr;
+    }
+    return new IVFPQIndex(d, mp, device, seg_shift);
+  }
+  set_last_error("unsupported index type " + type);
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+// Router merge (mergeSortedArrays, client.go:1530-1589) on device: per query, k-way merge keyed by
+// (score, later partition first).  Input scores are already sorted per partition.
+__global__ void merge_partitions_kernel(const float* __restrict__ dis, const int64_t* __restrict__ ids, int nparts,
+                                        int nq, int k, int metric, float* __restrict__ out_dis,
+                                        int64_t* __restrict__ out_ids) {
+  extern __shared__ unsigned long long mk[];  // [NP] keys, then [NP] payload
+  const int q = blockIdx.x;
+  const int total = nparts * k;
+  int NP = 1;
+  while (NP < total) NP <<= 1;
+  unsigned long long* pay = mk + NP;
+  for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+    unsigned long long key = kKeySentinel, pl = 0;
+    if (i < total) {
+      int p = i / k, j = i - p * k;
+      int64_t id = ids[((int64_t)p * nq + q) * k + j];
+      if (id >= 0) {
+        float s = dis[((int64_t)p * nq + q) * k + j];
+        // low word: later partition first, then rank inside the partition
+        uint32_t lo = ((uint32_t)(nparts - 1 - p) << 16) | (uint32_t)j;
+        key = make_key(score2ord(s, metric), lo);
+        pl = ((unsigned long long)p << 32) | (uint32_t)id;
+      }
+    }
+    mk[i] = key;
+    pay[i] = pl;
+  }
+  __syncthreads();
+  // bitonic sort on keys carrying the payload
+  for (int kk = 2; kk <= NP; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = mk[i], b = mk[ixj];
+          bool up = ((i & kk) == 0);
+          if ((a > b) == up) {
+            mk[i] = b;
+            mk[ixj] = a;
+            unsigned long long t = pay[i];
+            pay[i] = pay[ixj];
+            pay[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    if (i < NP && mk[i] != kKeySentinel) {
+      out_dis[(int64_t)q * k + i] = ord2score((uint32_t)(mk[i] >> 32), metric);
+      out_ids[(int64_t)q * k + i] = (int64_t)pay[i];
+    } else {
+      out_dis[(int64_t)q * k + i] = metric == kMetricL2 ? FLT_MAX : -FLT_MAX;
+      out_ids[(int64_t)q * k + i] = -1;
+    }
+  }
+}
+}  // namespace
+
+int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, int nq, int k, int metric, float* out_dis,
+                            int64_t* out_ids, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  int NP = next_pow2(nparts * k);
+  if (nparts > 65535 || k > 65535 || NP > 8192) {
+    set_last_error("merge_partitions: nparts*k too large");
+    return -1;
+  }
+  size_t smem = (size_t)NP * 16;
+  if (smem > 48 * 1024)
+    GB_CUDA(cudaFuncSetAttribute(merge_partitions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_partitions_kernel<<<nq, 256, smem, st>>>(dis, ids, nparts, nq, k, metric, out_dis, out_ids);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gb

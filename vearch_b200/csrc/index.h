@@ -1,0 +1,302 @@
+// Host side of the hot path: device-resident raw vectors, inverted lists, and the three index
+// models, mirroring the reference's IndexModel plug-in interface
+// (index/index_model.h:229-335: Init / Indexing / Add / Search, RetrievalContext,
+// RetrievalParameters) so that the engine above it (engine.cc) reads like search/engine.cc +
+// vector/vector_manager.cc.  No CPU compute path exists here: every Search/Train/Add call runs
+// CUDA kernels and fails if the device is unavailable.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace gb {
+
+void set_last_error(const std::string& msg);
+const char* last_error();
+#define GB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      ::gb::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " @" __FILE__ ":" + \
+                           std::to_string(__LINE__));                                              \
+      return -1;                                                                                   \
+    }                                                                                              \
+  } while (0)
+
+// Stream-ordered scratch allocations released when the object dies.
+class Scratch {
+ public:
+  explicit Scratch(cudaStream_t st) : st_(st) {}
+  ~Scratch();
+  void* alloc(size_t bytes);  // nullptr on failure (last_error set)
+  template <typename T>
+  T* alloc_n(size_t n) {
+    return static_cast<T*>(alloc(n * sizeof(T)));
+  }
+  cudaStream_t stream() const { return st_; }
+
+ private:
+  cudaStream_t st_;
+  std::vector<void*> ptrs_;
+};
+
+// MemoryRawVector on device (vector/memory_raw_vector.cc:152-240): append-only fp32 rows kept in
+// fixed-size HBM segments, row stride dpad (d rounded up to 4 floats, zero padded).
+class RawStore {
+ public:
+  RawStore(int d, int seg_shift);
+  ~RawStore();
+  int d() const { return d_; }
+  int dpad() const { return dpad_; }
+  int64_t size() const { return n_; }
+  int seg_shift() const { return seg_shift_; }
+  int64_t seg_rows() const { return (int64_t)1 << seg_shift_; }
+  int nsegs() const { return (int)segs_.size(); }
+  const float* seg(int i) const { return segs_[i]; }
+  const float* const* d_segs() const { return d_segs_; }
+  // rows: n x d floats (stride d) on host, or n x dpad (stride ld) on device
+  int append_host(const float* x, int64_t n, cudaStream_t st);
+  int append_device(const float* x, int64_t ld, int64_t n, cudaStream_t st);
+  int update_host(int64_t vid, const float* x, cudaStream_t st);
+  int get_host(int64_t vid, float* out) const;
+  // contiguous copy of rows [0, n) (training slab, GetVectorHeader): returns device ptr, owned by `s`
+  const float* contiguous(int64_t n, Scratch& s);
+  int64_t mem_bytes() const { return (int64_t)segs_.size() * seg_rows() * dpad_ * 4; }
+
+ private:
+  int ensure(int64_t n_total);
+  int d_, dpad_, seg_shift_;
+  int64_t n_ = 0;
+  std::vector<float*> segs_;
+  float** d_segs_ = nullptr;  // device array [kMaxSegs]
+  static constexpr int kMaxSegs = 65536;
+};
+
+// RTInvertIndex / RealTimeMemData on device (index/realtime/realtime_mem_data.{h,cc}): per-list
+// growable arrays of fixed-size codes + int64 ids (top bit = tombstone), entries in insertion
+// order, length published after the data.
+class IvfLists {
+ public:
+  IvfLists(int nlist, int code_bytes);
+  ~IvfLists();
+  int nlist() const { return nlist_; }
+  int max_len() const { return max_len_; }
+  int64_t total() const { return total_; }
+  const std::vector<int>& lens() const { return h_len_; }
+  ListDirectory directory() const;
+  // make room for add[l] more entries in every list; grows by copy (x1.5) when needed
+  int reserve(const std::vector<int>& add, cudaStream_t st);
+  // device arrays of per-list base pointers (valid after reserve)
+  void* const* d_data() const { return d_data_; }
+  int64_t* const* d_ids() const { return d_ids_; }
+  // account for appended entries and publish the new lengths (after the scatter kernel, same stream)
+  int commit(const std::vector<int>& add, cudaStream_t st);
+  // tombstone one entry (Update path, realtime_mem_data.cc:298-320)
+  int tombstone(int list, int pos, cudaStream_t st);
+  // host copies for dump / parity tests
+  int download_list(int l, std::vector<uint8_t>* codes, std::vector<int64_t>* ids) const;
+  int64_t mem_bytes() const { return bytes_; }
+
+ private:
+  void* slab_alloc(size_t bytes);
+  int nlist_, code_bytes_;
+  std::vector<void*> h_data_;
+  std::vector<int64_t*> h_ids_;
+  std::vector<int> h_len_, h_cap_;
+  void** d_data_ = nullptr;
+  int64_t** d_ids_ = nullptr;
+  int* d_len_ = nullptr;
+  int max_len_ = 0;
+  int64_t total_ = 0, bytes_ = 0;
+  std::vector<void*> slabs_;
+  char* slab_cur_ = nullptr;
+  size_t slab_left_ = 0;
+};
+
+struct ModelParams {  // index/impl/gamma_index_ivfpq.h:1031-1257, gamma_index_ivfflat.cc:40-196
+  int ncentroids = 2048;
+  int nprobe = 80;
+  int metric = kMetricIP;       // gamma default: InnerProduct
+  int nsubvector = 0;           // 0 => d/2 ... see IVFPQIndex::init (gamma_index_ivfpq.cc:122-124)
+  int nbits = 8;
+  int training_threshold = 0;   // 0 => engine default
+  int bucket_init_size = 1000;
+  int bucket_max_size = 1280000;
+};
+
+struct RetrievalParams {  // gamma_index_ivfpq.cc:233-294, gamma_index_ivfflat.cc:293-340
+  int nprobe = -1;
+  int metric = -1;  // -1 => index metric
+  int recall_num = -1;
+  int parallel_on_queries = 1;
+  bool brute_force = false;
+};
+
+struct SearchContext {  // RetrievalContext / SearchCondition (common/gamma_common_data.h:33-121)
+  const uint8_t* del_bitmap = nullptr;     // host, bit set => deleted
+  const uint8_t* filter_bitmap = nullptr;  // host, bit set => allowed (nullptr => no filter)
+  int64_t bitmap_bits = 0;
+  float min_score = -3.4028235e38f, max_score = 3.4028235e38f;
+  RetrievalParams params;
+};
+
+class Index {
+ public:
+  Index(const std::string& type, int d, const ModelParams& mp, int device, int seg_shift);
+  virtual ~Index();
+  const std::string& type() const { return type_; }
+  int d() const { return d_; }
+  int device() const { return device_; }
+  int metric() const { return mp_.metric; }
+  const ModelParams& model_params() const { return mp_; }
+  RawStore& store() { return *store_; }
+  int64_t indexed_count() const { return indexed_count_; }
+  bool trained() const { return trained_; }
+  virtual int training_threshold() const { return 0; }
+
+  // AddToStore (vector_manager.cc:455): append raw vectors, host rows n x d
+  int add_vectors(const float* x, int64_t n);
+  int add_vectors_device(const float* x, int64_t ld, int64_t n);
+  // IndexModel::Indexing(): train on the first `num` stored vectors
+  virtual int train() { trained_ = true; return 0; }
+  // VectorManager::AddRTVecsToIndex (vector_manager.cc:572-702): index all not-yet-indexed rows
+  virtual int add_pending(const uint8_t* del_bitmap) { indexed_count_ = store_->size(); return 0; }
+  // IndexModel::Search (index_model.h:296): x = nq x d floats; out = nq x k, unfilled id -1.
+  // Returns 0, -1 on error (last_error), -2 if killed.  x/out pointers are host unless *_dev.
+  int search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
+  int search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
+                    int64_t* out_ids_dev, cudaStream_t st);
+  virtual int64_t index_mem_bytes() const { return 0; }
+  // device time spent in the dominant scan kernel(s) since the last call (ms), for the bench
+  // roofline: CUDA events recorded on the launching stream around the scan launches, read here.
+  float last_scan_ms();
+  void set_time_scan(bool on) { time_scan_ = on; }
+
+ protected:
+  // GammaFLATIndex::Search (gamma_index_flat.cc:130-370) over rows [0, nrows)
+  int flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                      int64_t nrows, unsigned long long* out_keys, Scratch& s);
+  virtual int search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                              unsigned long long* out_keys, Scratch& s) = 0;
+  int upload_bitmaps(const SearchContext& ctx, FilterArgs* f, Scratch& s);
+
+  std::string type_;
+  int d_, dpad_, device_;
+  ModelParams mp_;
+  std::unique_ptr<RawStore> store_;
+  int64_t indexed_count_ = 0;
+  bool trained_ = false;
+  mutable std::shared_mutex mu_;  // searches shared, index mutation exclusive
+  cudaStream_t build_stream_ = nullptr;
+  void scan_timer_begin(cudaStream_t st);
+  void scan_timer_end(cudaStream_t st);
+  std::mutex ev_mu_;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events_;
+  bool time_scan_ = false;
+};
+
+class FlatIndex : public Index {
+ public:
+  FlatIndex(int d, const ModelParams& mp, int device, int seg_shift) : Index("FLAT", d, mp, device, seg_shift) {
+    trained_ = true;
+  }
+
+ protected:
+  int search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                      unsigned long long* out_keys, Scratch& s) override;
+};
+
+// k-means on device (faiss Clustering restated)
+struct KMeansParams {
+  int niter = 25;
+  int64_t seed = 1234;
+  bool spherical = false;
+  int max_points_per_centroid = 256;
+};
+int kmeans_device(const float* x, int64_t ldx, int64_t n, int d, int k, const KMeansParams& kp, float* centroids,
+                  int64_t ldc, cudaStream_t st, std::vector<float>* obj);
+
+class IVFFlatIndex : public Index {
+ public:
+  IVFFlatIndex(int d, const ModelParams& mp, int device, int seg_shift, const std::string& type = "IVFFLAT");
+  ~IVFFlatIndex() override;
+  int training_threshold() const override;
+  int train() override;
+  int add_pending(const uint8_t* del_bitmap) override;
+  int64_t index_mem_bytes() const override;
+  int nlist() const { return nlist_; }
+  // parity hooks: exchange index state with the oracle
+  int set_centroids(const float* host, int nlist);  // marks trained
+  int get_centroids(float* host) const;
+  IvfLists* lists() { return lists_.get(); }
+  // quantizer->search (ivfflat.cc:568): top-nprobe lists per query
+  int coarse_search_host(int nq, const float* x, int nprobe, float* out_dis, int64_t* out_ids);
+  // search_preassigned with caller-provided (keys, coarse_dis): host in/out
+  virtual int search_preassigned_host(const SearchContext& ctx, int nq, const float* x, int k, const int64_t* keys,
+                                      const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids);
+
+ protected:
+  int search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                      unsigned long long* out_keys, Scratch& s) override;
+  int coarse_dev(int nq, const float* xq, int nprobe, int metric, int32_t* probe_ids, float* coarse_dis, Scratch& s);
+  virtual int scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                       const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
+                       Scratch& s);
+  int assign_dev(const float* x, int64_t ldx, int64_t n, int32_t* assign_dev_out, Scratch& s);
+  int resolve_nprobe(const SearchContext& ctx) const;
+  virtual int code_bytes() const { return dpad_ * 4; }
+  virtual int append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
+                           const int32_t* d_assign, Scratch& s);
+  virtual int train_extra(const float* xtrain, int64_t n, Scratch& s) { (void)xtrain; (void)n; (void)s; return 0; }
+
+  int nlist_;
+  float* d_centroids_ = nullptr;  // [nlist][dpad]
+  std::unique_ptr<IvfLists> lists_;
+};
+
+class IVFPQIndex : public IVFFlatIndex {
+ public:
+  IVFPQIndex(int d, const ModelParams& mp, int device, int seg_shift);
+  ~IVFPQIndex() override;
+  int training_threshold() const override;
+  int64_t index_mem_bytes() const override;
+  int M() const { return M_; }
+  int dsub() const { return dsub_; }
+  int set_pq_centroids(const float* host);  // [M][256][dsub]; rebuilds the precomputed table
+  int get_pq_centroids(float* host) const;
+  int get_precomputed_table(float* host) const;
+  int encode_host(const float* x, int64_t n, const int64_t* assign, uint8_t* codes_out);
+  int search_preassigned_host(const SearchContext& ctx, int nq, const float* x, int k, const int64_t* keys,
+                              const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids) override;
+
+ protected:
+  int scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
+               const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
+               Scratch& s) override;
+  int code_bytes() const override { return M_; }
+  int append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
+                   const int32_t* d_assign, Scratch& s) override;
+  int train_extra(const float* xtrain, int64_t n, Scratch& s) override;
+  int rebuild_table(cudaStream_t st);
+
+  int M_, dsub_;
+  float* d_pq_ = nullptr;     // [M][256][dsub]
+  float* d_table_ = nullptr;  // [nlist][M][256] (L2 only)
+};
+
+// reflector (index/reflector.h:68-80): type name -> index object
+Index* create_index(const std::string& type, int d, const ModelParams& mp, int device, int seg_shift);
+
+// cross-partition merge (router semantics, internal/client/client.go:1530-1609) on device:
+// in: nparts x nq x k (dis, ids) sorted per partition; out: nq x k, ids = (part << 32) | local id
+int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, int nq, int k, int metric, float* out_dis,
+                            int64_t* out_ids, cudaStream_t st);
+
+}  // namespace gb

@@ -1,0 +1,102 @@
+// Host-callable launchers of the sm_100a kernels (one per row of SURVEY.md 8a).
+// Plain pointers + stream, no torch types.  All device matrices are row-major fp32 with a row
+// stride ("ld") that is a multiple of 4 floats so rows are 16-byte aligned.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gb {
+
+constexpr int kMetricIP = 0;  // DistanceComputeType::INNER_PRODUCT (gamma default, gamma_index_ivfflat.cc:55)
+constexpr int kMetricL2 = 1;
+
+struct FilterArgs {            // RetrievalContext (index/index_model.h:86-110)
+  const uint32_t* del_bits;    // bit set => docid deleted            (nullable)
+  const uint32_t* filter_bits; // bit set => docid passes the filter  (nullable = no filter)
+  float min_score, max_score;  // IsSimilarScoreValid window
+};
+
+// ---- K1/K2/K6/K8: tiled exact distance kernel ------------------------------------------
+// out[i][j] = |X_i - C_j|^2 (L2) or <X_i, C_j> (IP), i<n, j<m.  d multiple of 4.
+cudaError_t launch_dist_matrix(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                               int metric, float* out, int64_t ldo, cudaStream_t st);
+// best[i] = min over j of key(score(X_i,C_j), j + col_base) via atomicMin; caller pre-fills
+// best with 0xFF.. .  Lowest j wins ties (faiss IndexFlat::assign, "first minimum wins").
+cudaError_t launch_dist_argmin(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                               int metric, unsigned long long* best, int col_base, cudaStream_t st);
+
+// ---- K7: top-k selection / merge ----------------------------------------------------------
+// Per row r: select the k best of m candidates.  Input is either scores (fp32, vid = id_base+col)
+// or ready-made keys.  Output keys sorted ascending (sentinel padded) in out_keys[r*k..].
+cudaError_t launch_select_scores(const float* scores, int64_t ld, int nrows, int m, int64_t id_base, int k, int metric,
+                                 FilterArgs f, unsigned long long* out_keys, int64_t out_stride, cudaStream_t st);
+cudaError_t launch_select_keys(const unsigned long long* keys, int64_t ld, int nrows, int m, int k,
+                               unsigned long long* out_keys, int64_t out_stride, cudaStream_t st);
+// keys -> (score, id) in the reference's output order (heap_reorder): L2 (score, id) ascending;
+// IP score descending, larger id first among equal scores.  Sentinels -> id -1, score +-FLT_MAX.
+cudaError_t launch_decode_keys(const unsigned long long* keys, int64_t ld, int nrows, int k, int metric, float* out_dis,
+                               int64_t* out_ids, int64_t id_or /* OR-ed into valid ids */, cudaStream_t st);
+// keys -> int32 ids / float scores only (coarse quantiser output)
+cudaError_t launch_split_keys(const unsigned long long* keys, int64_t n, int metric, float* out_scores, int32_t* out_ids,
+                              cudaStream_t st);
+
+// ---- K3: IVF-Flat list scan ---------------------------------------------------------------
+struct ListDirectory {            // device-resident mirror of RTInvertIndex (T1)
+  const float* const* vecs;       // [nlist] -> len x dpad fp32 rows (codes_array_)
+  const uint8_t* const* codes;    // [nlist] -> len x M bytes (IVFPQ)
+  const int64_t* const* ids;      // [nlist] -> len int64, top bit = tombstone (idx_array_)
+  const int* len;                 // [nlist] published length
+  int nlist;
+};
+// partial[q][part][k], part = probe*nsplit + split.  One CTA per (query, probe, split).
+cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, const int32_t* probe_ids, int nprobe,
+                                ListDirectory dir, int max_list_len, int k, int metric, FilterArgs f,
+                                unsigned long long* partial, int* nparts_out, cudaStream_t st);
+int ivfflat_scan_nparts(int nprobe, int max_list_len);
+
+// ---- K4/K5: IVF-PQ look-up tables + ADC scan --------------------------------------------
+// ip[q][m][c] = <x_q|m, pq_m[c]>   (pq.compute_inner_prod_table)
+cudaError_t launch_pq_ip_table(const float* xq, int64_t ldq, int nq, const float* pq_centroids, int M, int dsub,
+                               float* ip, cudaStream_t st);
+// T[l][m][c] = |pq_m[c]|^2 + 2 <centroid_l|m, pq_m[c]>  (IndexIVFPQ::precompute_table)
+cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nlist, const float* pq_centroids, int M,
+                                       int dsub, float* T, cudaStream_t st);
+// partial[q][group][k], group = ceil(nprobe/pg) CTAs per query, each scanning pg (<= 32) probed lists.
+// coarse_dis = dis0 per (q, probe).  T nullable for IP.
+cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis,
+                              int nprobe, int pg, ListDirectory dir, int M, const float* T, int k, int metric,
+                              FilterArgs f, unsigned long long* partial, cudaStream_t st);
+// K5r exact re-rank of ADC candidates (gamma_index_ivfpq.cc:675-726)
+cudaError_t launch_rerank(const unsigned long long* cand_keys, int ncand, int nq, const float* xq, int64_t ldq, int d,
+                          const float* const* raw_segments, int seg_shift, int64_t ld_raw, int k, int metric,
+                          FilterArgs f, unsigned long long* out_keys, cudaStream_t st);
+
+// ---- K6/K8: build-side kernels ------------------------------------------------------------
+// centroids[c] = (sum of x[perm[off[c]..off[c+1])] in that order) * (1/count); empty => zeros
+cudaError_t launch_segment_mean(const float* x, int64_t ldx, int d, const int32_t* perm, const int32_t* off, int k,
+                                float* centroids, int64_t ldc, cudaStream_t st);
+// out = x - centroids[assign]
+cudaError_t launch_residual(const float* x, int64_t ldx, int64_t n, int d, const float* centroids, int64_t ldc,
+                            const int32_t* assign, float* out, int64_t ldo, cudaStream_t st);
+// codes[i][m] = argmin_c |(x_i - coarse[assign_i])|m - pq_m[c]|^2 (coarse nullable => no residual)
+cudaError_t launch_pq_encode(const float* x, int64_t ldx, int64_t n, const float* coarse, int64_t ldc,
+                             const int32_t* assign, const float* pq_centroids, int M, int dsub, uint8_t* codes,
+                             cudaStream_t st);
+// copy a column slice [col0, col0+w) of x into a dense n x ldo buffer (zero padded to ldo)
+cudaError_t launch_slice_cols(const float* x, int64_t ldx, int64_t n, int col0, int w, float* out, int64_t ldo,
+                              cudaStream_t st);
+// gather rows: out[i] = x[idx[i]]
+cudaError_t launch_gather_rows(const float* x, int64_t ldx, const int32_t* idx, int64_t n, int d, float* out,
+                               int64_t ldo, cudaStream_t st);
+// scale rows to unit L2 norm in place (spherical k-means)
+cudaError_t launch_normalize_rows(float* x, int64_t ldx, int64_t n, int d, cudaStream_t st);
+// IVF append (RTInvertIndex::AddKeys): row i -> list[i] at pos[i]
+cudaError_t launch_ivf_append_vecs(const float* x, int64_t ldx, int64_t n, int d, const int32_t* list, const int32_t* pos,
+                                   float* const* list_vecs, int64_t* const* list_ids, int64_t vid0, cudaStream_t st);
+cudaError_t launch_ivf_append_codes(const uint8_t* codes, int64_t n, int M, const int32_t* list, const int32_t* pos,
+                                    uint8_t* const* list_codes, int64_t* const* list_ids, int64_t vid0,
+                                    cudaStream_t st);
+cudaError_t launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t st);
+cudaError_t launch_pad_rows(const float* src, int64_t n, int d, float* dst, int64_t ldd, cudaStream_t st);
+
+}  // namespace gb

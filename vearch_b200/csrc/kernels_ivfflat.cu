@@ -1,0 +1,210 @@
+// K3: IVF-Flat inverted-list scan (query-major), the HBM-roofline kernel of the path.
+//
+// Replaces GammaIVFFlatIndex::search_preassigned (index/impl/gamma_index_ivfflat.cc:579-787,
+// pmode-0 loop :695-733) and GammaIVFFlatScanner::scan_codes (gamma_index_ivfflat.h:63-91):
+//   for each query, for each probed list, for each entry j:
+//     skip if ids[j] & kDelIdxMask, skip if !IsValid(vid), dis = L2sqr/IP(x, vec_j),
+//     keep if IsSimilarScoreValid(dis) and better than the current k-th best.
+//
+// One CTA per (query, probed list, list split).  The list's rows stream HBM -> shared memory
+// through a 4-stage ring of TMA 1-D bulk copies (cp.async.bulk + mbarrier complete_tx), so the
+// copy engine keeps 4 x 16 KB in flight per CTA with no register staging.  LPR lanes share one
+// row (float4 chunks, rotated start so both the row and the query reads are bank-conflict-free),
+// partial sums meet through warp shuffles, and candidates that beat the running k-th best go to
+// the CandQueue (common.cuh).  List ids are only read for candidates that beat the threshold.
+//
+// Algorithmic bytes: (4*d + 8) per scanned entry; roofline: HBM.
+#include <float.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gb {
+
+namespace {
+
+constexpr int IVF_NT = 128;
+constexpr int IVF_NST = 4;                 // pipeline stages
+constexpr int IVF_STAGE_BYTES = 16 * 1024; // target bytes per stage
+constexpr int IVF_CHUNK_ROWS = 8192;       // rows per CTA (long lists are split)
+
+struct IvfGeom {
+  int LPR, G, R, T, J, S;
+  int stage_bytes;
+};
+
+__host__ __device__ inline IvfGeom ivf_geom(int d) {
+  IvfGeom g;
+  g.S = d >> 2;
+  int lpr = 1;
+  while (lpr < 32 && g.S / (lpr * 2) >= 8) lpr <<= 1;  // aim for >= 8 float4 chunks per lane
+  g.LPR = lpr;
+  g.G = IVF_NT / lpr;
+  g.J = (g.S + lpr - 1) / lpr;
+  int row_bytes = d * 4;
+  int r = IVF_STAGE_BYTES / (g.G * row_bytes);
+  g.R = r < 1 ? 1 : r;
+  g.T = g.G * g.R;
+  g.stage_bytes = g.T * row_bytes;
+  return g;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(IVF_NT)
+    ivfflat_scan_kernel(const float* __restrict__ xq, int64_t ldq, int d, const int32_t* __restrict__ probe_ids,
+                        int nprobe, int nsplit, ListDirectory dir, IvfGeom g, int k, int KP, int SORTN, FilterArgs f,
+                        unsigned long long* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  float* qs = reinterpret_cast<float*>(smem_raw + (size_t)IVF_NST * g.stage_bytes);
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(qs + d);
+  __shared__ __align__(8) uint64_t full_bar[IVF_NST];
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_tau;
+
+  const int tid = threadIdx.x;
+  const int q = blockIdx.y;
+  const int part = blockIdx.x;
+  const int probe = part / nsplit, split = part - probe * nsplit;
+  unsigned long long* out = partial + ((int64_t)q * gridDim.x + part) * k;
+
+  const int list = probe_ids[(int64_t)q * nprobe + probe];
+  int len = 0;
+  if (list >= 0 && list < dir.nlist) len = dir.len[list];
+  const int r0 = split * IVF_CHUNK_ROWS;
+  const int r1 = min(len, r0 + IVF_CHUNK_ROWS);
+  if (r0 >= r1) {  // nothing to scan: "not enough centroids" (ivfflat.cc:653) or empty split
+    for (int i = tid; i < k; i += IVF_NT) out[i] = kKeySentinel;
+    return;
+  }
+  const float* __restrict__ lvecs = dir.vecs[list];
+  const int64_t* __restrict__ lids = dir.ids[list];
+
+  CandQueue cq{buf, &s_cnt, &s_tau, k, KP, SORTN};
+  for (int i = tid; i < d; i += IVF_NT) qs[i] = xq[(int64_t)q * ldq + i];
+  if (tid == 0) {
+    for (int s = 0; s < IVF_NST; s++) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  cq.init();  // includes __syncthreads()
+
+  const int ntiles = (r1 - r0 + g.T - 1) / g.T;
+  const int row_bytes = d * 4;
+  auto issue = [&](int t) {
+    int s = t % IVF_NST;
+    int rows = min(g.T, r1 - (r0 + t * g.T));
+    uint32_t bytes = (uint32_t)rows * row_bytes;
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_g2s(reinterpret_cast<unsigned char*>(stages) + (size_t)s * g.stage_bytes,
+             lvecs + (int64_t)(r0 + t * g.T) * d, bytes, &full_bar[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < IVF_NST && t < ntiles; t++) issue(t);
+
+  const int grp = tid / g.LPR;      // row slot inside a round
+  const int p = tid - grp * g.LPR;  // lane inside the row group
+  const float4* qs4 = reinterpret_cast<const float4*>(qs);
+
+  for (int t = 0; t < ntiles; t++) {
+    const int s = t % IVF_NST;
+    mbar_wait(&full_bar[s], (t / IVF_NST) & 1);
+    const int tile_rows = min(g.T, r1 - (r0 + t * g.T));
+    const unsigned long long tau = s_tau;
+    const uint32_t tau_hi = (uint32_t)(tau >> 32);
+    const float4* st4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(stages) + (size_t)s * g.stage_bytes);
+
+    for (int r = 0; r < g.R; r++) {
+      const int rit = r * g.G + grp;  // row in tile
+      const bool valid = rit < tile_rows;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (valid) {
+        const float4* rowp = st4 + (size_t)rit * g.S;
+        int jj = rit % g.J;  // rotated start: bank-conflict-free for S % 8 == 0
+#pragma unroll 4
+        for (int j = 0; j < g.J; j++) {
+          int c = p + g.LPR * jj;
+          if (c < g.S) {
+            float4 v = rowp[c];
+            float4 w = qs4[c];
+            if (METRIC == kMetricL2) {
+              float t0 = v.x - w.x, t1 = v.y - w.y, t2 = v.z - w.z, t3 = v.w - w.w;
+              a0 = fmaf(t0, t0, a0), a1 = fmaf(t1, t1, a1), a2 = fmaf(t2, t2, a2), a3 = fmaf(t3, t3, a3);
+            } else {
+              a0 = fmaf(v.x, w.x, a0), a1 = fmaf(v.y, w.y, a1), a2 = fmaf(v.z, w.z, a2), a3 = fmaf(v.w, w.w, a3);
+            }
+          }
+          jj = (jj + 1 == g.J) ? 0 : jj + 1;
+        }
+      }
+      float dis = (a0 + a1) + (a2 + a3);
+      for (int off = g.LPR >> 1; off > 0; off >>= 1) dis += __shfl_xor_sync(0xffffffffu, dis, off);
+
+      bool pred = valid && p == 0 && dis <= f.max_score && dis >= f.min_score;
+      unsigned long long key = kKeySentinel;
+      if (pred) {
+        uint32_t ord = score2ord<METRIC>(dis);
+        pred = ord <= tau_hi;
+        if (pred) {
+          int64_t raw = lids[r0 + t * g.T + rit];
+          pred = raw >= 0;  // top bit set => tombstone (gamma_index_ivfflat.h:72)
+          uint32_t vid = (uint32_t)raw;
+          if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
+          key = make_key(ord, vid);
+          pred = pred && key < tau;
+        }
+      }
+      cq.push_warp(pred, key);
+    }
+    __syncthreads();  // stage s fully consumed, all pushes of this tile done
+    const int c_now = s_cnt;
+    if (tid == 0 && t + IVF_NST < ntiles) issue(t + IVF_NST);
+    __syncthreads();  // everyone holds the same c_now before any warp pushes again
+    if (t + 1 < ntiles && c_now + g.T > cq.cap()) cq.flush();
+  }
+  cq.flush();
+  for (int i = tid; i < k; i += IVF_NT) out[i] = buf[i];
+}
+
+void ivf_cq_geometry(int k, int T, int* KP, int* SORTN) {
+  *KP = next_pow2(k < 16 ? 16 : k);
+  *SORTN = next_pow2(*KP + 2 * T);
+}
+
+}  // namespace
+
+int ivfflat_scan_nparts(int nprobe, int max_list_len) {
+  int nsplit = (max_list_len + IVF_CHUNK_ROWS - 1) / IVF_CHUNK_ROWS;
+  if (nsplit < 1) nsplit = 1;
+  return nprobe * nsplit;
+}
+
+cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, const int32_t* probe_ids, int nprobe,
+                                ListDirectory dir, int max_list_len, int k, int metric, FilterArgs f,
+                                unsigned long long* partial, int* nparts_out, cudaStream_t st) {
+  if (nq <= 0 || nprobe <= 0) return cudaSuccess;
+  if ((d & 3) || k <= 0 || k > 4096 || nq > 65535) return cudaErrorInvalidValue;
+  IvfGeom g = ivf_geom(d);
+  int nparts = ivfflat_scan_nparts(nprobe, max_list_len);
+  int nsplit = nparts / nprobe;
+  if (nparts_out) *nparts_out = nparts;
+  int KP, SORTN;
+  ivf_cq_geometry(k, g.T, &KP, &SORTN);
+  size_t smem = (size_t)IVF_NST * g.stage_bytes + (size_t)d * 4 + (size_t)SORTN * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  dim3 grid(nparts, nq);
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(ivfflat_scan_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivfflat_scan_kernel<kMetricL2><<<grid, IVF_NT, smem, st>>>(xq, ldq, d, probe_ids, nprobe, nsplit, dir, g, k, KP,
+                                                               SORTN, f, partial);
+  } else {
+    e = cudaFuncSetAttribute(ivfflat_scan_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivfflat_scan_kernel<kMetricIP><<<grid, IVF_NT, smem, st>>>(xq, ldq, d, probe_ids, nprobe, nsplit, dir, g, k, KP,
+                                                               SORTN, f, partial);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace gb
