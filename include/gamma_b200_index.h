@@ -27,6 +27,8 @@ typedef struct gb_index gb_index;
 
 const char *gb_last_error(void);
 int gb_device_count(void);
+/* kernels launched by this library since load (bench.py's gpu_launches evidence) */
+long long gb_launch_count(void);
 
 /* reflector().GetNewIndex(type) + IndexModel::Init(model_parameters, training_threshold)
  * (index/reflector.h:68-80, vector/vector_manager.cc:171; gamma_index_ivfflat.cc:215-291,
@@ -42,6 +44,7 @@ int gb_index_add_vectors_device(gb_index *index, int64_t n, const float *x_dev, 
 /* RawVector update in place (engine.cc:736 Update path) */
 int gb_index_update_vector(gb_index *index, int64_t vid, const float *x);
 int gb_index_get_vector(gb_index *index, int64_t vid, float *out);
+int gb_index_get_vectors(gb_index *index, int64_t start, int64_t n, float *out); /* n x d */
 
 /* IndexModel::Indexing(): train on the first training_threshold stored vectors
  * (gamma_index_ivfflat.cc:342-411, gamma_index_ivfpq.cc:296-376). */

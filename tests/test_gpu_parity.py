@@ -354,16 +354,28 @@ def test_ivfpq_shared_state_bit_exact(ivf_state, pq_state, metric):
     if metric == L2:
         T = orc.ivfpq_precompute_table(s["cent"], pqc)
         assert np.array_equal(idx.get_precomputed_table(), T)  # K4 table bit-equal
-    for k, nprobe, recall_num in [(10, 8, 0), (50, 16, 0), (10, 8, 100), (10, 8, 5)]:
+    for k, nprobe, recall_num in [(10, 8, 0), (50, 16, 0), (100, 8, 0), (10, 8, 100), (10, 8, 5)]:
         cd, keys = orc.coarse_search(s["cent"], s["xq"], nprobe, metric)
-        params = {"recall_num": recall_num} if recall_num else None
-        dg, ig = idx.search_preassigned(s["xq"], k, keys, cd, params=params)
-        do, io = orc.ivfpq_search_preassigned(off, codes, ids, s["cent"], pqc, T, s["xq"], k, keys, cd, metric,
-                                              recall_num=recall_num, raw=s["db"])
-        if metric == IP:
-            # oracle recomputes dis0 = <x, centroid> with its own summation order: integer data => same bits
-            pass
-        assert_same_results(dg, ig, do, io, bit_exact=(recall_num == 0 or True))
+        kk = max(k, recall_num)
+        # ADC stage (K4+K5): bit-equal scores, ids equal up to exact ties at the kk-th boundary
+        dc, ic = idx.search_preassigned(s["xq"], kk, keys, cd)
+        do, io = orc.ivfpq_search_preassigned(off, codes, ids, s["cent"], pqc, T, s["xq"], kk, keys, cd, metric)
+        assert_same_results(dc, ic, do, io)
+        if not recall_num:
+            continue
+        # K5r exact re-rank (ivfpq.cc:675-726): the best k of the ADC candidates by exact score.
+        # Checked against the device's own candidate set because candidates tied at the ADC
+        # boundary are scan-order dependent in the reference.
+        dg, ig = idx.search_preassigned(s["xq"], k, keys, cd, params={"recall_num": recall_num})
+        for q in range(s["xq"].shape[0]):
+            cand = ic[q][ic[q] >= 0]
+            v = s["db"][cand]
+            exact = ((s["xq"][q] - v) ** 2).sum(1) if metric == L2 else v @ s["xq"][q]
+            order = np.lexsort((cand, exact if metric == L2 else -exact))[:k]
+            assert np.array_equal(dg[q][: len(order)], exact[order].astype(np.float32))
+            for val in np.unique(exact[order][:-1]):
+                if val != exact[order][-1]:
+                    assert set(ig[q][dg[q] == val]) == set(cand[order][exact[order] == val])
     # filters
     deleted = np.random.default_rng(5).random(s["n"]) < 0.25
     delb = np.packbits(deleted, bitorder="little")

@@ -30,6 +30,7 @@ def _declare(l):
     cstr = C.c_char_p
     l.gb_last_error.restype = cstr
     l.gb_device_count.restype = i32
+    l.gb_launch_count.restype = C.c_longlong
     l.gb_index_create.restype = vp
     l.gb_index_create.argtypes = [cstr, i32, cstr, i32]
     l.gb_index_destroy.restype = None
@@ -38,6 +39,7 @@ def _declare(l):
     l.gb_index_add_vectors_device.argtypes = [vp, i64, vp, i64]
     l.gb_index_update_vector.argtypes = [vp, i64, vp]
     l.gb_index_get_vector.argtypes = [vp, i64, vp]
+    l.gb_index_get_vectors.argtypes = [vp, i64, i64, vp]
     l.gb_index_train.argtypes = [vp]
     l.gb_index_add_pending.argtypes = [vp, vp]
     for n in ("gb_index_ntotal", "gb_index_indexed_count"):

@@ -113,6 +113,19 @@ int RawStore::get_host(int64_t vid, float* out) const {
   GB_CUDA(cudaMemcpy(out, segs_[si] + off * dpad_, (size_t)d_ * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
+int RawStore::get_rows_host(int64_t start, int64_t n, float* out) const {
+  if (start < 0 || n < 0 || start + n > n_) return -1;
+  int64_t done = 0;
+  while (done < n) {
+    int64_t vid = start + done;
+    int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
+    int64_t cnt = std::min(n - done, seg_rows() - off);
+    GB_CUDA(cudaMemcpy2D(out + done * d_, (size_t)d_ * 4, segs_[si] + off * dpad_, (size_t)dpad_ * 4, (size_t)d_ * 4,
+                         (size_t)cnt, cudaMemcpyDeviceToHost));
+    done += cnt;
+  }
+  return 0;
+}
 const float* RawStore::contiguous(int64_t n, Scratch& s) {
   if (n <= seg_rows()) return segs_.empty() ? nullptr : segs_[0];
   float* buf = s.alloc_n<float>((size_t)n * dpad_);
@@ -1093,6 +1106,7 @@ int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, in
   if (smem > 48 * 1024)
     GB_CUDA(cudaFuncSetAttribute(merge_partitions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_partitions_kernel<<<nq, 256, smem, st>>>(dis, ids, nparts, nq, k, metric, out_dis, out_ids);
+  note_launch();
   GB_CUDA(cudaGetLastError());
   return 0;
 }

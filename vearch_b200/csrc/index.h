@@ -66,6 +66,7 @@ class RawStore {
   int append_device(const float* x, int64_t ld, int64_t n, cudaStream_t st);
   int update_host(int64_t vid, const float* x, cudaStream_t st);
   int get_host(int64_t vid, float* out) const;
+  int get_rows_host(int64_t start, int64_t n, float* out) const;  // n x d, stride d
   // contiguous copy of rows [0, n) (training slab, GetVectorHeader): returns device ptr, owned by `s`
   const float* contiguous(int64_t n, Scratch& s);
   int64_t mem_bytes() const { return (int64_t)segs_.size() * seg_rows() * dpad_ * 4; }

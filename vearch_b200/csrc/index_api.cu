@@ -132,6 +132,8 @@ extern "C" {
 
 const char* gb_last_error(void) { return last_error(); }
 
+long long gb_launch_count(void) { return launch_count(); }
+
 int gb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -178,6 +180,11 @@ int gb_index_get_vector(gb_index* index, int64_t vid, float* out) {
   IDX_OR_FAIL(index);
   cudaSetDevice(index->impl->device());
   return index->impl->store().get_host(vid, out);
+}
+int gb_index_get_vectors(gb_index* index, int64_t start, int64_t n, float* out) {
+  IDX_OR_FAIL(index);
+  cudaSetDevice(index->impl->device());
+  return index->impl->store().get_rows_host(start, n, out);
 }
 int gb_index_train(gb_index* index) {
   IDX_OR_FAIL(index);

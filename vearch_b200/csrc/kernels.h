@@ -10,6 +10,10 @@ namespace gb {
 constexpr int kMetricIP = 0;  // DistanceComputeType::INNER_PRODUCT (gamma default, gamma_index_ivfflat.cc:55)
 constexpr int kMetricL2 = 1;
 
+// number of kernels launched by this library so far (bench.py's gpu_launches evidence)
+void note_launch(int n = 1);
+long long launch_count();
+
 struct FilterArgs {            // RetrievalContext (index/index_model.h:86-110)
   const uint32_t* del_bits;    // bit set => docid deleted            (nullable)
   const uint32_t* filter_bits; // bit set => docid passes the filter  (nullable = no filter)

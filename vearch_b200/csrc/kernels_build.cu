@@ -128,6 +128,7 @@ cudaError_t launch_segment_mean(const float* x, int64_t ldx, int d, const int32_
                                 float* centroids, int64_t ldc, cudaStream_t st) {
   if (k <= 0) return cudaSuccess;
   segment_mean_kernel<<<k, 128, 0, st>>>(x, ldx, d, perm, off, centroids, ldc);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -135,6 +136,7 @@ cudaError_t launch_residual(const float* x, int64_t ldx, int64_t n, int d, const
                             const int32_t* assign, float* out, int64_t ldo, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   residual_kernel<<<blocks_for(n * ldo, 256), 256, 0, st>>>(x, ldx, n, d, centroids, ldc, assign, out, ldo);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -142,6 +144,7 @@ cudaError_t launch_slice_cols(const float* x, int64_t ldx, int64_t n, int col0, 
                               cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   slice_cols_kernel<<<blocks_for(n * ldo, 256), 256, 0, st>>>(x, ldx, n, col0, w, out, ldo);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -149,12 +152,14 @@ cudaError_t launch_gather_rows(const float* x, int64_t ldx, const int32_t* idx, 
                                int64_t ldo, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   gather_rows_kernel<<<blocks_for(n * ldo, 256), 256, 0, st>>>(x, ldx, idx, n, d, out, ldo);
+  note_launch();
   return cudaGetLastError();
 }
 
 cudaError_t launch_normalize_rows(float* x, int64_t ldx, int64_t n, int d, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   normalize_rows_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>(x, ldx, n, d);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -162,6 +167,7 @@ cudaError_t launch_ivf_append_vecs(const float* x, int64_t ldx, int64_t n, int d
                                    float* const* list_vecs, int64_t* const* list_ids, int64_t vid0, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   ivf_append_vecs_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>(x, ldx, n, d, list, pos, list_vecs, list_ids, vid0);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -170,6 +176,7 @@ cudaError_t launch_ivf_append_codes(const uint8_t* codes, int64_t n, int M, cons
                                     cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   ivf_append_codes_kernel<<<blocks_for(n, 256), 256, 0, st>>>(codes, n, M, list, pos, list_codes, list_ids, vid0);
+  note_launch();
   return cudaGetLastError();
 }
 

@@ -12,7 +12,13 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <atomic>
+
 namespace gb {
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
 
@@ -143,6 +149,7 @@ cudaError_t launch_tile(const float* X, int64_t ldx, int n, const float* C, int6
   dim3 grid((m + BN - 1) / BN, (n + BM - 1) / BM);
   if (grid.y > 65535) return cudaErrorInvalidValue;
   dist_tile_kernel<METRIC, EPI><<<grid, NT, 0, st>>>(X, ldx, n, C, ldc, m, d, out, ldo, best, col_base);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -184,6 +191,7 @@ cudaError_t launch_dist_argmin(const float* X, int64_t ldx, int n, const float* 
 cudaError_t launch_fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -191,6 +199,7 @@ cudaError_t launch_pad_rows(const float* src, int64_t n, int d, float* dst, int6
   int64_t total = n * ldd;
   if (total <= 0) return cudaSuccess;
   pad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, n, d, dst, ldd);
+  note_launch();
   return cudaGetLastError();
 }
 

@@ -198,11 +198,13 @@ cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, con
     if (e != cudaSuccess) return e;
     ivfflat_scan_kernel<kMetricL2><<<grid, IVF_NT, smem, st>>>(xq, ldq, d, probe_ids, nprobe, nsplit, dir, g, k, KP,
                                                                SORTN, f, partial);
+                                                               note_launch();
   } else {
     e = cudaFuncSetAttribute(ivfflat_scan_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     ivfflat_scan_kernel<kMetricIP><<<grid, IVF_NT, smem, st>>>(xq, ldq, d, probe_ids, nprobe, nsplit, dir, g, k, KP,
                                                                SORTN, f, partial);
+                                                               note_launch();
   }
   return cudaGetLastError();
 }

@@ -357,6 +357,7 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
   dim3 grid(ngroups, nq);
   ivfpq_scan_kernel<METRIC, MW><<<grid, PQ_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, pg, dir, M, T,
                                                           tile_e, k, KP, SORTN, f, partial);
+                                                          note_launch();
   return cudaGetLastError();
 }
 
@@ -388,6 +389,7 @@ cudaError_t launch_pq_ip_table(const float* xq, int64_t ldq, int nq, const float
   }
   dim3 grid(M, (nq + IPT_QB - 1) / IPT_QB);
   pq_ip_table_kernel<<<grid, KSUB, smem, st>>>(xq, ldq, nq, pq_centroids, M, dsub, ip);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -395,6 +397,7 @@ cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nli
                                        int dsub, float* T, cudaStream_t st) {
   if (nlist <= 0) return cudaSuccess;
   pq_precompute_table_kernel<<<nlist, KSUB, 0, st>>>(coarse, ldc, pq_centroids, M, dsub, T);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -423,6 +426,7 @@ cudaError_t launch_rerank(const unsigned long long* cand_keys, int ncand, int nq
   }
   rerank_kernel<<<nq, RR_NT, smem, st>>>(cand_keys, ncand, NP, xq, ldq, d, raw_segments, seg_shift, ld_raw, k, metric,
                                          f, out_keys);
+                                         note_launch();
   return cudaGetLastError();
 }
 
@@ -441,6 +445,7 @@ cudaError_t launch_pq_encode(const float* x, int64_t ldx, int64_t n, const float
       if (e != cudaSuccess) return e;                                                                            \
     }                                                                                                            \
     pq_encode_kernel<DS><<<grid, ENC_NT, smem, st>>>(x, ldx, n, coarse, ldc, assign, pq_centroids, M, dsub, codes); \
+    note_launch(); \
   }
   switch (dsub) {
     case 2: GB_ENC(2) break;

@@ -131,6 +131,7 @@ cudaError_t launch_select(const void* in, int64_t ld, int nrows, int m, int64_t 
   }
   select_rows_kernel<KEYS_IN><<<nrows, SEL_NT, smem, st>>>(in, ld, m, id_base, k, KP, SORTN, metric, f, out_keys,
                                                          out_stride);
+                                                         note_launch();
   return cudaGetLastError();
 }
 
@@ -151,6 +152,7 @@ cudaError_t launch_decode_keys(const unsigned long long* keys, int64_t ld, int n
                                int64_t* out_ids, int64_t id_or, cudaStream_t st) {
   if (nrows <= 0) return cudaSuccess;
   decode_keys_kernel<<<nrows, 128, 0, st>>>(keys, ld, k, metric, out_dis, out_ids, id_or);
+  note_launch();
   return cudaGetLastError();
 }
 
@@ -158,6 +160,7 @@ cudaError_t launch_split_keys(const unsigned long long* keys, int64_t n, int met
                               cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   split_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, metric, out_scores, out_ids);
+  note_launch();
   return cudaGetLastError();
 }
 

@@ -125,6 +125,11 @@ class GammaIndex:
         _check(_lib.lib().gb_index_get_vector(self._h, vid, _ptr(out)), "get_vector")
         return out
 
+    def get_vectors(self, start, n):
+        out = np.empty((n, self.d), np.float32)
+        _check(_lib.lib().gb_index_get_vectors(self._h, start, n, _ptr(out)), "get_vectors")
+        return out
+
     # ---- search -------------------------------------------------------------------------
     def search(self, x, k, params=None, brute_force=False, del_bitmap=None, filter_bitmap=None, min_score=-FLT_MAX,
                max_score=FLT_MAX):
