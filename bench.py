@@ -62,6 +62,9 @@ def parse_args():
     ap.add_argument("--recall-num", type=int, default=-1, help="IVF-PQ exact re-rank depth (0 = off)")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed device steps (ncu --profile-from-start off)")
+    ap.add_argument("--sweep", default="", help="nprobe:recall_num,... -> recall/QPS table on stderr, then exit")
     return ap.parse_args()
 
 
@@ -268,6 +271,24 @@ def main():
     ns = min(1000, nq)
     xs = q_host[0][:ns].numpy()
     gt_d, gt_i = idx.search(xs, 10, brute_force=True)
+    if args.sweep:
+        for item in args.sweep.split(","):
+            npb, rn = (int(v) for v in item.split(":"))
+            p = {"nprobe": npb}
+            if rn > 0:
+                p["recall_num"] = rn
+            _, ri_ = idx.search(xs, 10, params=p)
+            a1, a10 = recall_stats(ri_, gt_i)
+            idx.search_device(q_dev[0], k, params=p)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for b in range(1, min(4, nbatches)):
+                idx.search_device(q_dev[b], k, params=p)
+            torch.cuda.synchronize()
+            qps = nq * (min(4, nbatches) - 1) / (time.perf_counter() - t0)
+            print(json.dumps({"sweep": {"nprobe": npb, "recall_num": rn, "recall_1nn_top10": a1, "recall10": a10,
+                                        "qps_device": qps}}), file=sys.stderr, flush=True)
+        return 0
     rd, ri = idx.search(xs, 10, params=sp or None)
     r1, r10 = recall_stats(ri, gt_i)
 
@@ -355,6 +376,8 @@ def main():
     launches0 = _lib.lib().gb_launch_count()
     sampler.start()
     step_ms, scan_ms = [], []
+    if args.profile:
+        torch.cuda.profiler.start()
     for s in range(args.steps):
         b = args.warmup + s
         flush.fill_(s)  # L2 flush between timed iterations (untimed)
@@ -366,6 +389,8 @@ def main():
         sync_all()
         step_ms.append(e0.elapsed_time(e1))
         scan_ms.append(idx.last_scan_ms)
+    if args.profile:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = (_lib.lib().gb_launch_count() - launches0) / max(1, args.steps)
     idx.set_scan_timing(False)

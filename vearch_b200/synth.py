@@ -1,21 +1,30 @@
 """Seeded synthetic inputs for tests and bench.
 
-SIFT-shaped: d-dim mixture of Gaussian clusters, clipped to [0, 218] and rounded to integers
-stored as fp32 -- every partial sum of squared differences is then exactly representable in
-fp32 (d * 218^2 < 2^24 for d <= 353), so distances are independent of summation order and
-GPU-vs-oracle parity on this data is bit-exact.
+SIFT-shaped: d-dim mixture of Gaussian clusters with ANISOTROPIC per-cluster noise (a quarter
+of the dimensions carry most of the variance, like SIFT's gradient-histogram bins), clipped to
+[0, 218] and rounded to integers stored as fp32 -- every partial sum of squared differences is
+then exactly representable in fp32 (d * 218^2 < 2^24 for d <= 353), so distances are independent
+of summation order and GPU-vs-oracle parity on this data is bit-exact.
 Embedding-shaped: same mixture, unrounded, L2-normalised (cosine == inner product).
 """
 import numpy as np
 
+HI_SIGMA, LO_SIGMA, HI_FRAC = 24.0, 3.0, 0.25
 
-def sift_like(n, d=128, seed=1234, n_clusters=256, centers_seed=99, sigma=16.0):
+
+def _centers_np(n_clusters, d, centers_seed):
     rng_c = np.random.default_rng(centers_seed)
     centers = rng_c.uniform(0, 128, size=(n_clusters, d)).astype(np.float32)
     centers *= (rng_c.random((n_clusters, d)) < 0.5)
+    scale = np.where(rng_c.random((n_clusters, d)) < HI_FRAC, HI_SIGMA, LO_SIGMA).astype(np.float32)
+    return centers, scale
+
+
+def sift_like(n, d=128, seed=1234, n_clusters=256, centers_seed=99):
+    centers, scale = _centers_np(n_clusters, d, centers_seed)
     rng = np.random.default_rng(seed)
     lab = rng.integers(0, n_clusters, size=n)
-    x = centers[lab] + rng.normal(0, sigma, size=(n, d)).astype(np.float32)
+    x = centers[lab] + rng.normal(0, 1, size=(n, d)).astype(np.float32) * scale[lab]
     return np.clip(np.rint(x), 0, 218).astype(np.float32)
 
 
@@ -29,20 +38,22 @@ def embed_like(n, d=768, seed=1234, n_clusters=256, centers_seed=99, sigma=0.6):
     return x.astype(np.float32)
 
 
-def sift_like_torch(n, d, seed, device, n_clusters=4096, centers_seed=99, sigma=16.0, chunk=1 << 20):
+def sift_like_torch(n, d, seed, device, n_clusters=4096, centers_seed=99, chunk=1 << 20):
     """Same family as sift_like, generated on `device` with torch (bench sizes)."""
     import torch
     gc = torch.Generator(device=device)
     gc.manual_seed(centers_seed)
     centers = torch.rand((n_clusters, d), generator=gc, device=device) * 128.0
     centers = centers * (torch.rand((n_clusters, d), generator=gc, device=device) < 0.5)
+    hi = torch.rand((n_clusters, d), generator=gc, device=device) < HI_FRAC
+    scale = torch.where(hi, torch.tensor(HI_SIGMA, device=device), torch.tensor(LO_SIGMA, device=device))
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     out = torch.empty((n, d), dtype=torch.float32, device=device)
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         lab = torch.randint(0, n_clusters, (e - s,), generator=g, device=device)
-        x = centers[lab] + torch.randn((e - s, d), generator=g, device=device) * sigma
+        x = centers[lab] + torch.randn((e - s, d), generator=g, device=device) * scale[lab]
         out[s:e] = torch.clamp(torch.round(x), 0, 218)
     return out
 
