@@ -1,0 +1,708 @@
+// Engine (see engine.h).  Reference call sites cited inline.
+#include "engine.h"
+
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <fstream>
+#include <map>
+
+#include "json.h"
+#include "params.h"
+#include "wire.h"
+
+namespace gb {
+
+std::string Status::ToString() const {  // util/status.cc:43-100
+  const char* type = "";
+  switch (code) {
+    case kOk: return "OK";
+    case kNotFound: type = "NotFound: "; break;
+    case kIndexError: type = "IndexError: "; break;
+    case kNotSupported: type = "Not implemented: "; break;
+    case kInvalidArgument: type = "Invalid argument: "; break;
+    case kIOError: type = "IO error: "; break;
+    case kBusy: type = "Resource busy: "; break;
+    case kTimedOut: type = "Operation timed out: "; break;
+    case kCanceled: type = "Operation canceled: "; break;
+    case kMemoryExceeded: type = "Memory exceed limit: "; break;
+    default: type = "Unknown code: "; break;
+  }
+  return std::string(type) + msg;
+}
+
+// ---- vearchpb.SearchRequest (router_grpc.proto:168-191; request.cc:17-91) --------------------
+bool SearchRequestPB::parse(const uint8_t* data, size_t len) {
+  PbReader r(data, len);
+  PbField f;
+  while (r.next(&f)) {
+    switch (f.num) {
+      case 1: {  // RequestHead: only params (field 7, map<string,string>) matter
+        if (f.wire != 2) break;
+        PbReader h(f.data, f.len);
+        PbField hf;
+        while (h.next(&hf)) {
+          if (hf.num != 7 || hf.wire != 2) continue;
+          PbReader e(hf.data, hf.len);
+          PbField ef;
+          std::string k, v;
+          while (e.next(&ef)) {
+            if (ef.wire != 2) continue;
+            if (ef.num == 1) k.assign(reinterpret_cast<const char*>(ef.data), ef.len);
+            if (ef.num == 2) v.assign(reinterpret_cast<const char*>(ef.data), ef.len);
+          }
+          if (k == "request_id") request_id = v;
+          if (k == "partition_id") partition_id = atoi(v.c_str());
+        }
+        if (h.error()) return false;
+        break;
+      }
+      case 2: req_num = (int)f.val; break;
+      case 3: topn = (int)f.val; break;
+      case 4: brute_force_search = (int)f.val; break;
+      case 5: {  // VectorQuery
+        if (f.wire != 2) break;
+        VecQuery q;
+        PbReader v(f.data, f.len);
+        PbField vf;
+        while (v.next(&vf)) {
+          if (vf.num == 1 && vf.wire == 2) q.name.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+          if (vf.num == 2 && vf.wire == 2) q.value.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+          if (vf.num == 3 && vf.wire == 1) q.min_score = pb_double(vf.val), q.has_min = true;
+          if (vf.num == 4 && vf.wire == 1) q.max_score = pb_double(vf.val), q.has_max = true;
+          if (vf.num == 6 && vf.wire == 2) q.index_type.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+        }
+        if (v.error()) return false;
+        vec_fields.push_back(std::move(q));
+        break;
+      }
+      case 6:
+        if (f.wire == 2) fields.emplace_back(reinterpret_cast<const char*>(f.data), f.len);
+        break;
+      case 7: n_range_filters++; break;
+      case 8: n_term_filters++; break;
+      case 9:
+        if (f.wire == 2) index_params.assign(reinterpret_cast<const char*>(f.data), f.len);
+        break;
+      case 10: multi_vector_rank = (int)f.val; break;
+      case 11: l2_sqrt = f.val != 0; break;
+      case 16: trace = f.val != 0; break;
+      case 20: offset = (int)f.val; break;
+      default: break;  // unknown / unused fields are skipped
+    }
+  }
+  return !r.error();
+}
+
+// ---- kill switch ---------------------------------------------------------------------------
+static std::mutex g_kill_mu;
+static std::map<std::pair<std::string, int>, int> g_killed;
+void Engine::SetKill(const std::string& request_id, int partition_id, int reason) {
+  std::lock_guard<std::mutex> g(g_kill_mu);
+  g_killed[{request_id, partition_id}] = reason;
+}
+void Engine::ClearKill(const std::string& request_id, int partition_id) {
+  std::lock_guard<std::mutex> g(g_kill_mu);
+  g_killed.erase({request_id, partition_id});
+}
+bool Engine::IsKilled(const std::string& request_id, int partition_id) {
+  if (request_id.empty()) return false;
+  std::lock_guard<std::mutex> g(g_kill_mu);
+  return g_killed.count({request_id, partition_id}) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+Engine::Engine(const std::string& path, const std::string& space_name, int device)
+    : path_(path), space_name_(space_name), device_(device) {}
+
+Engine::~Engine() {
+  // Close: stop the indexing thread (search/engine.cc Engine::~Engine / Close)
+  int st = indexing_state_.load();
+  if (st != 0) indexing_state_.store(3);
+  if (indexing_thread_.joinable()) indexing_thread_.join();
+  cudaSetDevice(device_);
+  index_.reset();
+}
+
+// Engine::CreateTable (search/engine.cc:582-690) + TableInfo::Deserialize (table.cc:30-157) +
+// VectorManager::CreateVectorTable (vector_manager.cc:343-453)
+Status Engine::CreateTable(const uint8_t* fb, size_t len) {
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  if (created_table_) return Status::Make(kInvalidArgument, "table is created");
+  FbTable t = FbTable::root(fb, len);
+  if (!t.ok()) return Status::Make(kInvalidArgument, "table deserialize error");
+  table_name_ = t.str(0);
+  fields_.clear();
+  field_idx_.clear();
+  bool has_id = false;
+  for (size_t i = 0; i < t.vec_len(1); i++) {
+    FbTable f = t.vec_table(1, i);
+    FieldDef fd{f.str(0), (int)f.scalar<int8_t>(1, 0)};
+    if (fd.name == "_id") has_id = true;
+    field_idx_[fd.name] = (int)fields_.size();
+    fields_.push_back(fd);
+  }
+  if (!has_id) {  // the key field always exists (table/table.cc)
+    field_idx_["_id"] = (int)fields_.size();
+    fields_.push_back({"_id", DT_STRING});
+  }
+  values_.assign(fields_.size(), {});
+  size_t nvec = t.vec_len(2);
+  if (nvec == 0) return Status::Make(kInvalidArgument, space_name_ + " table has no vector field");
+  if (nvec > 1) return Status::Make(kNotSupported, "multi-vector tables are not supported by the B200 engine yet");
+  FbTable v = t.vec_table(2, 0);
+  vec_name_ = v.str(0);
+  dim_ = v.scalar<int32_t>(3, 0);
+  if (dim_ <= 0) return Status::Make(kInvalidArgument, "invalid vector dimension");
+  std::string table_index_params = t.str(4);
+  refresh_interval_ = t.scalar<int32_t>(5, 1000);
+  enable_id_cache_ = t.scalar<uint8_t>(6, 0) != 0;
+  enable_realtime_ = t.scalar<uint8_t>(7, 0) != 0;
+  training_threshold_ = 0;
+  {
+    JsonValue jv;
+    int tt = 0;
+    if (!table_index_params.empty() && JsonParser::parse(table_index_params, &jv) && jv.get_int("training_threshold", &tt) &&
+        tt > 0)
+      training_threshold_ = tt;
+  }
+  // index type of the vector field: first entry of `indexes` with a matching field_name
+  // (vector_manager.cc:365-373)
+  index_type_.clear();
+  for (size_t i = 0; i < t.vec_len(8); i++) {
+    FbTable ix = t.vec_table(8, i);
+    if (ix.str(2) == vec_name_ && !ix.str(1).empty()) {
+      index_type_ = ix.str(1);
+      index_params_ = ix.str(4);
+      break;
+    }
+  }
+  if (index_type_.empty()) return Status::Make(kInvalidArgument, vec_name_ + " index type is empty");
+  ModelParams mp;
+  std::string err;
+  if (!parse_model_params(index_params_, &mp, &err)) return Status::Make(kInvalidArgument, err);
+  if (table_index_params.empty() && mp.training_threshold > training_threshold_)
+    training_threshold_ = mp.training_threshold;  // table.cc:143-150
+  if (training_threshold_ > 0) mp.training_threshold = training_threshold_;
+  Index* idx = create_index(index_type_, dim_, mp, device_, 20);
+  if (!idx) return Status::Make(index_type_ == "FLAT" || index_type_ == "IVFFLAT" || index_type_ == "IVFPQ"
+                                    ? kInvalidArgument
+                                    : kNotSupported,
+                                last_error());
+  index_.reset(idx);
+  if (training_threshold_ <= 0) training_threshold_ = index_->training_threshold();
+  created_table_ = true;
+  // <path>/<table>.schema, as the reference writes it (engine.cc:676-684)
+  if (!path_.empty()) {
+    mkdir(path_.c_str(), 0755);
+    std::ofstream f(path_ + "/" + table_name_ + ".schema", std::ios::binary);
+    if (f) f.write(reinterpret_cast<const char*>(fb), (std::streamsize)len);
+  }
+  return Status::OK();
+}
+
+int Engine::flush_pending_locked() {
+  if (pending_n_ == 0) return 0;
+  int rc = index_->add_vectors(pending_.data(), pending_n_);
+  if (rc) return rc;
+  pending_.clear();
+  pending_n_ = 0;
+  return 0;
+}
+
+// Engine::AddOrUpdate (search/engine.cc:691-772) + Doc::Deserialize (doc.cc:43-76)
+int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
+  if (!created_table_) return -1;
+  FbTable d = FbTable::root(fb, len);
+  if (!d.ok()) return -3;
+  std::string key;
+  std::vector<DocField> table_fields;
+  const uint8_t* vec = nullptr;
+  size_t vec_len = 0;
+  bool has_vec = false;
+  for (size_t i = 0; i < d.vec_len(0); i++) {
+    FbTable f = d.vec_table(0, i);
+    DocField df;
+    df.name = f.str(0);
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    f.bytes(1, &p, &n);
+    df.data_type = f.scalar<int8_t>(2, 0);
+    if (df.name == "_id") key.assign(reinterpret_cast<const char*>(p), n);
+    if (df.data_type == DT_VECTOR) {
+      if (df.name == vec_name_) {
+        vec = p;
+        vec_len = n;
+        has_vec = true;
+      }
+    } else {
+      if (!field_idx_.count(df.name)) continue;  // "Unknown field" (doc.cc:66-69)
+      df.value.assign(reinterpret_cast<const char*>(p), n);
+      table_fields.push_back(std::move(df));
+    }
+  }
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  auto it = key2docid_.find(key);
+  int docid = it == key2docid_.end() ? -1 : it->second;
+  if (docid != -1 && docid < max_docid_) {  // Update (engine.cc:703-710, 774-850)
+    for (auto& f : table_fields) values_[field_idx_[f.name]][docid] = f.value;
+    if (has_vec) {
+      if (vec_len != (size_t)dim_ * 4) return -1;
+      std::vector<float> x(dim_);
+      memcpy(x.data(), vec, vec_len);
+      if (flush_pending_locked()) return -1;
+      if (index_->update_vector(docid, x.data())) return -1;
+    }
+    return 0;
+  } else if (docid >= max_docid_) {
+    return -2;
+  }
+  // CheckDoc (engine.cc:802-813): every vector field present with d*4 bytes
+  if (!has_vec || vec_len != (size_t)dim_ * 4) return -3;
+  if (key.empty()) return -3;
+  for (size_t fi = 0; fi < fields_.size(); fi++) values_[fi].emplace_back();
+  for (auto& f : table_fields) values_[field_idx_[f.name]][max_docid_] = f.value;
+  values_[field_idx_["_id"]][max_docid_] = key;
+  keys_.push_back(key);
+  key2docid_[key] = max_docid_;
+  pending_.resize((size_t)(pending_n_ + 1) * dim_);
+  memcpy(pending_.data() + (size_t)pending_n_ * dim_, vec, vec_len);
+  pending_n_++;
+  ++max_docid_;
+  if ((size_t)(max_docid_ >> 3) + 1 > del_bitmap_.size()) del_bitmap_.resize((size_t)(max_docid_ >> 3) + 4096, 0);
+  if (pending_n_ >= 8192 && flush_pending_locked()) return -5;
+  // auto-start indexing (engine.cc:753-761)
+  if (refresh_interval_ >= 0 && indexing_state_.load() == 0 && index_status_.load() == 0 &&
+      max_docid_ - delete_num_ >= training_threshold_) {
+    lk.unlock();
+    BuildIndex();
+  }
+  return 0;
+}
+
+// Engine::Delete (search/engine.cc:852-879)
+int Engine::Delete(const std::string& key) {
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  auto it = key2docid_.find(key);
+  if (it == key2docid_.end() || it->second < 0) return -1;
+  int docid = it->second;
+  if ((del_bitmap_[docid >> 3] >> (docid & 7)) & 1) return 0;
+  del_bitmap_[docid >> 3] |= (uint8_t)(1u << (docid & 7));
+  ++delete_num_;
+  key2docid_.erase(it);  // table_->Delete(key)
+  return 0;
+}
+
+void Engine::serialize_doc(int docid, bool with_docid, std::string* out) {
+  FbBuilder b;
+  std::vector<FbBuilder::Off> offs;
+  auto add_field = [&](const std::string& name, const std::string& value, int dt) {
+    FbBuilder::Off v = b.create_bytes(value.data(), value.size(), false);
+    FbBuilder::Off n = b.create_string(name);
+    b.start_table(3);
+    b.add_offset(0, n);
+    b.add_offset(1, v);
+    if (dt) b.add_scalar<int8_t>(2, (int8_t)dt);
+    offs.push_back(b.end_table());
+  };
+  if (docid >= 0) {
+    for (size_t fi = 0; fi < fields_.size(); fi++) add_field(fields_[fi].name, values_[fi][docid], fields_[fi].data_type);
+    if (with_docid) add_field("_docid", std::string(reinterpret_cast<const char*>(&docid), 4), DT_INT);
+    std::vector<float> x(dim_);
+    bool got = false;
+    int64_t stored = index_->store().size();
+    if (docid < stored) {
+      got = index_->store().get_host(docid, x.data()) == 0;
+    } else if (docid - stored < pending_n_) {
+      memcpy(x.data(), pending_.data() + (size_t)(docid - stored) * dim_, (size_t)dim_ * 4);
+      got = true;
+    }
+    if (got) add_field(vec_name_, std::string(reinterpret_cast<const char*>(x.data()), (size_t)dim_ * 4), DT_VECTOR);
+  }
+  FbBuilder::Off fv = b.create_offset_vector(offs);
+  b.start_table(1);
+  b.add_offset(0, fv);
+  b.finish(b.end_table());
+  out->assign(reinterpret_cast<const char*>(b.data()), b.size());
+}
+
+// Engine::GetDoc (search/engine.cc:881-948)
+int Engine::GetDocByKey(const std::string& key, std::string* fb_out) {
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  cudaSetDevice(device_);
+  auto it = key2docid_.find(key);
+  if (it == key2docid_.end() || it->second < 0) {
+    serialize_doc(-1, false, fb_out);
+    return -1;
+  }
+  int docid = it->second;
+  if ((del_bitmap_[docid >> 3] >> (docid & 7)) & 1) {
+    serialize_doc(-1, false, fb_out);
+    return -1;
+  }
+  serialize_doc(docid, false, fb_out);
+  return 0;
+}
+int Engine::GetDocByDocid(int docid, bool next, std::string* fb_out) {
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  cudaSetDevice(device_);
+  auto deleted = [&](int id) { return ((del_bitmap_[id >> 3] >> (id & 7)) & 1) != 0; };
+  if ((next ? docid < -1 : docid < 0) || docid >= max_docid_) {
+    serialize_doc(-1, false, fb_out);
+    return -1;
+  }
+  if (next) {
+    while (++docid < max_docid_)
+      if (!deleted(docid)) break;
+    if (docid >= max_docid_) {
+      serialize_doc(-1, false, fb_out);
+      return -1;
+    }
+  } else if (deleted(docid)) {
+    serialize_doc(-1, false, fb_out);
+    return -1;
+  }
+  serialize_doc(docid, next, fb_out);
+  return 0;
+}
+
+// Engine::Search (search/engine.cc:242-402) + VectorManager::Search (vector_manager.cc:739-1079)
+// + Response::Serialize (response.cc:46-185)
+Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
+  if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
+  if (req.req_num <= 0) return Status::Make(kInvalidArgument, space_name_ + " req_num should not less than 0");
+  if (req.topn <= 0) return Status::Make(kInvalidArgument, "limit[topN] is zero");
+  if (req.n_range_filters || req.n_term_filters)
+    return Status::Make(kNotSupported, "scalar filters are not supported by the B200 engine yet");
+  if (req.vec_fields.size() != 1)
+    return Status::Make(req.vec_fields.empty() ? kInvalidArgument : kNotSupported,
+                        req.vec_fields.empty() ? "no vector query" : "multi-vector queries are not supported yet");
+  const auto& vq = req.vec_fields[0];
+  if (vq.name != vec_name_)
+    return Status::Make(kInvalidArgument, "Query name " + vq.name + " not exist in created vector table");
+  int brute = req.brute_force_search;
+  if (brute == 2 && index_status_.load() != 2) brute = 1;
+  if (brute == 0 && index_status_.load() != 2 && max_docid_ > 100 && !enable_realtime_)
+    return Status::Make(kIndexError, space_name_ + " index not trained, brute_force_search is 0, max_docid_ = " +
+                                         std::to_string(max_docid_) + ", threshold = 100");
+  int n = (int)(vq.value.size() / ((size_t)dim_ * 4));
+  if (n <= 0) return Status::Make(kInvalidArgument, "Search n shouldn't less than 0!");
+  if (IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
+  SearchContext ctx;
+  std::string err;
+  if (!parse_retrieval_params(req.index_params, &ctx.params, &err)) return Status::Make(kInvalidArgument, err);
+  ctx.params.brute_force = brute != 0;
+  // proto3 drops zero-valued doubles; the router always sends a window (doc_query.go:1220-1226)
+  ctx.min_score = vq.has_min ? (float)std::max(vq.min_score, -(double)FLT_MAX) : (vq.has_max ? 0.f : -FLT_MAX);
+  ctx.max_score = vq.has_max ? (float)std::min(vq.max_score, (double)FLT_MAX) : (vq.has_min ? 0.f : FLT_MAX);
+  if (!vq.has_min && !vq.has_max) {
+    ctx.min_score = -FLT_MAX;
+    ctx.max_score = FLT_MAX;
+  }
+  const int topN = req.topn + req.offset;
+  std::vector<float> x((size_t)n * dim_);
+  memcpy(x.data(), vq.value.data(), x.size() * 4);
+  std::vector<float> dis((size_t)n * topN);
+  std::vector<int64_t> ids((size_t)n * topN);
+  std::vector<uint8_t> bm;
+  int total_docs;
+  {
+    std::unique_lock<std::shared_mutex> wl(mu_, std::defer_lock);
+    std::shared_lock<std::shared_mutex> rl(mu_, std::defer_lock);
+    if (pending_n_ > 0) {
+      wl.lock();
+      if (flush_pending_locked()) return Status::Make(kIndexError, last_error());
+      wl.unlock();
+    }
+    rl.lock();
+    if (delete_num_ > 0) {
+      bm.assign(del_bitmap_.begin(), del_bitmap_.begin() + (max_docid_ >> 3) + 1);
+      ctx.del_bitmap = bm.data();
+      ctx.bitmap_bits = max_docid_;
+    }
+    total_docs = doc_num();
+  }
+  int rc = index_->search(ctx, n, x.data(), topN, dis.data(), ids.data());
+  if (rc == -2 || IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
+  if (rc != 0) return Status::Make(kInvalidArgument, "faild search of query " + vec_name_ + ": " + last_error());
+
+  // ---- Response::Serialize -------------------------------------------------------------------
+  std::shared_lock<std::shared_mutex> rl(mu_);
+  // fields to return: requested ones, or every table field (response.cc:70-86)
+  std::vector<int> attr;
+  bool want_vec = false;
+  if (!req.fields.empty()) {
+    for (auto& nme : req.fields) {
+      if (nme == vec_name_)
+        want_vec = true;
+      else if (field_idx_.count(nme))
+        attr.push_back(field_idx_[nme]);
+    }
+  } else {
+    for (size_t fi = 0; fi < fields_.size(); fi++) attr.push_back((int)fi);
+  }
+  std::sort(attr.begin(), attr.end(), [&](int a, int b) { return fields_[a].name < fields_[b].name; });  // std::map order
+  PbWriter resp;
+  Status okst;
+  std::vector<float> vbuf(dim_);
+  for (int i = 0; i < req.req_num && i < n; i++) {
+    PbWriter sr;
+    // field order on the wire follows the field numbers, like the C++ serializer
+    double max_score = -DBL_MAX;
+    PbWriter items;
+    for (int j = req.offset; j < topN; j++) {
+      int64_t docid = ids[(size_t)i * topN + j];
+      if (docid < 0) continue;  // vector_manager.cc:1059
+      double score = dis[(size_t)i * topN + j];
+      max_score = std::max(max_score, score);
+      PbWriter item;
+      item.put_double(1, score);
+      for (int fi : attr) {
+        PbWriter fld;
+        fld.put_string(1, fields_[fi].name);
+        const std::string& val = values_[fi][docid];
+        fld.put_bytes(3, val.data(), val.size());
+        item.put_message(2, fld.out);
+      }
+      if (want_vec && index_->store().get_host(docid, vbuf.data()) == 0) {
+        PbWriter fld;
+        fld.put_string(1, vec_name_);
+        fld.put_bytes(3, vbuf.data(), (size_t)dim_ * 4);
+        item.put_message(2, fld.out);
+      }
+      items.put_message(7, item.out);
+    }
+    sr.put_double(2, max_score);
+    PbWriter st;
+    st.put_int32(1, total_docs);
+    st.put_int32(3, total_docs);
+    sr.put_message(5, st.out);
+    sr.put_string(6, okst.ToString());
+    sr.out += items.out;
+    resp.put_message(2, sr.out);
+  }
+  *pb_out = resp.out;
+  return Status::OK();
+}
+
+// Engine::BuildIndex / Engine::Indexing (search/engine.cc:951-988, 1091-1142)
+int Engine::BuildIndex() {
+  if (!created_table_) return -1;
+  int expected = 0;
+  if (!indexing_state_.compare_exchange_strong(expected, 1)) return 0;  // already in progress
+  if (indexing_thread_.joinable()) indexing_thread_.join();
+  indexing_thread_ = std::thread(&Engine::indexing_loop, this);
+  return 0;
+}
+
+void Engine::indexing_loop() {
+  cudaSetDevice(device_);
+  int expected = 1;
+  if (!indexing_state_.compare_exchange_strong(expected, 2)) {
+    indexing_state_.store(0);
+    return;
+  }
+  {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    flush_pending_locked();
+  }
+  if (index_->train() != 0) {  // TrainIndex failed (e.g. fewer vectors than training_threshold)
+    indexing_state_.store(0);
+    idx_cv_.notify_all();
+    return;
+  }
+  bool has_error = false;
+  while (indexing_state_.load() == 2) {
+    if (has_error) {
+      std::this_thread::sleep_for(std::chrono::milliseconds(200));
+      continue;
+    }
+    std::vector<uint8_t> bm;
+    {
+      std::unique_lock<std::shared_mutex> lk(mu_);
+      if (flush_pending_locked()) has_error = true;
+      if (delete_num_ > 0) bm.assign(del_bitmap_.begin(), del_bitmap_.begin() + (max_docid_ >> 3) + 1);
+    }
+    if (!has_error && index_->add_pending(bm.empty() ? nullptr : bm.data()) != 0) has_error = true;
+    if (!has_error) index_status_.store(2);
+    // sleep refresh_interval ms, waking early on Close
+    std::unique_lock<std::mutex> lk(idx_mu_);
+    idx_cv_.wait_for(lk, std::chrono::milliseconds(refresh_interval_ > 0 ? refresh_interval_ : 1),
+                     [this] { return indexing_state_.load() != 2; });
+  }
+  indexing_state_.store(0);
+  idx_cv_.notify_all();
+}
+
+std::string Engine::EngineStatus() {  // search/engine.cc:1164-1176
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  int64_t min_indexed = created_table_ && index_ ? index_->indexed_count() : 0;
+  char buf[256];
+  snprintf(buf, sizeof buf,
+           "{\"backup_status\":0,\"doc_num\":%d,\"index_status\":%d,\"max_docid\":%d,\"min_indexed_num\":%lld}",
+           doc_num(), index_status_.load(), max_docid_ - 1, (long long)min_indexed);
+  return buf;
+}
+
+std::string Engine::MemoryInfo() {  // search/engine.cc:1178-1200
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  long long table_mem = 0;
+  for (auto& col : values_)
+    for (auto& v : col) table_mem += (long long)v.size() + (long long)sizeof(std::string);
+  long long index_mem = index_ ? index_->index_mem_bytes() : 0;
+  long long vec_mem = index_ ? index_->store().mem_bytes() : 0;
+  char buf[256];
+  snprintf(buf, sizeof buf,
+           "{\"bitmap_mem\":%lld,\"field_range_mem\":0,\"index_mem\":%lld,\"table_mem\":%lld,\"vector_mem\":%lld}",
+           (long long)del_bitmap_.size(), index_mem, table_mem, vec_mem);
+  return buf;
+}
+
+int Engine::SetConfig(const std::string& json) {  // search/engine.cc:1764-1790
+  JsonValue jv;
+  if (!JsonParser::parse(json, &jv)) return -1;
+  int v;
+  if (jv.get_int("refresh_interval", &v)) refresh_interval_ = v;
+  if (jv.get_int("slow_search_time", &v)) slow_search_time_ = v;
+  bool b;
+  if (jv.get_bool("enable_id_cache", &b)) enable_id_cache_ = b;
+  return 0;
+}
+std::string Engine::GetConfig() {  // search/engine.cc:1792-1807
+  char buf[256];
+  snprintf(buf, sizeof buf,
+           "{\"enable_id_cache\":%s,\"engine_cache_size\":0,\"refresh_interval\":%d,\"slow_search_time\":%d}",
+           enable_id_cache_ ? "true" : "false", refresh_interval_, slow_search_time_);
+  return buf;
+}
+
+// ---- Dump / Load (own snapshot format; byte-compatible gamma dumps are a "next" row) --------
+namespace {
+template <typename T>
+void wr(std::ofstream& f, const T& v) {
+  f.write(reinterpret_cast<const char*>(&v), sizeof(T));
+}
+void wr_str(std::ofstream& f, const std::string& s) {
+  uint64_t n = s.size();
+  wr(f, n);
+  f.write(s.data(), (std::streamsize)n);
+}
+template <typename T>
+bool rdv(std::ifstream& f, T* v) {
+  return (bool)f.read(reinterpret_cast<char*>(v), sizeof(T));
+}
+bool rd_str(std::ifstream& f, std::string* s) {
+  uint64_t n;
+  if (!rdv(f, &n) || n > ((uint64_t)1 << 40)) return false;
+  s->resize(n);
+  return n == 0 || (bool)f.read(&(*s)[0], (std::streamsize)n);
+}
+}  // namespace
+
+// Engine::Dump (search/engine.cc:1202-1247): <path>/retrieval_model_index/<name>.gbdump + dump.done
+int Engine::Dump() {
+  if (!created_table_) return -1;
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  if (flush_pending_locked()) return -1;
+  std::string dir = path_ + "/retrieval_model_index";
+  mkdir(path_.c_str(), 0755);
+  mkdir(dir.c_str(), 0755);
+  std::ofstream f(dir + "/" + table_name_ + ".gbdump", std::ios::binary | std::ios::trunc);
+  if (!f) return -1;
+  const char magic[8] = {'G', 'B', '2', '0', '0', 'D', 'M', 'P'};
+  f.write(magic, 8);
+  wr<int32_t>(f, 1);
+  wr<int32_t>(f, max_docid_);
+  wr<int32_t>(f, delete_num_);
+  wr<int32_t>(f, dim_);
+  wr<uint64_t>(f, fields_.size());
+  for (size_t fi = 0; fi < fields_.size(); fi++)
+    for (int d = 0; d < max_docid_; d++) wr_str(f, values_[fi][d]);
+  wr_str(f, std::string(del_bitmap_.begin(), del_bitmap_.end()));
+  std::vector<float> rows((size_t)max_docid_ * dim_);
+  if (max_docid_ && index_->store().get_rows_host(0, max_docid_, rows.data())) return -1;
+  f.write(reinterpret_cast<const char*>(rows.data()), (std::streamsize)(rows.size() * 4));
+  int trained = index_->trained() ? 1 : 0;
+  wr<int32_t>(f, trained);
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index_.get());
+  IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index_.get());
+  if (trained && ivf) {
+    std::vector<float> c((size_t)ivf->nlist() * dim_);
+    if (ivf->get_centroids(c.data())) return -1;
+    f.write(reinterpret_cast<const char*>(c.data()), (std::streamsize)(c.size() * 4));
+    if (pq) {
+      std::vector<float> p((size_t)pq->M() * 256 * pq->dsub());
+      if (pq->get_pq_centroids(p.data())) return -1;
+      f.write(reinterpret_cast<const char*>(p.data()), (std::streamsize)(p.size() * 4));
+    }
+  }
+  f.close();
+  std::ofstream done(dir + "/dump.done");
+  done << "ok";
+  return f.fail() ? -1 : 0;
+}
+
+// Engine::Load (search/engine.cc:1278-1400): restore the newest complete dump, then let the
+// indexing thread re-add the vectors (the lists are a deterministic function of the stored
+// vectors and the trained state).
+int Engine::Load() {
+  if (!created_table_) return -1;
+  cudaSetDevice(device_);
+  std::string dir = path_ + "/retrieval_model_index";
+  std::ifstream done(dir + "/dump.done");
+  if (!done) return 0;  // nothing to load
+  std::ifstream f(dir + "/" + table_name_ + ".gbdump", std::ios::binary);
+  if (!f) return -1;
+  char magic[8];
+  int32_t ver, maxd, deln, dim;
+  uint64_t nf;
+  if (!f.read(magic, 8) || memcmp(magic, "GB200DMP", 8) || !rdv(f, &ver) || ver != 1 || !rdv(f, &maxd) || !rdv(f, &deln) ||
+      !rdv(f, &dim) || dim != dim_ || !rdv(f, &nf) || nf != fields_.size())
+    return -1;
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  if (max_docid_ != 0) return -1;
+  for (size_t fi = 0; fi < fields_.size(); fi++) {
+    values_[fi].resize(maxd);
+    for (int d = 0; d < maxd; d++)
+      if (!rd_str(f, &values_[fi][d])) return -1;
+  }
+  std::string bm;
+  if (!rd_str(f, &bm)) return -1;
+  del_bitmap_.assign(bm.begin(), bm.end());
+  del_bitmap_.resize(std::max<size_t>(del_bitmap_.size(), (size_t)(maxd >> 3) + 4096), 0);
+  std::vector<float> rows((size_t)maxd * dim_);
+  if (maxd && !f.read(reinterpret_cast<char*>(rows.data()), (std::streamsize)(rows.size() * 4))) return -1;
+  int32_t trained;
+  if (!rdv(f, &trained)) return -1;
+  keys_.resize(maxd);
+  int idf = field_idx_["_id"];
+  for (int d = 0; d < maxd; d++) {
+    keys_[d] = values_[idf][d];
+    if (!((del_bitmap_[d >> 3] >> (d & 7)) & 1)) key2docid_[keys_[d]] = d;
+  }
+  max_docid_ = maxd;
+  delete_num_ = deln;
+  if (maxd && index_->add_vectors(rows.data(), maxd)) return -1;
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index_.get());
+  IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index_.get());
+  if (trained && ivf) {
+    std::vector<float> c((size_t)ivf->nlist() * dim_);
+    if (!f.read(reinterpret_cast<char*>(c.data()), (std::streamsize)(c.size() * 4))) return -1;
+    if (ivf->set_centroids(c.data(), ivf->nlist())) return -1;
+    if (pq) {
+      std::vector<float> p((size_t)pq->M() * 256 * pq->dsub());
+      if (!f.read(reinterpret_cast<char*>(p.data()), (std::streamsize)(p.size() * 4))) return -1;
+      if (pq->set_pq_centroids(p.data())) return -1;
+    }
+  }
+  lk.unlock();
+  if (trained) BuildIndex();  // train() is a no-op on a trained index; the loop re-adds the vectors
+  return 0;
+}
+
+}  // namespace gb

@@ -1,0 +1,137 @@
+// vearch::Engine re-implemented for the B200 hot path (search/engine.{h,cc} +
+// vector/vector_manager.{h,cc} reduced to what the vector path needs): docid allocation,
+// `_id` <-> docid map, in-memory field table, deletion bitmap, indexing state machine and
+// thread, status JSON.  One vector field per table (multi-vector ranking is a "next" row).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "index.h"
+
+namespace gb {
+
+struct Status {  // util/status.h
+  int code = 0;  // vearch::status::Code (idl/fbs/status.fbs)
+  std::string msg;
+  bool ok() const { return code == 0; }
+  std::string ToString() const;
+  static Status OK() { return Status(); }
+  static Status Make(int code, const std::string& msg) {
+    Status s;
+    s.code = code;
+    s.msg = msg;
+    return s;
+  }
+};
+enum StatusCode {
+  kOk = 0, kNotFound = 1, kIndexError = 2, kNotSupported = 3, kInvalidArgument = 4, kIOError = 5, kBusy = 6,
+  kTimedOut = 7, kMemoryExceeded = 8, kCanceled = 9
+};
+
+enum DataType { DT_INT = 0, DT_LONG, DT_FLOAT, DT_DOUBLE, DT_STRING, DT_VECTOR, DT_BOOL, DT_DATE, DT_STRINGARRAY };
+
+struct DocField {
+  std::string name;
+  std::string value;
+  int data_type = DT_STRING;
+};
+
+struct SearchRequestPB {  // c_api/api_data/request.{h,cc}
+  std::string request_id;
+  int partition_id = 0;
+  int req_num = 0;
+  int topn = 0;
+  int brute_force_search = 0;
+  struct VecQuery {
+    std::string name, value, index_type;
+    double min_score = 0, max_score = 0;
+    bool has_min = false, has_max = false;
+  };
+  std::vector<VecQuery> vec_fields;
+  std::vector<std::string> fields;
+  int n_range_filters = 0, n_term_filters = 0;
+  std::string index_params;
+  int multi_vector_rank = 0;
+  bool l2_sqrt = false;
+  bool trace = false;
+  int offset = 0;
+  bool parse(const uint8_t* data, size_t len);
+};
+
+class Engine {
+ public:
+  Engine(const std::string& path, const std::string& space_name, int device);
+  ~Engine();
+
+  Status CreateTable(const uint8_t* fb, size_t len);
+  int AddOrUpdate(const uint8_t* fb, size_t len);
+  int Delete(const std::string& key);
+  int GetDocByKey(const std::string& key, std::string* fb_out);
+  int GetDocByDocid(int docid, bool next, std::string* fb_out);
+  Status Search(const SearchRequestPB& req, std::string* pb_out);
+  int BuildIndex();
+  std::string EngineStatus();
+  std::string MemoryInfo();
+  int SetConfig(const std::string& json);
+  std::string GetConfig();
+  int Dump();
+  int Load();
+  const std::string& space_name() const { return space_name_; }
+
+  // cooperative cancellation (c_api/api_data/request_context.h:51-88)
+  static void SetKill(const std::string& request_id, int partition_id, int reason);
+  static void ClearKill(const std::string& request_id, int partition_id);
+  static bool IsKilled(const std::string& request_id, int partition_id);
+
+ private:
+  int flush_pending_locked();
+  void indexing_loop();
+  void serialize_doc(int docid, bool with_docid, std::string* out);
+  int doc_num() const { return max_docid_ - delete_num_; }
+
+  std::string path_, space_name_;
+  int device_;
+  bool created_table_ = false;
+
+  // table (table/table.{h,cc} reduced to an in-memory column store)
+  std::string table_name_;
+  struct FieldDef {
+    std::string name;
+    int data_type;
+  };
+  std::vector<FieldDef> fields_;
+  std::unordered_map<std::string, int> field_idx_;
+  std::vector<std::vector<std::string>> values_;  // [field][docid]
+  std::unordered_map<std::string, int> key2docid_;
+  std::vector<std::string> keys_;  // docid -> _id
+
+  // vector field
+  std::string vec_name_, index_type_, index_params_;
+  int dim_ = 0;
+  std::unique_ptr<Index> index_;
+  std::vector<float> pending_;  // rows accepted by AddOrUpdate, not yet uploaded to HBM
+  int pending_n_ = 0;
+
+  std::vector<uint8_t> del_bitmap_;
+  int max_docid_ = 0, delete_num_ = 0;
+  int training_threshold_ = 0;
+  int refresh_interval_ = 1000;
+  bool enable_id_cache_ = false, enable_realtime_ = false;
+  int slow_search_time_ = 0;
+
+  std::atomic<int> index_status_{0};    // IndexStatus: 0 UNINDEXED, 1 INDEXING, 2 INDEXED
+  std::atomic<int> indexing_state_{0};  // IndexingState: 0 IDLE, 1 STARTING, 2 RUNNING, 3 STOPPING
+  std::thread indexing_thread_;
+  std::mutex idx_mu_;
+  std::condition_variable idx_cv_;
+  mutable std::shared_mutex mu_;  // table state: searches shared, writes exclusive
+};
+
+}  // namespace gb

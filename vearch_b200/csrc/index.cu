@@ -672,50 +672,74 @@ int IVFFlatIndex::append_batch(const float* x, int64_t n, int64_t vid0, const in
 
 // GammaIVFFlatIndex::Add (gamma_index_ivfflat.cc:413-474) driven like
 // VectorManager::AddRTVecsToIndex (vector_manager.cc:572-702), in large device batches.
+int IVFFlatIndex::index_batch(const float* x, int64_t n, int64_t vid0, const uint8_t* del_bitmap) {
+  cudaStream_t st = build_stream_;
+  Scratch s(st);
+  GB_ALLOC(d_assign, int32_t, n, s);
+  if (assign_dev(x, dpad_, n, d_assign, s)) return -1;
+  std::vector<int32_t> h_list(n), h_pos(n);
+  GB_CUDA(cudaMemcpyAsync(h_list.data(), d_assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> add(nlist_, 0);
+  const std::vector<int>& lens = lists_->lens();
+  if ((int64_t)vid2pos_.size() < vid0 + n) vid2pos_.resize(vid0 + n, ~(uint64_t)0);
+  for (int64_t i = 0; i < n; i++) {
+    int64_t vid = vid0 + i;
+    int l = h_list[i];
+    if (del_bitmap && ((del_bitmap[vid >> 3] >> (vid & 7)) & 1)) {  // ivfflat.cc:436: deleted before indexing
+      h_list[i] = -1;
+      h_pos[i] = 0;
+      continue;
+    }
+    if (l < 0 || l >= nlist_) l = (int)(vid % nlist_);  // ivfflat.cc:443-446
+    h_list[i] = l;
+    h_pos[i] = lens[l] + add[l]++;  // insertion (vid) order inside the list
+    vid2pos_[vid] = ((uint64_t)l << 32) | (uint32_t)h_pos[i];
+  }
+  GB_ALLOC(d_list, int32_t, n, s);
+  GB_ALLOC(d_pos, int32_t, n, s);
+  GB_CUDA(cudaMemcpyAsync(d_list, h_list.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_pos, h_pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  if (lists_->reserve(add, st)) return -1;
+  if (append_batch(x, n, vid0, d_list, d_pos, d_assign, s)) return -1;
+  if (lists_->commit(add, st)) return -1;
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
   if (!trained_) return 0;
   cudaSetDevice(device_);
-  cudaStream_t st = build_stream_;
   const int64_t BATCH = 1 << 20;
   while (indexed_count_ < store_->size()) {
     int64_t vid0 = indexed_count_;
     int64_t si = vid0 >> store_->seg_shift(), off = vid0 & (store_->seg_rows() - 1);
     int64_t n = std::min<int64_t>(std::min(store_->size() - vid0, store_->seg_rows() - off), BATCH);
     const float* x = store_->seg((int)si) + off * dpad_;
-    Scratch s(st);
-    GB_ALLOC(d_assign, int32_t, n, s);
-    if (assign_dev(x, dpad_, n, d_assign, s)) return -1;
-    std::vector<int32_t> h_list(n), h_pos(n);
-    GB_CUDA(cudaMemcpyAsync(h_list.data(), d_assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> add(nlist_, 0);
-    const std::vector<int>& lens = lists_->lens();
-    for (int64_t i = 0; i < n; i++) {
-      int64_t vid = vid0 + i;
-      int l = h_list[i];
-      if (del_bitmap && ((del_bitmap[vid >> 3] >> (vid & 7)) & 1)) {  // ivfflat.cc:436: deleted before indexing
-        h_list[i] = -1;
-        h_pos[i] = 0;
-        continue;
-      }
-      if (l < 0 || l >= nlist_) l = (int)(vid % nlist_);  // ivfflat.cc:443-446
-      h_list[i] = l;
-      h_pos[i] = lens[l] + add[l]++;  // insertion (vid) order inside the list
-    }
-    GB_ALLOC(d_list, int32_t, n, s);
-    GB_ALLOC(d_pos, int32_t, n, s);
-    GB_CUDA(cudaMemcpyAsync(d_list, h_list.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    GB_CUDA(cudaMemcpyAsync(d_pos, h_pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    {
-      std::unique_lock<std::shared_mutex> lk(mu_);
-      if (lists_->reserve(add, st)) return -1;
-      if (append_batch(x, n, vid0, d_list, d_pos, d_assign, s)) return -1;
-      if (lists_->commit(add, st)) return -1;
-      GB_CUDA(cudaStreamSynchronize(st));
-      indexed_count_ += n;
-    }
+    if (index_batch(x, n, vid0, del_bitmap)) return -1;
+    indexed_count_ += n;
   }
   return 0;
+}
+
+int Index::update_vector(int64_t vid, const float* x) {
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  return store_->update_host(vid, x, build_stream_);
+}
+
+// GammaIVFFlatIndex::Update / GammaIVFPQIndex::Update (gamma_index_ivfflat.cc:476-522,
+// gamma_index_ivfpq.cc:402-453): tombstone the old entry, append the new vector to its list.
+int IVFFlatIndex::update_vector(int64_t vid, const float* x) {
+  if (Index::update_vector(vid, x)) return -1;
+  if (!trained_ || vid >= indexed_count_) return 0;  // not indexed yet: the add path will pick it up
+  if (vid < (int64_t)vid2pos_.size() && vid2pos_[vid] != ~(uint64_t)0) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    if (lists_->tombstone((int)(vid2pos_[vid] >> 32), (int)(uint32_t)vid2pos_[vid], build_stream_)) return -1;
+  }
+  int64_t si = vid >> store_->seg_shift(), off = vid & (store_->seg_rows() - 1);
+  return index_batch(store_->seg((int)si) + off * dpad_, 1, vid, nullptr);
 }
 
 int IVFFlatIndex::resolve_nprobe(const SearchContext& ctx) const {

@@ -169,6 +169,9 @@ class Index {
   virtual int train() { trained_ = true; return 0; }
   // VectorManager::AddRTVecsToIndex (vector_manager.cc:572-702): index all not-yet-indexed rows
   virtual int add_pending(const uint8_t* del_bitmap) { indexed_count_ = store_->size(); return 0; }
+  // Engine::Update -> RawVector update + IndexModel::Update (search/engine.cc:774-850;
+  // realtime_mem_data.cc:298-320: old entry tombstoned, vector re-appended to its new list)
+  virtual int update_vector(int64_t vid, const float* x);
   // IndexModel::Search (index_model.h:296): x = nq x d floats; out = nq x k, unfilled id -1.
   // Returns 0, -1 on error (last_error), -2 if killed.  x/out pointers are host unless *_dev.
   int search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
@@ -231,6 +234,7 @@ class IVFFlatIndex : public Index {
   int training_threshold() const override;
   int train() override;
   int add_pending(const uint8_t* del_bitmap) override;
+  int update_vector(int64_t vid, const float* x) override;
   int64_t index_mem_bytes() const override;
   int nlist() const { return nlist_; }
   // parity hooks: exchange index state with the oracle
@@ -257,9 +261,13 @@ class IVFFlatIndex : public Index {
                            const int32_t* d_assign, Scratch& s);
   virtual int train_extra(const float* xtrain, int64_t n, Scratch& s) { (void)xtrain; (void)n; (void)s; return 0; }
 
+  // index rows [vid0, vid0+n) (device pointer x, stride dpad) into the lists
+  int index_batch(const float* x, int64_t n, int64_t vid0, const uint8_t* del_bitmap);
+
   int nlist_;
   float* d_centroids_ = nullptr;  // [nlist][dpad]
   std::unique_ptr<IvfLists> lists_;
+  std::vector<uint64_t> vid2pos_;  // vid -> (list << 32 | pos), ~0 = not in a list (vid_bucket_no_pos_)
 };
 
 class IVFPQIndex : public IVFFlatIndex {

@@ -15,6 +15,7 @@
 //
 // Algorithmic bytes: (4*d + 8) per scanned entry; roofline: HBM.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -170,6 +171,182 @@ void ivf_cq_geometry(int k, int T, int* KP, int* SORTN) {
   *SORTN = next_pow2(*KP + 2 * T);
 }
 
+// ---- fast path: compile-time geometry ---------------------------------------------------
+// LPR >= 8 lanes share a row, lane p owns float4 chunks {p + LPR*j, j < J} (S = LPR*J).  A
+// quarter-warp then reads 8 consecutive float4 of ONE row, so shared-memory reads are
+// conflict-free without rotation and the query chunks sit in registers (4*J floats per lane).
+// One __syncthreads_count per tile both releases the stage and gives every thread the same
+// upper bound on the queue fill, so the flush decision needs no second barrier.
+template <int METRIC, int LPR, int J>
+__global__ void __launch_bounds__(IVF_NT)
+    ivfflat_scan_fast_kernel(const float* __restrict__ xq, int64_t ldq, const int32_t* __restrict__ probe_ids,
+                             int nprobe, int nsplit, ListDirectory dir, int R, int k, int KP, int SORTN, FilterArgs f,
+                             unsigned long long* __restrict__ partial) {
+  constexpr int S = LPR * J;        // float4 per row
+  constexpr int G = IVF_NT / LPR;   // rows per round
+  constexpr int ROW_BYTES = S * 16;
+  const int T = G * R;
+  const int stage_bytes = T * ROW_BYTES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)IVF_NST * stage_bytes);
+  __shared__ __align__(8) uint64_t full_bar[IVF_NST];
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_tau;
+
+  const int tid = threadIdx.x;
+  const int q = blockIdx.y;
+  const int part = blockIdx.x;
+  const int probe = part / nsplit, split = part - probe * nsplit;
+  unsigned long long* out = partial + ((int64_t)q * gridDim.x + part) * k;
+
+  const int list = probe_ids[(int64_t)q * nprobe + probe];
+  int len = 0;
+  if (list >= 0 && list < dir.nlist) len = dir.len[list];
+  const int r0 = split * IVF_CHUNK_ROWS;
+  const int r1 = min(len, r0 + IVF_CHUNK_ROWS);
+  if (r0 >= r1) {
+    for (int i = tid; i < k; i += IVF_NT) out[i] = kKeySentinel;
+    return;
+  }
+  const float* __restrict__ lvecs = dir.vecs[list];
+  const int64_t* __restrict__ lids = dir.ids[list];
+
+  const int grp = tid / LPR, p = tid % LPR;
+  float4 qreg[J];
+  {
+    const float4* q4 = reinterpret_cast<const float4*>(xq + (int64_t)q * ldq);
+#pragma unroll
+    for (int j = 0; j < J; j++) qreg[j] = __ldg(q4 + p + LPR * j);
+  }
+  CandQueue cq{buf, &s_cnt, &s_tau, k, KP, SORTN};
+  if (tid == 0) {
+    for (int s = 0; s < IVF_NST; s++) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  cq.init();
+
+  const int ntiles = (r1 - r0 + T - 1) / T;
+  auto issue = [&](int t) {
+    int s = t % IVF_NST;
+    int rows = min(T, r1 - (r0 + t * T));
+    uint32_t bytes = (uint32_t)rows * ROW_BYTES;
+    mbar_arrive_expect_tx(&full_bar[s], bytes);
+    bulk_g2s(smem_raw + (size_t)s * stage_bytes, lvecs + (int64_t)(r0 + t * T) * (S * 4), bytes, &full_bar[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < IVF_NST && t < ntiles; t++) issue(t);
+
+  int est = 0;  // upper bound of the queue fill, identical in every thread
+  for (int t = 0; t < ntiles; t++) {
+    const int s = t % IVF_NST;
+    mbar_wait(&full_bar[s], (t / IVF_NST) & 1);
+    const int tile_rows = min(T, r1 - (r0 + t * T));
+    const unsigned long long tau = s_tau;
+    const uint32_t tau_hi = (uint32_t)(tau >> 32);
+    const float4* st4 = reinterpret_cast<const float4*>(smem_raw + (size_t)s * stage_bytes);
+    int pushed = 0;
+    for (int r = 0; r < R; r++) {
+      const int rit = r * G + grp;
+      const bool valid = rit < tile_rows;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (valid) {
+        const float4* rowp = st4 + (size_t)rit * S + p;
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+          float4 v = rowp[LPR * j];
+          float4 w = qreg[j];
+          if (METRIC == kMetricL2) {
+            float t0 = v.x - w.x, t1 = v.y - w.y, t2 = v.z - w.z, t3 = v.w - w.w;
+            a0 = fmaf(t0, t0, a0), a1 = fmaf(t1, t1, a1), a2 = fmaf(t2, t2, a2), a3 = fmaf(t3, t3, a3);
+          } else {
+            a0 = fmaf(v.x, w.x, a0), a1 = fmaf(v.y, w.y, a1), a2 = fmaf(v.z, w.z, a2), a3 = fmaf(v.w, w.w, a3);
+          }
+        }
+      }
+      float dis = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int off = LPR >> 1; off > 0; off >>= 1) dis += __shfl_xor_sync(0xffffffffu, dis, off);
+
+      bool pred = valid && p == 0 && dis <= f.max_score && dis >= f.min_score;
+      unsigned long long key = kKeySentinel;
+      if (pred) {
+        uint32_t ord = score2ord<METRIC>(dis);
+        pred = ord <= tau_hi;
+        if (pred) {
+          int64_t raw = lids[r0 + t * T + rit];
+          pred = raw >= 0;  // top bit set => tombstone (gamma_index_ivfflat.h:72)
+          uint32_t vid = (uint32_t)raw;
+          if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
+          key = make_key(ord, vid);
+          pred = pred && key < tau;
+        }
+      }
+      cq.push_warp(pred, key);
+      pushed |= pred ? 1 : 0;
+    }
+    // stage s consumed + pushes done; the count is the same value in every thread
+    est += __syncthreads_count(pushed) * R;
+    if (tid == 0 && t + IVF_NST < ntiles) issue(t + IVF_NST);
+    if (t + 1 < ntiles && est + T > cq.cap()) {
+      cq.flush();
+      est = 0;
+    }
+  }
+  __syncthreads();
+  cq.flush();
+  for (int i = tid; i < k; i += IVF_NT) out[i] = buf[i];
+}
+
+template <int METRIC, int LPR, int J>
+cudaError_t launch_fast(const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe, int nsplit,
+                        ListDirectory dir, int k, FilterArgs f, unsigned long long* partial, cudaStream_t st) {
+  constexpr int S = LPR * J, G = IVF_NT / LPR, ROW_BYTES = S * 16;
+  int stage_target = IVF_STAGE_BYTES;
+  if (const char* e = getenv("GB_IVF_STAGE_KB")) stage_target = atoi(e) * 1024;
+  int R = stage_target / (G * ROW_BYTES);
+  if (R < 1) R = 1;
+  const int T = G * R;
+  int KP, SORTN;
+  ivf_cq_geometry(k, T, &KP, &SORTN);
+  size_t smem = (size_t)IVF_NST * T * ROW_BYTES + (size_t)SORTN * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(ivfflat_scan_fast_kernel<METRIC, LPR, J>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(nprobe * nsplit, nq);
+  ivfflat_scan_fast_kernel<METRIC, LPR, J><<<grid, IVF_NT, smem, st>>>(xq, ldq, probe_ids, nprobe, nsplit, dir, R, k, KP,
+                                                                       SORTN, f, partial);
+  note_launch();
+  return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when no instantiation fits (caller falls back to the generic kernel)
+template <int METRIC>
+cudaError_t dispatch_fast(int S, const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe,
+                          int nsplit, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
+                          cudaStream_t st) {
+#define GB_FAST(LPR, J)   if (S == (LPR) * (J)) return launch_fast<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, dir, k, f, partial, st)
+  GB_FAST(8, 1);   // d = 32
+  GB_FAST(8, 2);   // d = 64
+  GB_FAST(8, 3);   // d = 96
+  GB_FAST(8, 4);   // d = 128
+  GB_FAST(8, 5);
+  GB_FAST(8, 6);   // d = 192
+  GB_FAST(8, 7);
+  GB_FAST(8, 8);   // d = 256
+  GB_FAST(16, 5);
+  GB_FAST(16, 6);  // d = 384
+  GB_FAST(16, 7);
+  GB_FAST(16, 8);  // d = 512
+  GB_FAST(32, 5);
+  GB_FAST(32, 6);  // d = 768
+  GB_FAST(32, 7);
+  GB_FAST(32, 8);  // d = 1024
+  GB_FAST(32, 12); // d = 1536
+#undef GB_FAST
+  return cudaErrorNotSupported;
+}
+
 }  // namespace
 
 int ivfflat_scan_nparts(int nprobe, int max_list_len) {
@@ -187,6 +364,13 @@ cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, con
   int nparts = ivfflat_scan_nparts(nprobe, max_list_len);
   int nsplit = nparts / nprobe;
   if (nparts_out) *nparts_out = nparts;
+  if (ldq % 4 == 0 && !getenv("GB_IVF_GENERIC")) {
+    cudaError_t fe = metric == kMetricL2 ? dispatch_fast<kMetricL2>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, dir,
+                                                                    k, f, partial, st)
+                                         : dispatch_fast<kMetricIP>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, dir,
+                                                                    k, f, partial, st);
+    if (fe != cudaErrorNotSupported) return fe;
+  }
   int KP, SORTN;
   ivf_cq_geometry(k, g.T, &KP, &SORTN);
   size_t smem = (size_t)IVF_NST * g.stage_bytes + (size_t)d * 4 + (size_t)SORTN * 8;

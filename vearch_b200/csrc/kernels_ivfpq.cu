@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(KSUB)
 }
 
 // ---------------- ADC scan ------------------------------------------------------------------
-constexpr int PQ_NT = 128;
+constexpr int PQ_NT = 256;
 constexpr int PQ_NST = 4;
 constexpr int PQ_MAX_PG = 32;  // probes per CTA
 
@@ -132,9 +132,7 @@ __global__ void __launch_bounds__(PQ_NT)
   const int tile_bytes = tile_e * M;
   unsigned char* stages = smem_raw;
   float* lut = reinterpret_cast<float*>(smem_raw + (size_t)PQ_NST * tile_bytes);
-  float* ipq = lut + M * KSUB;  // only used for L2
-  unsigned long long* buf =
-      reinterpret_cast<unsigned long long*>(lut + (METRIC == kMetricL2 ? 2 : 1) * M * KSUB);
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(lut + M * KSUB);
   __shared__ __align__(8) uint64_t full_bar[PQ_NST];
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
@@ -170,11 +168,12 @@ __global__ void __launch_bounds__(PQ_NT)
     return;
   }
 
-  // per-query inner-product table -> smem (L2: kept aside, IP: it IS the LUT, dis0 = <x, centroid>)
-  {
-    const float4* src = reinterpret_cast<const float4*>(ip_table + (int64_t)q * M * KSUB);
-    float4* dst = reinterpret_cast<float4*>(METRIC == kMetricL2 ? ipq : lut);
-    for (int i = tid; i < M * KSUB / 4; i += PQ_NT) dst[i] = __ldg(src + i);
+  // per-query inner-product table (L2-resident): IP => it IS the LUT (dis0 = <x, centroid>);
+  // L2 => combined with the list's precomputed row when a new list starts
+  const float4* ipq4 = reinterpret_cast<const float4*>(ip_table + (int64_t)q * M * KSUB);
+  if (METRIC != kMetricL2) {
+    float4* dst = reinterpret_cast<float4*>(lut);
+    for (int i = tid; i < M * KSUB / 4; i += PQ_NT) dst[i] = __ldg(ipq4 + i);
   }
 
   // producer cursor (thread 0 only)
@@ -195,7 +194,11 @@ __global__ void __launch_bounds__(PQ_NT)
   int pi = -1;  // consumer cursor
   float dis0 = 0.f;
   const int64_t* __restrict__ lids = nullptr;
-  const int per_thread = tile_e / PQ_NT;
+  // entries per thread per tile: compile-time for the vector-load code layouts (gives the
+  // compiler PT independent ADC chains to interleave), runtime for the generic layout
+  constexpr int PT = MW == 2 ? 4 : (MW == 4 ? 2 : 1);
+  const int per_thread = MW > 0 ? PT : tile_e / PQ_NT;
+  int est = 0;  // upper bound of the queue fill, identical in every thread
 
   for (int gt = 0; gt < total_tiles; gt++) {
     int npi = pi < 0 ? 0 : pi;
@@ -205,12 +208,10 @@ __global__ void __launch_bounds__(PQ_NT)
       dis0 = g_dis0[pi];
       lids = dir.ids[g_list[pi]];
       if (METRIC == kMetricL2) {
-        __syncthreads();  // previous list's readers of lut are done (and ipq is loaded)
         const float4* Tl = reinterpret_cast<const float4*>(T + (int64_t)g_list[pi] * M * KSUB);
-        const float4* ip4 = reinterpret_cast<const float4*>(ipq);
         float4* lut4 = reinterpret_cast<float4*>(lut);
         for (int i = tid; i < M * KSUB / 4; i += PQ_NT) {
-          float4 t = __ldg(Tl + i), a = ip4[i];
+          float4 t = __ldg(Tl + i), a = __ldg(ipq4 + i);
           lut4[i] = make_float4(fmaf(-2.0f, a.x, t.x), fmaf(-2.0f, a.y, t.y), fmaf(-2.0f, a.z, t.z),
                                 fmaf(-2.0f, a.w, t.w));
         }
@@ -224,33 +225,50 @@ __global__ void __launch_bounds__(PQ_NT)
     const unsigned long long tau = s_tau;
     const uint32_t tau_hi = (uint32_t)(tau >> 32);
     const unsigned char* st = stages + (size_t)s * tile_bytes;
+    int pushed = 0;
 
-    for (int u = 0; u < per_thread; u++) {
-      const int e = u * PQ_NT + tid;
-      bool pred = e < n_e;
+    auto consider = [&](int e, float dis) {
+      bool pred = e < n_e && dis <= f.max_score && dis >= f.min_score;
       unsigned long long key = kKeySentinel;
+      uint32_t ord = score2ord<METRIC>(dis);
+      pred = pred && ord <= tau_hi;
       if (pred) {
-        float dis = adc_distance<MW>(st + (size_t)e * M, lut, dis0, M);
-        pred = dis <= f.max_score && dis >= f.min_score;
-        uint32_t ord = score2ord<METRIC>(dis);
-        pred = pred && ord <= tau_hi;
-        if (pred) {
-          int64_t raw = lids[(int64_t)ti * tile_e + e];
-          pred = raw >= 0;  // tombstone (gamma_index_ivfpq.h:930)
-          uint32_t vid = (uint32_t)raw;
-          if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
-          key = make_key(ord, vid);
-          pred = pred && key < tau;
-        }
+        int64_t raw = lids[(int64_t)ti * tile_e + e];
+        pred = raw >= 0;  // tombstone (gamma_index_ivfpq.h:930)
+        uint32_t vid = (uint32_t)raw;
+        if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
+        key = make_key(ord, vid);
+        pred = pred && key < tau;
       }
       cq.push_warp(pred, key);
+      pushed |= pred ? 1 : 0;
+    };
+    if (MW > 0) {
+      float dis[PT];
+#pragma unroll
+      for (int u = 0; u < PT; u++) {
+        const int e = u * PQ_NT + tid;
+        // entries past n_e read stale-but-in-bounds stage bytes; they are masked in consider()
+        dis[u] = adc_distance<MW>(st + (size_t)e * M, lut, dis0, M);
+      }
+#pragma unroll
+      for (int u = 0; u < PT; u++) consider(u * PQ_NT + tid, dis[u]);
+    } else {
+      for (int u = 0; u < per_thread; u++) {
+        const int e = u * PQ_NT + tid;
+        float dis = e < n_e ? adc_distance<MW>(st + (size_t)e * M, lut, dis0, M) : 0.f;
+        consider(e, dis);
+      }
     }
-    __syncthreads();
-    const int c_now = s_cnt;
+    // stage consumed + pushes done; the count is identical in every thread (no 2nd barrier needed)
+    est += __syncthreads_count(pushed) * per_thread;
     if (tid == 0 && gt + PQ_NST < total_tiles) issue(gt + PQ_NST);
-    __syncthreads();
-    if (gt + 1 < total_tiles && c_now + tile_e > cq.cap()) cq.flush();
+    if (gt + 1 < total_tiles && est + tile_e > cq.cap()) {
+      cq.flush();
+      est = 0;
+    }
   }
+  __syncthreads();
   cq.flush();
   for (int i = tid; i < k; i += PQ_NT) out[i] = buf[i];
 }
@@ -338,7 +356,7 @@ __global__ void __launch_bounds__(ENC_NT)
 
 void pq_cq_geometry(int k, int tile_e, int* KP, int* SORTN) {
   *KP = next_pow2(k < 16 ? 16 : k);
-  *SORTN = next_pow2(*KP + 2 * tile_e);
+  *SORTN = next_pow2(*KP + tile_e + tile_e / 2);  // cap >= tile_e: one tile always fits after a flush
 }
 
 template <int METRIC, int MW>
@@ -348,7 +366,7 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
   int tile_e = pq_tile_entries(M);
   int KP, SORTN;
   pq_cq_geometry(k, tile_e, &KP, &SORTN);
-  size_t smem = (size_t)PQ_NST * tile_e * M + (size_t)(METRIC == kMetricL2 ? 2 : 1) * M * KSUB * 4 + (size_t)SORTN * 8;
+  size_t smem = (size_t)PQ_NST * tile_e * M + (size_t)M * KSUB * 4 + (size_t)SORTN * 8;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(ivfpq_scan_kernel<METRIC, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
