@@ -113,6 +113,13 @@ int gb_kmeans_update(int device, const float *x, int64_t n, int d, int k, const 
 int gb_merge_partitions_device(int device, const float *dis_dev, const int64_t *ids_dev, int nparts, int nq, int k,
                                int metric, float *out_dis_dev, int64_t *out_ids_dev, void *stream);
 
+/* ---- host-logic test hooks: run the C++ wire codecs of the gamma boundary without a GPU ---- */
+int gb_debug_parse_search_request(const char *buf, int len, char **json_out, int *out_len);
+int gb_debug_roundtrip_doc(const char *buf, int len, char **out, int *out_len);
+int gb_debug_parse_table(const char *buf, int len, char **json_out, int *out_len);
+int gb_debug_encode_response(int nq, int k, const double *scores, const char *const *keys, int total, char **out,
+                             int *out_len);
+
 #ifdef __cplusplus
 }
 #endif

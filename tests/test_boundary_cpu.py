@@ -1,0 +1,157 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the
+headers declare, and the hand-written wire codecs (C++ in libgamma.so, Python in vearch_b200/wire.py)
+agree with golden bytes produced by the official protobuf runtime (tests/golden/gen_golden.py) and
+with each other.  No compute call is made: Init / index creation must FAIL without a GPU."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from vearch_b200 import _lib, wire
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+libc = C.CDLL(None)
+libc.free.argtypes = [C.c_void_p]
+
+
+def declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", txt)) - {"defined", "C"})
+
+
+@pytest.mark.parametrize("header", ["gamma_api.h", "gamma_b200_index.h"])
+def test_library_exports_every_declared_symbol(header):
+    lib = _lib.lib()
+    names = declared_symbols(header)
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"{header}: not exported by libgamma.so: {missing}"
+    if header == "gamma_api.h":
+        # exactly the 23 entry points of internal/engine/c_api/gamma_api.h:26-188
+        assert len(names) == 23
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.lib()
+    assert lib.gb_device_count() == 0
+    assert not lib.gb_index_create(b"FLAT", 8, b"", 0)
+    assert b"no CUDA device" in lib.gb_last_error()
+    lib.Init.restype = C.c_void_p
+    cfg = json.dumps({"path": "/tmp/x", "space_name": "s", "log_dir": "/tmp"}).encode()
+    assert not lib.Init(cfg, len(cfg))  # NULL, like a failed gamma.Init (gammacb/gamma.go:84-88)
+
+
+def _call_json(fn, payload):
+    p, n = C.c_void_p(), C.c_int()
+    fn.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    rc = fn(payload, len(payload), C.byref(p), C.byref(n))
+    data = C.string_at(p.value, n.value) if p.value else b""
+    if p.value:
+        libc.free(p.value)
+    return rc, data
+
+
+@pytest.mark.parametrize("name", ["search_request_router.bin", "search_request_minimal.bin"])
+def test_cpp_parses_official_search_request_bytes(name):
+    exp = json.load(open(os.path.join(GOLD, "search_requests.json")))[name]
+    raw = open(os.path.join(GOLD, name), "rb").read()
+    rc, out = _call_json(_lib.lib().gb_debug_parse_search_request, raw)
+    assert rc == 0
+    got = json.loads(out)
+    for k, v in exp.items():
+        assert got[k] == v, (k, got[k], v)
+
+
+def test_cpp_rejects_truncated_request():
+    raw = open(os.path.join(GOLD, "search_request_router.bin"), "rb").read()
+    rc, _ = _call_json(_lib.lib().gb_debug_parse_search_request, raw[:-3])
+    assert rc == -1
+
+
+def test_python_encoder_matches_official_parser():
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_golden
+    cls = gen_golden.classes()
+    q = np.arange(24, dtype=np.float32).reshape(3, 8)
+    mine = wire.encode_search_request("emb", q, 10, index_params='{"nprobe": 4}', request_id="r1", partition_id=3,
+                                      min_score=-1e300, max_score=1e300, offset=1, trace=True)
+    m = cls["SearchRequest"]()
+    m.ParseFromString(mine)
+    assert m.req_num == 3 and m.topN == 10 and m.offset == 1 and m.trace and m.index_params == '{"nprobe": 4}'
+    assert m.head.params["request_id"] == "r1" and m.head.params["partition_id"] == "3"
+    assert m.vec_fields[0].name == "emb" and m.vec_fields[0].value == q.tobytes()
+    assert m.vec_fields[0].min_score == -1e300 and list(m.fields) == ["_id"]
+    rc, out = _call_json(_lib.lib().gb_debug_parse_search_request, mine)
+    got = json.loads(out)
+    assert rc == 0 and got["request_id"] == "r1" and got["partition_id"] == 3 and got["vec_fields"][0]["value_len"] == 96
+
+
+def test_cpp_response_bytes_equal_official_serializer():
+    exp = json.load(open(os.path.join(GOLD, "search_response.json")))
+    official = open(os.path.join(GOLD, "search_response.bin"), "rb").read()
+    nq, k = len(exp["scores"]), len(exp["scores"][0])
+    scores = (C.c_double * (nq * k))(*[s for row in exp["scores"] for s in row])
+    keys = (C.c_char_p * (nq * k))(*[s.encode() for row in exp["keys"] for s in row])
+    fn = _lib.lib().gb_debug_encode_response
+    fn.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    p, n = C.c_void_p(), C.c_int()
+    assert fn(nq, k, scores, keys, exp["total"], C.byref(p), C.byref(n)) == 0
+    mine = C.string_at(p.value, n.value)
+    libc.free(p.value)
+    assert mine == official  # byte-identical to what libprotobuf emits for Response::Serialize
+    dec = wire.decode_search_response(official)
+    assert [[it["score"] for it in r["items"]] for r in dec] == exp["scores"]
+    assert [[it["fields"]["_id"].decode() for it in r["items"]] for r in dec] == exp["keys"]
+    assert dec[0]["total"] == 1000 and dec[0]["msg"] == "OK" and dec[1]["max_score"] == 5.0
+
+
+def test_flatbuffers_doc_roundtrip_python_and_cpp():
+    vec = np.arange(8, dtype=np.float32).tobytes()
+    fields = [("_id", b"doc-1", wire.DT_STRING), ("price", (7).to_bytes(4, "little"), wire.DT_INT),
+              ("emb", vec, wire.DT_VECTOR)]
+    for as_string in (True, False):  # Go SDK writes value via CreateString; schema says [ubyte]
+        buf = wire.build_doc(fields, value_as_string=as_string)
+        got = wire.parse_doc(buf)
+        assert got == {n: (v, dt) for n, v, dt in fields}
+        rc, out = _call_json(_lib.lib().gb_debug_roundtrip_doc, buf)  # C++ reader -> C++ builder
+        assert rc == 0 and wire.parse_doc(out) == got
+    rc, _ = _call_json(_lib.lib().gb_debug_roundtrip_doc, b"\x01\x02\x03")
+    assert rc == -1
+
+
+def test_flatbuffers_table_parsed_by_cpp():
+    tb = wire.build_table("ts_space", [("_id", wire.DT_STRING, False), ("price", wire.DT_INT, True)],
+                          [("emb", 128, "MemoryOnly", "")],
+                          [("idx", "IVFPQ", "emb", json.dumps({"ncentroids": 256, "nsubvector": 16}))],
+                          refresh_interval=250, enable_id_cache=True)
+    rc, out = _call_json(_lib.lib().gb_debug_parse_table, tb)
+    assert rc == 0
+    t = json.loads(out)
+    assert t["name"] == "ts_space" and t["refresh_interval"] == 250 and t["enable_id_cache"] == 1
+    assert t["fields"] == [{"name": "_id", "data_type": 4, "is_index": 0}, {"name": "price", "data_type": 0, "is_index": 1}]
+    assert t["vectors"] == [{"name": "emb", "dimension": 128, "store_type": "MemoryOnly"}]
+    assert t["indexes"][0]["type"] == "IVFPQ" and json.loads(t["indexes"][0]["params"])["nsubvector"] == 16
+    # default refresh_interval (1000) is omitted on the wire and must read back as 1000
+    tb2 = wire.build_table("t", [], [("emb", 4, "", "")], [("i", "FLAT", "emb", "{}")], refresh_interval=1000)
+    assert json.loads(_call_json(_lib.lib().gb_debug_parse_table, tb2)[1])["refresh_interval"] == 1000
+
+
+def test_oracle_matches_known_answer_vectors():
+    g = np.load(os.path.join(GOLD, "flat_small.npz"))
+    db, xq = g["db"].astype(np.float32), g["xq"].astype(np.float32)
+    d, i = orc.flat_search(db, xq, 10, orc.METRIC_L2)
+    assert np.array_equal(i, g["l2_ids"]) and np.array_equal(d, g["l2_dis"])
+    d, i = orc.flat_search(db, xq, 10, orc.METRIC_IP)
+    assert np.array_equal(d, g["ip_dis"])
+    for q in range(xq.shape[0]):  # CMin reorder lists equal scores with the larger id first
+        assert sorted(zip(-d[q], i[q])) == sorted(zip(-g["ip_dis"][q], g["ip_ids"][q]))

@@ -1,0 +1,263 @@
+"""GPU tests of the gamma C-ABI drop-in (include/gamma_api.h) driven the way the Go partition
+server drives it: Init -> CreateTable(flatbuffers) -> AddOrUpdateDoc(flatbuffers) x N ->
+BuildIndex / auto-build -> poll GetEngineStatus -> Search(protobuf) -> Dump -> Load
+(internal/engine/tests/test.h:1000-1033 TestIndexes, internal/ps/engine/gammacb/*).
+Results are checked against the CPU oracle; error codes against the reference's conventions."""
+import ctypes as C
+import json
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from vearch_b200 import synth, wire
+
+pytestmark = pytest.mark.gpu
+L2, IP = orc.METRIC_L2, orc.METRIC_IP
+D, N, NQ = 32, 6000, 24
+
+
+def eng_mod():
+    from vearch_b200 import engine
+    return engine
+
+
+@pytest.fixture(scope="module")
+def data():
+    return synth.sift_like(N, D, seed=81), synth.sift_like(NQ, D, seed=82)
+
+
+def keys_of(res):
+    return [[it["fields"]["_id"].decode() for it in r["items"]] for r in res]
+
+
+def scores_of(res):
+    return [[it["score"] for it in r["items"]] for r in res]
+
+
+def make_engine(tmp_path, index_type, params, name="ts"):
+    e = eng_mod().GammaEngine(str(tmp_path), space_name=name)
+    e.create_table(name, D, index_type, params, fields=(("_id", wire.DT_STRING, False), ("tag", wire.DT_STRING, False)))
+    return e
+
+
+def add_all(e, db, start=0):
+    for i, v in enumerate(db):
+        assert e.add_doc(f"doc{start + i}", v, extra_fields=[("tag", f"t{(start + i) % 7}".encode(), wire.DT_STRING)]) == 0
+
+
+def test_ivfflat_full_flow_matches_oracle(tmp_path, data):
+    db, xq = data
+    e = make_engine(tmp_path, "IVFFLAT", {"ncentroids": 32, "nprobe": 8, "metric_type": "L2", "training_threshold": 2000})
+    assert e.status() == {"backup_status": 0, "doc_num": 0, "index_status": 0, "max_docid": -1, "min_indexed_num": 0}
+    add_all(e, db[:1500])
+    # untrained, > 100 docs, brute_force_search == 0  =>  IndexNotTrained (search/engine.cc:285-302)
+    with pytest.raises(eng_mod().GammaStatusError) as ei:
+        e.search(xq, 10)
+    assert ei.value.code == 2 and "index not trained" in ei.value.msg
+    # is_brute_search = 1 works before training and is exact (FLAT path, gamma_index_flat.cc)
+    res = e.search(xq, 10, is_brute_search=1)
+    do, io = orc.flat_search(db[:1500], xq, 10, L2)
+    assert keys_of(res) == [[f"doc{i}" for i in row] for row in io]
+    assert np.array_equal(np.array(scores_of(res), np.float32), do)
+    assert res[0]["total"] == 1500 and res[0]["msg"] == "OK" and res[0]["max_score"] == max(scores_of(res)[0])
+    add_all(e, db[1500:], start=1500)  # crossing training_threshold auto-starts indexing (engine.cc:753-761)
+    st = e.wait_indexed(N)
+    assert st["index_status"] == 2 and st["doc_num"] == N and st["max_docid"] == N - 1
+    res = e.search(xq, 10, index_params={"nprobe": 8})
+    _, gt = orc.flat_search(db, xq, 10, L2)
+    got = keys_of(res)
+    hit = np.mean([f"doc{gt[q, 0]}" in got[q] for q in range(NQ)])
+    assert hit >= 0.9  # reference CI pin for IVFFLAT r@10 (test/test_vector_index_ivfflat.py:89-94)
+    for q in range(NQ):  # returned score == sum (x - y)^2 of the returned doc (test_module_vector.py:337-364)
+        for key, s in zip(got[q], scores_of(res)[q]):
+            assert s == float(((xq[q] - db[int(key[3:])]) ** 2).sum())
+        assert scores_of(res)[q] == sorted(scores_of(res)[q])
+    # auto mode (2) on an indexed table == normal search; offset trims the head (vector_manager.cc:1054-1068)
+    res2 = e.search(xq, 5, index_params={"nprobe": 8}, is_brute_search=2, offset=3)
+    assert keys_of(res2) == [row[3:8] for row in keys_of(e.search(xq, 8, index_params={"nprobe": 8}))]
+    # requested fields
+    res3 = e.search(xq[:1], 3, fields=("_id", "tag", "emb"))
+    it = res3[0]["items"][0]
+    docid = int(it["fields"]["_id"].decode()[3:])
+    assert it["fields"]["tag"] == f"t{docid % 7}".encode()
+    assert np.array_equal(np.frombuffer(it["fields"]["emb"], np.float32), db[docid])
+    mi = e.memory_info()
+    assert mi["vector_mem"] > 0 and mi["index_mem"] > 0 and set(mi) == {"table_mem", "index_mem", "vector_mem",
+                                                                        "field_range_mem", "bitmap_mem"}
+    e.close()
+
+
+def test_error_conventions(tmp_path, data):
+    db, xq = data
+    E = eng_mod()
+    e = E.GammaEngine(str(tmp_path))
+    with pytest.raises(E.GammaStatusError) as ei:  # search before CreateTable
+        e.vec_name = "emb"
+        e.search(xq, 10)
+    assert ei.value.code == 4
+    with pytest.raises(E.GammaStatusError) as ei:  # unknown index type
+        e.create_table("t", D, "HNSW", {})
+    assert ei.value.code == 3
+    with pytest.raises(E.GammaStatusError) as ei:  # nprobe > ncentroids (gamma_index_ivfflat.cc:95-99)
+        e.create_table("t", D, "IVFFLAT", {"ncentroids": 8, "nprobe": 32})
+    assert ei.value.code == 4
+    with pytest.raises(E.GammaStatusError) as ei:  # d % nsubvector != 0 (gamma_index_ivfpq.cc:125-133)
+        e.create_table("t", D, "IVFPQ", {"ncentroids": 8, "nprobe": 4, "nsubvector": 5})
+    assert ei.value.code == 4 and "cannot divide by nsubvector" in ei.value.msg
+    e.create_table("t", D, "FLAT", {"metric_type": "L2"})
+    with pytest.raises(E.GammaStatusError) as ei:
+        e.create_table("t", D, "FLAT", {})
+    assert ei.value.code == 4
+    assert e.add_doc("a", db[0]) == 0
+    assert e.add_doc("b", db[1][:-1]) == -3  # CheckDoc: wrong vector length (engine.cc:802-813)
+    assert e.add_doc_raw(wire.build_doc([("_id", b"c", wire.DT_STRING)])) == -3  # no vector field
+    assert e.delete_doc("nope") == -1
+    for kw, code in ((dict(topn=0), 4), (dict(topn=5, req_num=0), 4)):
+        with pytest.raises(E.GammaStatusError) as ei:
+            e.search(xq[:1], kw.pop("topn"), **kw)
+        assert ei.value.code == code
+    with pytest.raises(E.GammaStatusError) as ei:
+        e.search_raw(wire.encode_search_request("other_field", xq[:1], 5))
+    assert ei.value.code == 4
+    with pytest.raises(E.GammaStatusError) as ei:
+        e.search_raw(b"\x0a\xff\xff")  # malformed protobuf
+    assert ei.value.code == 4
+    assert e.query_status() == 3  # Query: kNotSupported
+    # FLAT, few docs, not "indexed": allowed because max_docid <= 100 (brute_force_search_threshold)
+    res = e.search(xq[:1], 5)
+    assert keys_of(res) == [["a"]] or keys_of(res) == [["a"]]
+    e.close()
+
+
+def test_delete_update_getdoc(tmp_path, data):
+    db, xq = data
+    e = make_engine(tmp_path, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 1000})
+    add_all(e, db[:3000])
+    e.wait_indexed(3000)
+    base = keys_of(e.search(xq, 5, index_params={"nprobe": 16}))
+    victim = base[0][0]
+    assert e.delete_doc(victim) == 0 and e.delete_doc(victim) == -1  # key mapping removed (table_->Delete)
+    assert e.status()["doc_num"] == 2999
+    after = keys_of(e.search(xq, 5, index_params={"nprobe": 16}))
+    assert victim not in after[0]
+    vid = int(victim[3:])
+    alive = np.ones(3000, bool)
+    alive[vid] = False
+    delb = np.packbits(~alive, bitorder="little")
+    do, io = orc.flat_search(db[:3000], xq, 5, L2, del_bitmap=delb)
+    assert after == [[f"doc{i}" for i in row] for row in io]  # nprobe == nlist => exact
+    rc, doc = e.get_doc_by_id(victim)
+    assert rc == -1 and doc == {}
+    rc, doc = e.get_doc_by_id("doc5")
+    assert rc == 0 and doc["_id"][0] == b"doc5" and doc["tag"][0] == b"t5"
+    assert np.array_equal(np.frombuffer(doc["emb"][0], np.float32), db[5]) and doc["emb"][1] == wire.DT_VECTOR
+    rc, doc = e.get_doc_by_docid(vid - 1, next_=True)  # next undeleted docid after vid-1 skips the victim
+    assert rc == 0 and int.from_bytes(doc["_docid"][0], "little") == vid + 1
+    assert e.get_doc_by_docid(vid)[0] == -1 and e.get_doc_by_docid(10 ** 6)[0] == -1
+    # update: same key, new vector -> old entry tombstoned, new vector searchable (engine.cc:774-850)
+    target = xq[3] + 1.0
+    assert e.add_doc("doc7", target) == 0
+    assert e.status()["doc_num"] == 2999
+    res = e.search(xq[3:4], 1, index_params={"nprobe": 16})
+    assert keys_of(res) == [["doc7"]] and scores_of(res)[0][0] == float(D)
+    rc, doc = e.get_doc_by_id("doc7")
+    assert np.array_equal(np.frombuffer(doc["emb"][0], np.float32), target)
+    # re-adding a deleted key creates a fresh doc
+    assert e.add_doc(victim, db[vid]) == 0
+    e.wait_indexed(3001)
+    assert e.status()["doc_num"] == 3000 and e.status()["max_docid"] == 3000
+    e.close()
+
+
+@pytest.mark.parametrize("index_type,params", [
+    ("FLAT", {"metric_type": "InnerProduct"}),
+    ("IVFPQ", {"ncentroids": 16, "nprobe": 16, "nsubvector": 8, "metric_type": "L2", "training_threshold": 1000}),
+])
+def test_flat_ip_and_ivfpq_tables(tmp_path, data, index_type, params):
+    db, xq = data
+    e = make_engine(tmp_path, index_type, params)
+    add_all(e, db[:2500])
+    assert e.build_index() == 0 and e.build_index() == 0  # idempotent while running (engine.cc:953-976)
+    e.wait_indexed(2500)
+    if index_type == "FLAT":
+        res = e.search(xq, 10)
+        do, io = orc.flat_search(db[:2500], xq, 10, IP)
+        assert np.array_equal(np.array(scores_of(res), np.float32), do)
+        assert all(sorted(a) == sorted(f"doc{i}" for i in b) for a, b in zip(keys_of(res), io))
+    else:
+        res = e.search(xq, 10, index_params={"nprobe": 16, "recall_num": 100})
+        _, gt = orc.flat_search(db[:2500], xq, 1, L2)
+        got = keys_of(res)
+        assert np.mean([f"doc{gt[q, 0]}" in got[q] for q in range(NQ)]) >= 0.9
+        for q in range(NQ):  # re-ranked scores are exact
+            assert scores_of(res)[q][0] == float(((xq[q] - db[int(got[q][0][3:])]) ** 2).sum())
+    e.close()
+
+
+def test_dump_load_roundtrip(tmp_path, data):
+    db, xq = data
+    params = {"ncentroids": 16, "nprobe": 4, "metric_type": "L2", "training_threshold": 1000}
+    e = make_engine(tmp_path, "IVFFLAT", params)
+    add_all(e, db[:2000])
+    e.wait_indexed(2000)
+    e.delete_doc("doc11")
+    before = e.search(xq, 10, index_params={"nprobe": 4})
+    assert e.dump() == 0
+    e.close()
+    e2 = make_engine(tmp_path, "IVFFLAT", params)  # gammacb.New: CreateTable then Load (gamma.go:104-130)
+    assert e2.load() == 0
+    e2.wait_indexed(2000)
+    assert e2.status()["doc_num"] == 1999
+    after = e2.search(xq, 10, index_params={"nprobe": 4})
+    assert keys_of(after) == keys_of(before) and scores_of(after) == scores_of(before)
+    assert e2.get_doc_by_id("doc11")[0] == -1 and e2.get_doc_by_id("doc12")[0] == 0
+    e2.close()
+
+
+def test_kill_switch_and_config(tmp_path, data):
+    db, xq = data
+    E = eng_mod()
+    e = make_engine(tmp_path, "FLAT", {"metric_type": "L2"})
+    add_all(e, db[:50])
+    api = E._api()
+    api.SetKillStatus(b"rq-1", 9, 1)
+    with pytest.raises(E.GammaStatusError) as ei:  # killed request -> MemoryExceeded, code 8 (reader.go:170-174)
+        e.search(xq[:1], 3, request_id="rq-1", partition_id=9)
+    assert ei.value.code == 8
+    assert len(e.search(xq[:1], 3, request_id="rq-2", partition_id=9)[0]["items"]) == 3
+    api.DeleteKillStatus(b"rq-1", 9)
+    assert len(e.search(xq[:1], 3, request_id="rq-1", partition_id=9)[0]["items"]) == 3
+    assert e.set_config({"refresh_interval": 50, "slow_search_time": 7}) == 0
+    cfg = e.get_config()
+    assert cfg["refresh_interval"] == 50 and cfg["slow_search_time"] == 7
+    e.close()
+
+
+def test_concurrent_search_while_adding(tmp_path, data):
+    db, xq = data
+    e = make_engine(tmp_path, "IVFFLAT", {"ncentroids": 16, "nprobe": 8, "metric_type": "L2", "training_threshold": 1000})
+    add_all(e, db[:2000])
+    e.wait_indexed(2000)
+    errors = []
+
+    def searcher():
+        try:
+            for _ in range(30):
+                res = e.search(xq[:4], 5, index_params={"nprobe": 8})
+                assert all(len(r["items"]) == 5 for r in res)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    ts = [threading.Thread(target=searcher) for _ in range(4)]
+    for t in ts:
+        t.start()
+    add_all(e, db[2000:4000], start=2000)  # raft apply thread keeps writing (raft_state_machine.go:128)
+    for t in ts:
+        t.join()
+    assert not errors
+    e.wait_indexed(4000)
+    res = keys_of(e.search(db[3999:4000], 1, index_params={"nprobe": 16}))
+    assert res == [["doc3999"]]
+    e.close()

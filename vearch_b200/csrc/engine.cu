@@ -123,6 +123,7 @@ Engine::~Engine() {
   // Close: stop the indexing thread (search/engine.cc Engine::~Engine / Close)
   int st = indexing_state_.load();
   if (st != 0) indexing_state_.store(3);
+  idx_cv_.notify_all();
   if (indexing_thread_.joinable()) indexing_thread_.join();
   cudaSetDevice(device_);
   index_.reset();
@@ -412,8 +413,10 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   int total_docs;
   {
     std::unique_lock<std::shared_mutex> wl(mu_, std::defer_lock);
-    std::shared_lock<std::shared_mutex> rl(mu_, std::defer_lock);
-    if (pending_n_ > 0) {
+    std::shared_lock<std::shared_mutex> rl(mu_);
+    bool need_flush = pending_n_ > 0;
+    rl.unlock();
+    if (need_flush) {
       wl.lock();
       if (flush_pending_locked()) return Status::Make(kIndexError, last_error());
       wl.unlock();

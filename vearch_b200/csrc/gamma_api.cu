@@ -178,3 +178,133 @@ void DeleteKillStatus(const char* request_id, int partition_id) {
 }
 
 }  // extern "C"
+
+// ---- host-logic test hooks (declared in include/gamma_b200_index.h): exercise the wire codecs
+// without a GPU so the CPU test suite can pin them against golden bytes -------------------------
+#include "wire.h"
+
+static std::string hex_escape(const std::string& s) { return gb::json_escape(s); }
+
+extern "C" {
+
+int gb_debug_parse_search_request(const char* buf, int len, char** json_out, int* out_len) {
+  gb::SearchRequestPB r;
+  bool ok = r.parse(reinterpret_cast<const uint8_t*>(buf), (size_t)len);
+  std::string j = "{";
+  j += "\"ok\":" + std::string(ok ? "true" : "false");
+  j += ",\"request_id\":\"" + hex_escape(r.request_id) + "\"";
+  j += ",\"partition_id\":" + std::to_string(r.partition_id);
+  j += ",\"req_num\":" + std::to_string(r.req_num);
+  j += ",\"topn\":" + std::to_string(r.topn);
+  j += ",\"brute_force_search\":" + std::to_string(r.brute_force_search);
+  j += ",\"index_params\":\"" + hex_escape(r.index_params) + "\"";
+  j += ",\"multi_vector_rank\":" + std::to_string(r.multi_vector_rank);
+  j += ",\"l2_sqrt\":" + std::string(r.l2_sqrt ? "true" : "false");
+  j += ",\"trace\":" + std::string(r.trace ? "true" : "false");
+  j += ",\"offset\":" + std::to_string(r.offset);
+  j += ",\"n_range_filters\":" + std::to_string(r.n_range_filters);
+  j += ",\"n_term_filters\":" + std::to_string(r.n_term_filters);
+  j += ",\"fields\":[";
+  for (size_t i = 0; i < r.fields.size(); i++) j += (i ? ",\"" : "\"") + hex_escape(r.fields[i]) + "\"";
+  j += "],\"vec_fields\":[";
+  for (size_t i = 0; i < r.vec_fields.size(); i++) {
+    auto& v = r.vec_fields[i];
+    char nb[128];
+    snprintf(nb, sizeof nb, "%.17g,\"max_score\":%.17g", v.has_min ? v.min_score : 0.0, v.has_max ? v.max_score : 0.0);
+    j += std::string(i ? "," : "") + "{\"name\":\"" + hex_escape(v.name) + "\",\"value_len\":" +
+         std::to_string(v.value.size()) + ",\"index_type\":\"" + hex_escape(v.index_type) + "\",\"min_score\":" + nb + "}";
+  }
+  j += "]}";
+  out_buffer(j, json_out, out_len);
+  return ok ? 0 : -1;
+}
+
+// flatbuffers Doc -> re-serialised with the C++ builder (reader + builder round trip)
+int gb_debug_roundtrip_doc(const char* buf, int len, char** out, int* out_len) {
+  gb::FbTable d = gb::FbTable::root(reinterpret_cast<const uint8_t*>(buf), (size_t)len);
+  if (!d.ok()) return -1;
+  gb::FbBuilder b;
+  std::vector<gb::FbBuilder::Off> offs;
+  for (size_t i = 0; i < d.vec_len(0); i++) {
+    gb::FbTable f = d.vec_table(0, i);
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    f.bytes(1, &p, &n);
+    gb::FbBuilder::Off v = b.create_bytes(p, n, false);
+    gb::FbBuilder::Off nm = b.create_string(f.str(0));
+    b.start_table(3);
+    b.add_offset(0, nm);
+    b.add_offset(1, v);
+    int8_t dt = f.scalar<int8_t>(2, 0);
+    if (dt) b.add_scalar<int8_t>(2, dt);
+    offs.push_back(b.end_table());
+  }
+  gb::FbBuilder::Off fv = b.create_offset_vector(offs);
+  b.start_table(1);
+  b.add_offset(0, fv);
+  b.finish(b.end_table());
+  out_buffer(std::string(reinterpret_cast<const char*>(b.data()), b.size()), out, out_len);
+  return 0;
+}
+
+// flatbuffers Table -> JSON summary of what CreateTable would see
+int gb_debug_parse_table(const char* buf, int len, char** json_out, int* out_len) {
+  gb::FbTable t = gb::FbTable::root(reinterpret_cast<const uint8_t*>(buf), (size_t)len);
+  if (!t.ok()) return -1;
+  std::string j = "{\"name\":\"" + hex_escape(t.str(0)) + "\",\"fields\":[";
+  for (size_t i = 0; i < t.vec_len(1); i++) {
+    gb::FbTable f = t.vec_table(1, i);
+    j += std::string(i ? "," : "") + "{\"name\":\"" + hex_escape(f.str(0)) + "\",\"data_type\":" +
+         std::to_string((int)f.scalar<int8_t>(1, 0)) + ",\"is_index\":" + std::to_string((int)f.scalar<uint8_t>(2, 0)) + "}";
+  }
+  j += "],\"vectors\":[";
+  for (size_t i = 0; i < t.vec_len(2); i++) {
+    gb::FbTable v = t.vec_table(2, i);
+    j += std::string(i ? "," : "") + "{\"name\":\"" + hex_escape(v.str(0)) + "\",\"dimension\":" +
+         std::to_string(v.scalar<int32_t>(3, 0)) + ",\"store_type\":\"" + hex_escape(v.str(4)) + "\"}";
+  }
+  j += "],\"refresh_interval\":" + std::to_string(t.scalar<int32_t>(5, 1000));
+  j += ",\"enable_id_cache\":" + std::to_string((int)t.scalar<uint8_t>(6, 0));
+  j += ",\"enable_realtime\":" + std::to_string((int)t.scalar<uint8_t>(7, 0));
+  j += ",\"indexes\":[";
+  for (size_t i = 0; i < t.vec_len(8); i++) {
+    gb::FbTable ix = t.vec_table(8, i);
+    j += std::string(i ? "," : "") + "{\"name\":\"" + hex_escape(ix.str(0)) + "\",\"type\":\"" + hex_escape(ix.str(1)) +
+         "\",\"field_name\":\"" + hex_escape(ix.str(2)) + "\",\"params\":\"" + hex_escape(ix.str(4)) + "\"}";
+  }
+  j += "]}";
+  out_buffer(j, json_out, out_len);
+  return 0;
+}
+
+// SearchResponse encoder check: one result with the given scores/keys
+int gb_debug_encode_response(int nq, int k, const double* scores, const char* const* keys, int total, char** out,
+                             int* out_len) {
+  gb::PbWriter resp;
+  for (int i = 0; i < nq; i++) {
+    gb::PbWriter sr, items;
+    double mx = -1.7976931348623157e308;
+    for (int j = 0; j < k; j++) {
+      gb::PbWriter item, fld;
+      double s = scores[i * k + j];
+      if (s > mx) mx = s;
+      item.put_double(1, s);
+      fld.put_string(1, "_id");
+      fld.put_bytes(3, keys[i * k + j], strlen(keys[i * k + j]));
+      item.put_message(2, fld.out);
+      items.put_message(7, item.out);
+    }
+    sr.put_double(2, mx);
+    gb::PbWriter st;
+    st.put_int32(1, total);
+    st.put_int32(3, total);
+    sr.put_message(5, st.out);
+    sr.put_string(6, "OK");
+    sr.out += items.out;
+    resp.put_message(2, sr.out);
+  }
+  out_buffer(resp.out, out, out_len);
+  return 0;
+}
+
+}  // extern "C"

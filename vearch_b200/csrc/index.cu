@@ -629,6 +629,7 @@ int IVFFlatIndex::get_centroids(float* host) const {
 
 // GammaIVFFlatIndex::Indexing (gamma_index_ivfflat.cc:342-411): train on the FIRST num vectors.
 int IVFFlatIndex::train() {
+  std::lock_guard<std::mutex> bg(build_mu_);
   if (trained_) return 0;
   cudaSetDevice(device_);
   int64_t num = training_threshold();
@@ -709,6 +710,7 @@ int IVFFlatIndex::index_batch(const float* x, int64_t n, int64_t vid0, const uin
 }
 
 int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
+  std::lock_guard<std::mutex> bg(build_mu_);
   if (!trained_) return 0;
   cudaSetDevice(device_);
   const int64_t BATCH = 1 << 20;
@@ -732,6 +734,7 @@ int Index::update_vector(int64_t vid, const float* x) {
 // GammaIVFFlatIndex::Update / GammaIVFPQIndex::Update (gamma_index_ivfflat.cc:476-522,
 // gamma_index_ivfpq.cc:402-453): tombstone the old entry, append the new vector to its list.
 int IVFFlatIndex::update_vector(int64_t vid, const float* x) {
+  std::lock_guard<std::mutex> bg(build_mu_);
   if (Index::update_vector(vid, x)) return -1;
   if (!trained_ || vid >= indexed_count_) return 0;  // not indexed yet: the add path will pick it up
   if (vid < (int64_t)vid2pos_.size() && vid2pos_[vid] != ~(uint64_t)0) {

@@ -198,6 +198,7 @@ class Index {
   int64_t indexed_count_ = 0;
   bool trained_ = false;
   mutable std::shared_mutex mu_;  // searches shared, index mutation exclusive
+  std::mutex build_mu_;           // serialises train / add_pending / update_vector (one writer at a time)
   cudaStream_t build_stream_ = nullptr;
   void scan_timer_begin(cudaStream_t st);
   void scan_timer_end(cudaStream_t st);
