@@ -245,7 +245,7 @@ def main():
     nq = args.nq or wl["nq"]
     k = args.k
     nprobe = args.nprobe or wl["nprobe"]
-    recall_num = args.recall_num if args.recall_num >= 0 else (100 if wl["type"] == "IVFPQ" else 0)
+    recall_num = args.recall_num if args.recall_num >= 0 else (400 if wl["type"] == "IVFPQ" else 0)
     idx, params, build = build_index(args, wl, rank, local)
     if wl["type"] != "FLAT":
         nprobe = min(nprobe, params["ncentroids"])
@@ -484,8 +484,13 @@ def main():
                        "l2": "512 MiB write between timed steps + distinct query batch per step",
                        "build_seconds": build},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * wl["d"] * 4,
-                    "d2h_bytes_per_step": nq * k * 12, "cabi_host_call_qps": cabi_qps},
+            # N=1: the reference-facing C-ABI call gb_index_search(host queries -> host results), H2D/D2H inside;
+            # N>1: pinned-host H2D -> search -> NCCL all-gather + merge -> D2H through the Python API
+            "e2e": {"value": cabi_qps if cabi_qps else e2e_value, "unit": "queries/s",
+                    "h2d_bytes_per_step": nq * wl["d"] * 4, "d2h_bytes_per_step": nq * k * 12,
+                    "path": "gb_index_search C-ABI, host buffers" if cabi_qps else
+                            "pinned H2D + search_device + all_gather/merge + D2H",
+                    "pinned_h2d_search_d2h_qps": e2e_value},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu}

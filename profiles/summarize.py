@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Turns the raw ncu artefacts brought back in gpurun_out/ into the small text summaries that
+are committed under profiles/ (the .ncu-rep files themselves stay in gpurun_out/, untracked).
+
+    python profiles/summarize.py launches gpurun_out/r1_launches_ivfflat_1m.csv  > profiles/r1_launches_ivfflat_1m.txt
+    python profiles/summarize.py full     gpurun_out/r1_prof_ivfflat_scan.ncu-rep > profiles/r1_ncu_ivfflat_scan.txt
+"""
+import csv
+import io
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+    "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+]
+
+
+def launches(path):
+    rows = []
+    with open(path) as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            ns = float(r["Metric Value"].replace(",", ""))
+            if r.get("Metric Unit") == "us":
+                ns *= 1e3
+            elif r.get("Metric Unit") == "ms":
+                ns *= 1e6
+            rows.append((r["Kernel Name"].split("(")[0][-90:], ns))
+    agg = OrderedDict()
+    for name, ns in rows:
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += ns
+    total = sum(v[1] for v in agg.values())
+    print(f"# {path}: {len(rows)} launches, {total / 1e6:.3f} ms total (ncu per-launch times: cold-cache, serialised -> compare SHARES)")
+    print(f"{'kernel':92s} {'launches':>8s} {'ms':>10s} {'share':>7s}")
+    for name, (cnt, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{name:92s} {cnt:8d} {ns / 1e6:10.3f} {ns / total:7.3f}")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    print(f"# {path}")
+    for vals in rows[2:]:
+        name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        print(f"## {name[:140]}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"{k:80s} {vals[i]:>18s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

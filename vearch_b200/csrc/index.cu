@@ -776,8 +776,9 @@ int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int me
   int nparts = ivfflat_scan_nparts(nprobe, lists_->max_len());
   GB_ALLOC(partial, unsigned long long, (size_t)nq * nparts * k, s);
   scan_timer_begin(st);
-  GB_CUDA(launch_ivfflat_scan(xq, dpad_, nq, dpad_, probe_ids, nprobe, lists_->directory(), lists_->max_len(), k, metric,
-                              f, partial, nullptr, st));
+  int avg_len = (int)(lists_->total() / std::max(1, nlist_));
+  GB_CUDA(launch_ivfflat_scan(xq, dpad_, nq, dpad_, probe_ids, nprobe, lists_->directory(), lists_->max_len(), avg_len, k,
+                              metric, f, partial, &nparts, st));
   scan_timer_end(st);
   GB_CUDA(launch_select_keys(partial, (int64_t)nparts * k, nq, nparts * k, k, out_keys, k, st));
   return 0;

@@ -52,9 +52,10 @@ struct ListDirectory {            // device-resident mirror of RTInvertIndex (T1
   const int* len;                 // [nlist] published length
   int nlist;
 };
-// partial[q][part][k], part = probe*nsplit + split.  One CTA per (query, probe, split).
+// partial[q][part][k]; *nparts_out (<= ivfflat_scan_nparts) = parts actually written per query.
+// One CTA per (query, group of (probe, split) work items).
 cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, const int32_t* probe_ids, int nprobe,
-                                ListDirectory dir, int max_list_len, int k, int metric, FilterArgs f,
+                                ListDirectory dir, int max_list_len, int avg_list_len, int k, int metric, FilterArgs f,
                                 unsigned long long* partial, int* nparts_out, cudaStream_t st);
 int ivfflat_scan_nparts(int nprobe, int max_list_len);
 

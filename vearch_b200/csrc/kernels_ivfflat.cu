@@ -177,39 +177,59 @@ void ivf_cq_geometry(int k, int T, int* KP, int* SORTN) {
 // conflict-free without rotation and the query chunks sit in registers (4*J floats per lane).
 // One __syncthreads_count per tile both releases the stage and gives every thread the same
 // upper bound on the queue fill, so the flush decision needs no second barrier.
+constexpr int IVF_MAX_PG = 32;  // work items (probe, split) per CTA
+
 template <int METRIC, int LPR, int J>
 __global__ void __launch_bounds__(IVF_NT)
     ivfflat_scan_fast_kernel(const float* __restrict__ xq, int64_t ldq, const int32_t* __restrict__ probe_ids,
-                             int nprobe, int nsplit, ListDirectory dir, int R, int k, int KP, int SORTN, FilterArgs f,
-                             unsigned long long* __restrict__ partial) {
+                             int nprobe, int nsplit, int pg, ListDirectory dir, int R, int nst, int k, int KP, int SORTN,
+                             FilterArgs f, unsigned long long* __restrict__ partial) {
   constexpr int S = LPR * J;        // float4 per row
   constexpr int G = IVF_NT / LPR;   // rows per round
   constexpr int ROW_BYTES = S * 16;
   const int T = G * R;
   const int stage_bytes = T * ROW_BYTES;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)IVF_NST * stage_bytes);
-  __shared__ __align__(8) uint64_t full_bar[IVF_NST];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)nst * stage_bytes);
+  __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
+  __shared__ int g_list[IVF_MAX_PG], g_r0[IVF_MAX_PG], g_r1[IVF_MAX_PG], g_tile0[IVF_MAX_PG + 1];
 
   const int tid = threadIdx.x;
-  const int q = blockIdx.y;
-  const int part = blockIdx.x;
-  const int probe = part / nsplit, split = part - probe * nsplit;
-  unsigned long long* out = partial + ((int64_t)q * gridDim.x + part) * k;
+  const int q = blockIdx.y, grp_id = blockIdx.x;
+  unsigned long long* out = partial + ((int64_t)q * gridDim.x + grp_id) * k;
+  const int nitems = nprobe * nsplit;
+  const int i0 = grp_id * pg;
+  const int ni = min(pg, nitems - i0);
 
-  const int list = probe_ids[(int64_t)q * nprobe + probe];
-  int len = 0;
-  if (list >= 0 && list < dir.nlist) len = dir.len[list];
-  const int r0 = split * IVF_CHUNK_ROWS;
-  const int r1 = min(len, r0 + IVF_CHUNK_ROWS);
-  if (r0 >= r1) {
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < ni; i++) {
+      const int item = i0 + i;
+      const int probe = item / nsplit, split = item - probe * nsplit;
+      const int list = probe_ids[(int64_t)q * nprobe + probe];
+      int len = 0;
+      if (list >= 0 && list < dir.nlist) len = dir.len[list];  // key < 0: "not enough centroids" (ivfflat.cc:653)
+      const int r0 = split * IVF_CHUNK_ROWS;
+      const int r1 = min(len, r0 + IVF_CHUNK_ROWS);
+      g_list[i] = list;
+      g_r0[i] = r0;
+      g_r1[i] = r1 > r0 ? r1 : r0;
+      g_tile0[i] = acc;
+      acc += r1 > r0 ? (r1 - r0 + T - 1) / T : 0;
+    }
+    g_tile0[ni > 0 ? ni : 0] = acc;
+    for (int s = 0; s < nst; s++) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  CandQueue cq{buf, &s_cnt, &s_tau, k, KP, SORTN};
+  cq.init();  // __syncthreads inside
+  const int total_tiles = ni > 0 ? g_tile0[ni] : 0;
+  if (total_tiles == 0) {
     for (int i = tid; i < k; i += IVF_NT) out[i] = kKeySentinel;
     return;
   }
-  const float* __restrict__ lvecs = dir.vecs[list];
-  const int64_t* __restrict__ lids = dir.ids[list];
 
   const int grp = tid / LPR, p = tid % LPR;
   float4 qreg[J];
@@ -218,29 +238,38 @@ __global__ void __launch_bounds__(IVF_NT)
 #pragma unroll
     for (int j = 0; j < J; j++) qreg[j] = __ldg(q4 + p + LPR * j);
   }
-  CandQueue cq{buf, &s_cnt, &s_tau, k, KP, SORTN};
-  if (tid == 0) {
-    for (int s = 0; s < IVF_NST; s++) mbar_init(&full_bar[s], 1);
-    mbar_fence_init();
-  }
-  cq.init();
 
-  const int ntiles = (r1 - r0 + T - 1) / T;
-  auto issue = [&](int t) {
-    int s = t % IVF_NST;
-    int rows = min(T, r1 - (r0 + t * T));
-    uint32_t bytes = (uint32_t)rows * ROW_BYTES;
+  // producer (thread 0): walks the same (item, tile) sequence NST tiles ahead of the consumers,
+  // so the ring keeps streaming across list boundaries
+  int pr_pi = 0;
+  auto issue = [&](int gt) {
+    while (gt >= g_tile0[pr_pi + 1]) pr_pi++;
+    const int ti = gt - g_tile0[pr_pi];
+    const int row0 = g_r0[pr_pi] + ti * T;
+    const int rows = min(T, g_r1[pr_pi] - row0);
+    const uint32_t bytes = (uint32_t)rows * ROW_BYTES;
+    const int s = gt % nst;
     mbar_arrive_expect_tx(&full_bar[s], bytes);
-    bulk_g2s(smem_raw + (size_t)s * stage_bytes, lvecs + (int64_t)(r0 + t * T) * (S * 4), bytes, &full_bar[s]);
+    bulk_g2s(smem_raw + (size_t)s * stage_bytes, dir.vecs[g_list[pr_pi]] + (int64_t)row0 * (S * 4), bytes, &full_bar[s]);
   };
   if (tid == 0)
-    for (int t = 0; t < IVF_NST && t < ntiles; t++) issue(t);
+    for (int gt = 0; gt < nst && gt < total_tiles; gt++) issue(gt);
 
+  int pi = 0;
+  const int64_t* __restrict__ lids = nullptr;
+  int cur = -1;
   int est = 0;  // upper bound of the queue fill, identical in every thread
-  for (int t = 0; t < ntiles; t++) {
-    const int s = t % IVF_NST;
-    mbar_wait(&full_bar[s], (t / IVF_NST) & 1);
-    const int tile_rows = min(T, r1 - (r0 + t * T));
+  for (int gt = 0; gt < total_tiles; gt++) {
+    while (gt >= g_tile0[pi + 1]) pi++;
+    if (pi != cur) {
+      cur = pi;
+      lids = dir.ids[g_list[pi]];
+    }
+    const int ti = gt - g_tile0[pi];
+    const int row0 = g_r0[pi] + ti * T;
+    const int tile_rows = min(T, g_r1[pi] - row0);
+    const int s = gt % nst;
+    mbar_wait(&full_bar[s], (gt / nst) & 1);
     const unsigned long long tau = s_tau;
     const uint32_t tau_hi = (uint32_t)(tau >> 32);
     const float4* st4 = reinterpret_cast<const float4*>(smem_raw + (size_t)s * stage_bytes);
@@ -273,7 +302,7 @@ __global__ void __launch_bounds__(IVF_NT)
         uint32_t ord = score2ord<METRIC>(dis);
         pred = ord <= tau_hi;
         if (pred) {
-          int64_t raw = lids[r0 + t * T + rit];
+          int64_t raw = lids[row0 + rit];
           pred = raw >= 0;  // top bit set => tombstone (gamma_index_ivfflat.h:72)
           uint32_t vid = (uint32_t)raw;
           if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
@@ -286,8 +315,8 @@ __global__ void __launch_bounds__(IVF_NT)
     }
     // stage s consumed + pushes done; the count is the same value in every thread
     est += __syncthreads_count(pushed) * R;
-    if (tid == 0 && t + IVF_NST < ntiles) issue(t + IVF_NST);
-    if (t + 1 < ntiles && est + T > cq.cap()) {
+    if (tid == 0 && gt + nst < total_tiles) issue(gt + nst);
+    if (gt + 1 < total_tiles && est + T > cq.cap()) {
       cq.flush();
       est = 0;
     }
@@ -297,25 +326,47 @@ __global__ void __launch_bounds__(IVF_NT)
   for (int i = tid; i < k; i += IVF_NT) out[i] = buf[i];
 }
 
+struct FastCfg {
+  int pg, nst, stage_bytes;
+};
+inline FastCfg fast_cfg(int nprobe, int nsplit, int avg_len) {
+  FastCfg c;
+  c.stage_bytes = 8 * 1024;
+  c.nst = 4;
+  // ~4096 rows of work per CTA: enough tiles to amortise start-up, enough CTAs to balance
+  int per = avg_len > 0 ? 4096 / avg_len : 1;
+  c.pg = per < 1 ? 1 : (per > IVF_MAX_PG ? IVF_MAX_PG : per);
+  if (nsplit > 1) c.pg = 1;
+  if (const char* e = getenv("GB_IVF_STAGE_KB")) c.stage_bytes = atoi(e) * 1024;
+  if (const char* e = getenv("GB_IVF_NST")) c.nst = atoi(e);
+  if (const char* e = getenv("GB_IVF_PG")) c.pg = atoi(e);
+  if (c.nst < 2) c.nst = 2;
+  if (c.nst > 8) c.nst = 8;
+  if (c.pg < 1) c.pg = 1;
+  if (c.pg > IVF_MAX_PG) c.pg = IVF_MAX_PG;
+  if (c.pg > nprobe * nsplit) c.pg = nprobe * nsplit;
+  return c;
+}
+
 template <int METRIC, int LPR, int J>
 cudaError_t launch_fast(const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe, int nsplit,
-                        ListDirectory dir, int k, FilterArgs f, unsigned long long* partial, cudaStream_t st) {
+                        FastCfg c, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
+                        cudaStream_t st) {
   constexpr int S = LPR * J, G = IVF_NT / LPR, ROW_BYTES = S * 16;
-  int stage_target = IVF_STAGE_BYTES;
-  if (const char* e = getenv("GB_IVF_STAGE_KB")) stage_target = atoi(e) * 1024;
-  int R = stage_target / (G * ROW_BYTES);
+  int R = c.stage_bytes / (G * ROW_BYTES);
   if (R < 1) R = 1;
   const int T = G * R;
   int KP, SORTN;
   ivf_cq_geometry(k, T, &KP, &SORTN);
-  size_t smem = (size_t)IVF_NST * T * ROW_BYTES + (size_t)SORTN * 8;
+  size_t smem = (size_t)c.nst * T * ROW_BYTES + (size_t)SORTN * 8;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(ivfflat_scan_fast_kernel<METRIC, LPR, J>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid(nprobe * nsplit, nq);
-  ivfflat_scan_fast_kernel<METRIC, LPR, J><<<grid, IVF_NT, smem, st>>>(xq, ldq, probe_ids, nprobe, nsplit, dir, R, k, KP,
-                                                                       SORTN, f, partial);
+  const int nitems = nprobe * nsplit;
+  dim3 grid((nitems + c.pg - 1) / c.pg, nq);
+  ivfflat_scan_fast_kernel<METRIC, LPR, J><<<grid, IVF_NT, smem, st>>>(xq, ldq, probe_ids, nprobe, nsplit, c.pg, dir, R,
+                                                                       c.nst, k, KP, SORTN, f, partial);
   note_launch();
   return cudaGetLastError();
 }
@@ -323,9 +374,9 @@ cudaError_t launch_fast(const float* xq, int64_t ldq, int nq, const int32_t* pro
 // returns cudaErrorNotSupported when no instantiation fits (caller falls back to the generic kernel)
 template <int METRIC>
 cudaError_t dispatch_fast(int S, const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe,
-                          int nsplit, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
+                          int nsplit, FastCfg c, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
                           cudaStream_t st) {
-#define GB_FAST(LPR, J)   if (S == (LPR) * (J)) return launch_fast<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, dir, k, f, partial, st)
+#define GB_FAST(LPR, J)   if (S == (LPR) * (J)) return launch_fast<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, c, dir, k, f, partial, st)
   GB_FAST(8, 1);   // d = 32
   GB_FAST(8, 2);   // d = 64
   GB_FAST(8, 3);   // d = 96
@@ -356,7 +407,7 @@ int ivfflat_scan_nparts(int nprobe, int max_list_len) {
 }
 
 cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, const int32_t* probe_ids, int nprobe,
-                                ListDirectory dir, int max_list_len, int k, int metric, FilterArgs f,
+                                ListDirectory dir, int max_list_len, int avg_list_len, int k, int metric, FilterArgs f,
                                 unsigned long long* partial, int* nparts_out, cudaStream_t st) {
   if (nq <= 0 || nprobe <= 0) return cudaSuccess;
   if ((d & 3) || k <= 0 || k > 4096 || nq > 65535) return cudaErrorInvalidValue;
@@ -365,11 +416,15 @@ cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, con
   int nsplit = nparts / nprobe;
   if (nparts_out) *nparts_out = nparts;
   if (ldq % 4 == 0 && !getenv("GB_IVF_GENERIC")) {
-    cudaError_t fe = metric == kMetricL2 ? dispatch_fast<kMetricL2>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, dir,
-                                                                    k, f, partial, st)
-                                         : dispatch_fast<kMetricIP>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, dir,
-                                                                    k, f, partial, st);
-    if (fe != cudaErrorNotSupported) return fe;
+    FastCfg c = fast_cfg(nprobe, nsplit, avg_list_len);
+    cudaError_t fe = metric == kMetricL2 ? dispatch_fast<kMetricL2>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, c,
+                                                                    dir, k, f, partial, st)
+                                         : dispatch_fast<kMetricIP>(d >> 2, xq, ldq, nq, probe_ids, nprobe, nsplit, c,
+                                                                    dir, k, f, partial, st);
+    if (fe != cudaErrorNotSupported) {
+      if (nparts_out) *nparts_out = (nparts + c.pg - 1) / c.pg;  // partial[q][group][k]
+      return fe;
+    }
   }
   int KP, SORTN;
   ivf_cq_geometry(k, g.T, &KP, &SORTN);
