@@ -331,8 +331,10 @@ struct FastCfg {
 };
 inline FastCfg fast_cfg(int nprobe, int nsplit, int avg_len) {
   FastCfg c;
+  // measured on B200 (gpurun_out/cfg_sweep.log): resident CTAs matter more than ring depth --
+  // 8 KiB x 2 stages: 59 ms, x3: 62 ms, x4: 74 ms, x6: 100 ms, 16 KiB x 4: 91 ms (C2, nq = 10 k)
   c.stage_bytes = 8 * 1024;
-  c.nst = 4;
+  c.nst = 2;
   // ~4096 rows of work per CTA: enough tiles to amortise start-up, enough CTAs to balance
   int per = avg_len > 0 ? 4096 / avg_len : 1;
   c.pg = per < 1 ? 1 : (per > IVF_MAX_PG ? IVF_MAX_PG : per);
