@@ -16,6 +16,7 @@
 // Algorithmic bytes: (4*d + 8) per scanned entry; roofline: HBM.
 #include <float.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(IVF_NT)
 
 struct FastCfg {
   int pg, nst, stage_bytes;
+  int warp_mode;  // 1: warp-autonomous kernel (per-warp TMA rings), 0: block-synchronous ring
 };
 inline FastCfg fast_cfg(int nprobe, int nsplit, int avg_len) {
   FastCfg c;
@@ -335,6 +337,12 @@ inline FastCfg fast_cfg(int nprobe, int nsplit, int avg_len) {
   // 8 KiB x 2 stages: 59 ms, x3: 62 ms, x4: 74 ms, x6: 100 ms, 16 KiB x 4: 91 ms (C2, nq = 10 k)
   c.stage_bytes = 8 * 1024;
   c.nst = 2;
+  c.warp_mode = 0;
+  if (const char* e = getenv("GB_IVF_MODE")) c.warp_mode = !strcmp(e, "warp");
+  if (c.warp_mode) {  // per-warp rings: 4 KiB per warp per slot, 3 slots
+    c.stage_bytes = 16 * 1024;
+    c.nst = 3;
+  }
   // ~4096 rows of work per CTA: enough tiles to amortise start-up, enough CTAs to balance
   int per = avg_len > 0 ? 4096 / avg_len : 1;
   c.pg = per < 1 ? 1 : (per > IVF_MAX_PG ? IVF_MAX_PG : per);
@@ -373,12 +381,225 @@ cudaError_t launch_fast(const float* xq, int64_t ldq, int nq, const int32_t* pro
   return cudaGetLastError();
 }
 
+// ---- warp-autonomous variant ---------------------------------------------------------------
+// Same work decomposition as the fast kernel (one CTA per query x group of (probe, split) items,
+// flat tile sequence), but every WARP owns its slice of the tile sequence (tiles w, w+4, ...), its
+// own ring of TMA bulk copies with its own mbarriers (lane 0 produces), its own threshold and its
+// own candidate queue (count and tau live in registers, pushes are ballot-compacted, flushes are
+// warp-level bitonic sorts).  No block-wide barrier exists until the final 4-way merge, so a warp
+// never waits for another warp's memory latency.
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long* a, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n; i += 32) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long x = a[i], y = a[ixj];
+          bool up = ((i & k) == 0);
+          if ((x > y) == up) {
+            a[i] = y;
+            a[ixj] = x;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+constexpr int IVF_NWARP = IVF_NT / 32;
+constexpr int IVF_MAX_NST = 8;
+
+template <int METRIC, int LPR, int J>
+__global__ void __launch_bounds__(IVF_NT)
+    ivfflat_scan_warp_kernel(const float* __restrict__ xq, int64_t ldq, const int32_t* __restrict__ probe_ids,
+                             int nprobe, int nsplit, int pg, ListDirectory dir, int R, int nst, int k, int KP, int SORTNW,
+                             FilterArgs f, unsigned long long* __restrict__ partial) {
+  constexpr int S = LPR * J;
+  constexpr int RPW = 32 / LPR;  // rows per warp round
+  constexpr int ROW_BYTES = S * 16;
+  const int TW = RPW * R;  // rows per warp tile
+  const int stage_bytes = TW * ROW_BYTES;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)IVF_NWARP * nst * stage_bytes);
+  unsigned long long* fin = keys + (size_t)IVF_NWARP * SORTNW;  // [IVF_NWARP * KP]
+  __shared__ __align__(8) uint64_t bars[IVF_NWARP][IVF_MAX_NST];
+  __shared__ int g_list[IVF_MAX_PG], g_r0[IVF_MAX_PG], g_r1[IVF_MAX_PG], g_tile0[IVF_MAX_PG + 1];
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int q = blockIdx.y, grp_id = blockIdx.x;
+  unsigned long long* out = partial + ((int64_t)q * gridDim.x + grp_id) * k;
+  const int nitems = nprobe * nsplit;
+  const int i0 = grp_id * pg;
+  const int ni = min(pg, nitems - i0);
+
+  if (tid == 0) {
+    int acc = 0;
+    for (int i = 0; i < ni; i++) {
+      const int item = i0 + i;
+      const int probe = item / nsplit, split = item - probe * nsplit;
+      const int list = probe_ids[(int64_t)q * nprobe + probe];
+      int len = 0;
+      if (list >= 0 && list < dir.nlist) len = dir.len[list];
+      const int r0 = split * IVF_CHUNK_ROWS;
+      const int r1 = min(len, r0 + IVF_CHUNK_ROWS);
+      g_list[i] = list;
+      g_r0[i] = r0;
+      g_r1[i] = r1 > r0 ? r1 : r0;
+      g_tile0[i] = acc;
+      acc += r1 > r0 ? (r1 - r0 + TW - 1) / TW : 0;
+    }
+    g_tile0[ni > 0 ? ni : 0] = acc;
+    for (int ww = 0; ww < IVF_NWARP; ww++)
+      for (int s = 0; s < nst; s++) mbar_init(&bars[ww][s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int total_tiles = ni > 0 ? g_tile0[ni] : 0;
+  if (total_tiles == 0) {
+    for (int i = tid; i < k; i += IVF_NT) out[i] = kKeySentinel;
+    return;
+  }
+
+  unsigned long long* wbuf = keys + (size_t)w * SORTNW;
+  for (int i = lane; i < SORTNW; i += 32) wbuf[i] = kKeySentinel;
+  __syncwarp();
+  const int capw = SORTNW - KP;
+  unsigned long long tau = kKeySentinel;
+  int cnt = 0;
+  const int rowslot = lane / LPR, p = lane % LPR;
+  float4 qreg[J];
+  {
+    const float4* q4 = reinterpret_cast<const float4*>(xq + (int64_t)q * ldq);
+#pragma unroll
+    for (int j = 0; j < J; j++) qreg[j] = __ldg(q4 + p + LPR * j);
+  }
+  unsigned char* wstage = smem_raw + (size_t)w * nst * stage_bytes;
+  const int n_my = total_tiles > w ? (total_tiles - w + IVF_NWARP - 1) / IVF_NWARP : 0;
+
+  auto warp_flush = [&]() {
+    for (int i = KP + cnt + lane; i < SORTNW; i += 32) wbuf[i] = kKeySentinel;
+    __syncwarp();
+    warp_bitonic_sort(wbuf, SORTNW, lane);
+    tau = wbuf[k - 1];
+    cnt = 0;
+    __syncwarp();
+  };
+
+  int pr_pi = 0;  // producer cursor (lane 0)
+  auto issue = [&](int li) {
+    const int gt = w + IVF_NWARP * li;
+    while (gt >= g_tile0[pr_pi + 1]) pr_pi++;
+    const int ti = gt - g_tile0[pr_pi];
+    const int row0 = g_r0[pr_pi] + ti * TW;
+    const int rows = min(TW, g_r1[pr_pi] - row0);
+    const uint32_t bytes = (uint32_t)rows * ROW_BYTES;
+    const int s = li % nst;
+    mbar_arrive_expect_tx(&bars[w][s], bytes);
+    bulk_g2s(wstage + (size_t)s * stage_bytes, dir.vecs[g_list[pr_pi]] + (int64_t)row0 * (S * 4), bytes, &bars[w][s]);
+  };
+  if (lane == 0)
+    for (int li = 0; li < nst && li < n_my; li++) issue(li);
+
+  int pi = 0;
+  for (int li = 0; li < n_my; li++) {
+    const int gt = w + IVF_NWARP * li;
+    while (gt >= g_tile0[pi + 1]) pi++;
+    const int64_t* __restrict__ lids = dir.ids[g_list[pi]];
+    const int ti = gt - g_tile0[pi];
+    const int row0 = g_r0[pi] + ti * TW;
+    const int tile_rows = min(TW, g_r1[pi] - row0);
+    const int s = li % nst;
+    mbar_wait(&bars[w][s], (li / nst) & 1);
+    const float4* st4 = reinterpret_cast<const float4*>(wstage + (size_t)s * stage_bytes);
+    for (int r = 0; r < R; r++) {
+      const int rit = r * RPW + rowslot;
+      const bool valid = rit < tile_rows;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (valid) {
+        const float4* rowp = st4 + (size_t)rit * S + p;
+#pragma unroll
+        for (int j = 0; j < J; j++) {
+          float4 v = rowp[LPR * j];
+          float4 wq = qreg[j];
+          if (METRIC == kMetricL2) {
+            float t0 = v.x - wq.x, t1 = v.y - wq.y, t2 = v.z - wq.z, t3 = v.w - wq.w;
+            a0 = fmaf(t0, t0, a0), a1 = fmaf(t1, t1, a1), a2 = fmaf(t2, t2, a2), a3 = fmaf(t3, t3, a3);
+          } else {
+            a0 = fmaf(v.x, wq.x, a0), a1 = fmaf(v.y, wq.y, a1), a2 = fmaf(v.z, wq.z, a2), a3 = fmaf(v.w, wq.w, a3);
+          }
+        }
+      }
+      float dis = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int off = LPR >> 1; off > 0; off >>= 1) dis += __shfl_xor_sync(0xffffffffu, dis, off);
+
+      bool pred = valid && p == 0 && dis <= f.max_score && dis >= f.min_score;
+      unsigned long long key = kKeySentinel;
+      if (pred) {
+        uint32_t ord = score2ord<METRIC>(dis);
+        pred = ord <= (uint32_t)(tau >> 32);
+        if (pred) {
+          int64_t raw = lids[row0 + rit];
+          pred = raw >= 0;  // top bit set => tombstone (gamma_index_ivfflat.h:72)
+          uint32_t vid = (uint32_t)raw;
+          if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
+          key = make_key(ord, vid);
+          pred = pred && key < tau;
+        }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, pred);
+      if (mask) {
+        if (pred) wbuf[KP + cnt + __popc(mask & ((1u << lane) - 1u))] = key;
+        cnt += __popc(mask);
+        if (cnt + RPW > capw) warp_flush();  // warp-uniform
+      }
+    }
+    __syncwarp();  // every lane is done with stage s
+    if (lane == 0 && li + nst < n_my) issue(li + nst);
+  }
+  warp_flush();
+  __syncthreads();
+  // merge the four per-warp top-KP lists
+  const int NF = IVF_NWARP * KP;
+  for (int i = tid; i < NF; i += IVF_NT) fin[i] = keys[(size_t)(i / KP) * SORTNW + (i % KP)];
+  __syncthreads();
+  block_bitonic_sort(fin, NF);
+  for (int i = tid; i < k; i += IVF_NT) out[i] = fin[i];
+}
+
+template <int METRIC, int LPR, int J>
+cudaError_t launch_warp(const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe, int nsplit,
+                        FastCfg c, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
+                        cudaStream_t st) {
+  constexpr int S = LPR * J, RPW = 32 / LPR, ROW_BYTES = S * 16;
+  int R = c.stage_bytes / IVF_NWARP / (RPW * ROW_BYTES);  // stage_bytes = per-CTA bytes per ring slot
+  if (R < 1) R = 1;
+  const int TW = RPW * R;
+  const int KP = next_pow2(k < 16 ? 16 : k);
+  const int SORTNW = next_pow2(KP + 2 * RPW + TW);
+  size_t smem = (size_t)IVF_NWARP * c.nst * TW * ROW_BYTES + (size_t)IVF_NWARP * SORTNW * 8 + (size_t)IVF_NWARP * KP * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(ivfflat_scan_warp_kernel<METRIC, LPR, J>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int nitems = nprobe * nsplit;
+  dim3 grid((nitems + c.pg - 1) / c.pg, nq);
+  ivfflat_scan_warp_kernel<METRIC, LPR, J><<<grid, IVF_NT, smem, st>>>(xq, ldq, probe_ids, nprobe, nsplit, c.pg, dir, R,
+                                                                       c.nst, k, KP, SORTNW, f, partial);
+  note_launch();
+  return cudaGetLastError();
+}
+
 // returns cudaErrorNotSupported when no instantiation fits (caller falls back to the generic kernel)
 template <int METRIC>
 cudaError_t dispatch_fast(int S, const float* xq, int64_t ldq, int nq, const int32_t* probe_ids, int nprobe,
                           int nsplit, FastCfg c, ListDirectory dir, int k, FilterArgs f, unsigned long long* partial,
                           cudaStream_t st) {
-#define GB_FAST(LPR, J)   if (S == (LPR) * (J)) return launch_fast<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, c, dir, k, f, partial, st)
+#define GB_FAST(LPR, J)                                                                                              \
+  if (S == (LPR) * (J))                                                                                            \
+    return c.warp_mode ? launch_warp<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, c, dir, k, f, partial, st) \
+                       : launch_fast<METRIC, LPR, J>(xq, ldq, nq, probe_ids, nprobe, nsplit, c, dir, k, f, partial, st)
   GB_FAST(8, 1);   // d = 32
   GB_FAST(8, 2);   // d = 64
   GB_FAST(8, 3);   // d = 96
