@@ -335,16 +335,15 @@ inline FastCfg fast_cfg(int nprobe, int nsplit, int avg_len) {
   FastCfg c;
   // measured on B200 (gpurun_out/cfg_sweep.log): resident CTAs matter more than ring depth --
   // 8 KiB x 2 stages: 59 ms, x3: 62 ms, x4: 74 ms, x6: 100 ms, 16 KiB x 4: 91 ms (C2, nq = 10 k)
-  c.stage_bytes = 8 * 1024;
+  // warp-autonomous kernel, 4 KiB per warp per ring slot, 2 slots: 51 ms on C2 (10.4 TB/s
+  // algorithmic) vs 58 ms for the best block-synchronous configuration (gpurun_out/cfg_sweep2.log)
+  c.stage_bytes = 16 * 1024;
   c.nst = 2;
-  c.warp_mode = 0;
+  c.warp_mode = 1;
   if (const char* e = getenv("GB_IVF_MODE")) c.warp_mode = !strcmp(e, "warp");
-  if (c.warp_mode) {  // per-warp rings: 4 KiB per warp per slot, 3 slots
-    c.stage_bytes = 16 * 1024;
-    c.nst = 3;
-  }
-  // ~4096 rows of work per CTA: enough tiles to amortise start-up, enough CTAs to balance
-  int per = avg_len > 0 ? 4096 / avg_len : 1;
+  if (!c.warp_mode) c.stage_bytes = 8 * 1024;
+  // ~16k rows of work per CTA: enough tiles to amortise start-up, enough CTAs to balance
+  int per = avg_len > 0 ? 16384 / avg_len : 1;
   c.pg = per < 1 ? 1 : (per > IVF_MAX_PG ? IVF_MAX_PG : per);
   if (nsplit > 1) c.pg = 1;
   if (const char* e = getenv("GB_IVF_STAGE_KB")) c.stage_bytes = atoi(e) * 1024;
