@@ -113,6 +113,10 @@ int gb_kmeans_update(int device, const float *x, int64_t n, int d, int k, const 
 int gb_merge_partitions_device(int device, const float *dis_dev, const int64_t *ids_dev, int nparts, int nq, int k,
                                int metric, float *out_dis_dev, int64_t *out_ids_dev, void *stream);
 
+/* exact (CUDA-core fp32) or tensor-core (tcgen05 3xTF32) score matrix, host in/out: out[n][m] */
+int gb_debug_dist_matrix(int device, const float *x, int n, const float *c, int m, int d, int metric, int use_tc,
+                         float *out);
+
 /* ---- host-logic test hooks: run the C++ wire codecs of the gamma boundary without a GPU ---- */
 int gb_debug_parse_search_request(const char *buf, int len, char **json_out, int *out_len);
 int gb_debug_roundtrip_doc(const char *buf, int len, char **out, int *out_len);

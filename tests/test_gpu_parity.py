@@ -452,3 +452,27 @@ def test_search_device_resident_matches_host(ivf_state, ivfflat_index):
     dd, di = ivfflat_index.search_device(xq_dev, 10, params={"nprobe": 8})
     torch.cuda.synchronize()
     assert np.array_equal(dd.cpu().numpy(), dg) and np.array_equal(di.cpu().numpy(), ig)
+
+
+# ----------------------------------------------------------------------------------------------
+# K2 tensor-core variant (tcgen05 3xTF32) against the exact CUDA-core kernel
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", [L2, IP])
+@pytest.mark.parametrize("n,m,d", [(128, 128, 32), (300, 200, 100), (129, 257, 128), (1000, 4096, 64), (70, 33, 8)])
+def test_tensor_core_distance_kernel(metric, n, m, d):
+    # integer-valued operands: TF32 holds them exactly => bit-equal to the exact kernel and to fp64 maths
+    x = synth.sift_like(n, d, seed=91)
+    c = synth.sift_like(m, d, seed=92)
+    exact = gi().debug_dist_matrix(x, c, metric, 0)
+    tc = gi().debug_dist_matrix(x, c, metric, 1)
+    ref = ((x[:, None, :].astype(np.float64) - c[None].astype(np.float64)) ** 2).sum(-1) if metric == L2 \
+        else x.astype(np.float64) @ c.astype(np.float64).T
+    assert np.array_equal(exact.astype(np.float64), ref)
+    assert np.array_equal(tc, exact)
+    # float operands: error-compensated 3xTF32 stays within ~1e-6 of fp32 (north_star bar: 1e-4 relative)
+    xf = synth.embed_like(n, d, seed=93) * 3.0
+    cf = synth.embed_like(m, d, seed=94) * 3.0
+    exact = gi().debug_dist_matrix(xf, cf, metric, 0)
+    tc = gi().debug_dist_matrix(xf, cf, metric, 1)
+    scale = np.abs(exact).max()
+    assert np.abs(tc - exact).max() <= 2e-5 * scale

@@ -395,6 +395,38 @@ int gb_kmeans_update(int device, const float* x, int64_t n, int d, int k, const 
   return 0;
 }
 
+int gb_debug_dist_matrix(int device, const float* x, int n, const float* c, int m, int d, int metric, int use_tc,
+                         float* out) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_last_error("no CUDA device");
+    return -1;
+  }
+  cudaStream_t st = nullptr;
+  Scratch s(st);
+  const int dpad = (d + 3) / 4 * 4;
+  const int64_t ldo = (m + 3) / 4 * 4;
+  float* dx = s.alloc_n<float>((size_t)n * dpad);
+  float* dc = s.alloc_n<float>((size_t)m * dpad);
+  float* dout = s.alloc_n<float>((size_t)n * ldo);
+  float* xn = s.alloc_n<float>(n);
+  float* cn = s.alloc_n<float>(m);
+  if (!dx || !dc || !dout || !xn || !cn) return -1;
+  GB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * dpad * 4, st));
+  GB_CUDA(cudaMemsetAsync(dc, 0, (size_t)m * dpad * 4, st));
+  GB_CUDA(cudaMemcpy2DAsync(dx, (size_t)dpad * 4, x, (size_t)d * 4, (size_t)d * 4, n, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpy2DAsync(dc, (size_t)dpad * 4, c, (size_t)d * 4, (size_t)d * 4, m, cudaMemcpyHostToDevice, st));
+  if (use_tc) {
+    GB_CUDA(launch_row_norms(dx, dpad, n, dpad, xn, st));
+    GB_CUDA(launch_row_norms(dc, dpad, m, dpad, cn, st));
+    GB_CUDA(launch_dist_matrix_tc(dx, dpad, n, dc, dpad, m, dpad, metric, xn, cn, dout, ldo, st));
+  } else {
+    GB_CUDA(launch_dist_matrix(dx, dpad, n, dc, dpad, m, dpad, metric, dout, ldo, st));
+  }
+  GB_CUDA(cudaMemcpy2DAsync(out, (size_t)m * 4, dout, (size_t)ldo * 4, (size_t)m * 4, n, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int gb_merge_partitions_device(int device, const float* dis_dev, const int64_t* ids_dev, int nparts, int nq, int k,
                                int metric, float* out_dis_dev, int64_t* out_ids_dev, void* stream) {
   if (cudaSetDevice(device) != cudaSuccess) {

@@ -29,6 +29,17 @@ cudaError_t launch_dist_matrix(const float* X, int64_t ldx, int n, const float* 
 cudaError_t launch_dist_argmin(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
                                int metric, unsigned long long* best, int col_base, cudaStream_t st);
 
+// tensor-core (tcgen05, 3xTF32) variants of the two calls above; L2 needs the row norms
+// (launch_row_norms).  Scores agree with the exact kernel to ~1e-6 relative and are bit-equal on
+// integer-valued operands below 2^11.
+cudaError_t launch_row_norms(const float* x, int64_t ldx, int64_t n, int d, float* out, cudaStream_t st);
+cudaError_t launch_dist_matrix_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                                  int metric, const float* xnorm, const float* cnorm, float* out, int64_t ldo,
+                                  cudaStream_t st);
+cudaError_t launch_dist_argmin_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                                  int metric, const float* xnorm, const float* cnorm, unsigned long long* best,
+                                  cudaStream_t st);
+
 // ---- K7: top-k selection / merge ----------------------------------------------------------
 // Per row r: select the k best of m candidates.  Input is either scores (fp32, vid = id_base+col)
 // or ready-made keys.  Output keys sorted ascending (sentinel padded) in out_keys[r*k..].

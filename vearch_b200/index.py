@@ -318,3 +318,14 @@ def merge_partitions_device(dis, ids, metric):
                                                  C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(st)),
            "merge_partitions_device")
     return od, oi
+
+
+def debug_dist_matrix(x, c, metric, use_tc, device=0):
+    """score matrix through the exact CUDA-core kernel (use_tc=0) or the tcgen05 3xTF32 kernel (use_tc=1)."""
+    x, c = _f32(x), _f32(c)
+    out = np.empty((x.shape[0], c.shape[0]), np.float32)
+    fn = _lib.lib().gb_debug_dist_matrix
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _check(fn(device, _ptr(x), x.shape[0], _ptr(c), c.shape[0], x.shape[1], metric, int(use_tc), _ptr(out)),
+           "debug_dist_matrix")
+    return out
