@@ -476,3 +476,35 @@ def test_tensor_core_distance_kernel(metric, n, m, d):
     tc = gi().debug_dist_matrix(xf, cf, metric, 1)
     scale = np.abs(exact).max()
     assert np.abs(tc - exact).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("metric", [L2, IP])
+def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric):
+    """Many queries per list => the list-major grouped-GEMM scan (kernels_tc.cu) is selected.
+    Integer data: scores bit-equal to the oracle; filters and tombstones honoured."""
+    d, n, nlist, nq, nprobe, k = 64, 30000, 16, 700, 6, 10
+    db = synth.sift_like(n, d, seed=95)
+    xq = synth.sift_like(nq, d, seed=96)
+    cent, _, _ = orc.kmeans(db[:4000], nlist, niter=5)
+    cent = np.rint(cent).astype(np.float32)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": nprobe, "metric_type": mt(metric)})
+    idx.set_centroids(cent)
+    idx.add_vectors(db)
+    idx.add_pending()
+    off, codes, ids = idx.export_lists()
+    vecs = codes.view(np.float32).reshape(len(ids), -1)[:, :d]
+    cd, keys = orc.coarse_search(cent, xq, nprobe, metric)
+    keys[5, 2] = -1  # "not enough centroids"
+    deleted = np.random.default_rng(2).random(n) < 0.2
+    delb = np.packbits(deleted, bitorder="little")
+    idx.tombstone(int(np.searchsorted(off, 0, side="right") - 1), 0)
+    ids2 = ids.copy()
+    ids2[0] |= orc.DEL_MASK
+    dg, ig = idx.search_preassigned(xq, k, keys, cd, del_bitmap=delb)
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, xq, k, keys, metric, del_bitmap=delb)
+    assert_same_results(dg, ig, do, io)
+    lo, hi = float(min(do[0, 1], do[0, 6])), float(max(do[0, 1], do[0, 6]))
+    dg, ig = idx.search_preassigned(xq, k, keys, cd, min_score=lo, max_score=hi)
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, xq, k, keys, metric, min_score=lo, max_score=hi)
+    assert_same_results(dg, ig, do, io)
+    idx.close()

@@ -2,6 +2,7 @@
 #include "index.h"
 
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -17,6 +18,17 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 const char* last_error() { return g_last_error.c_str(); }
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// tensor-core (tcgen05 3xTF32) path for the dense query x centroid contraction: coarse search and
+// the k-means assign step.  GB_TC=0 selects the exact CUDA-core kernel everywhere.  List assignment
+// at add time always uses the exact kernel so list membership is deterministic against the oracle.
+static bool tc_enabled() {
+  static int v = [] {
+    const char* e = getenv("GB_TC");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
 
 static cudaStream_t thread_stream(int device) {
   static thread_local cudaStream_t st[64] = {nullptr};
@@ -523,9 +535,14 @@ int kmeans_device(const float* x_in, int64_t ldx_in, int64_t n_in, int d, int k,
   std::vector<int32_t> h_off(k + 1), h_perm(n), cursor(k);
   std::vector<float> hassign(k), h_cent;
   const int metric = kp.spherical ? kMetricIP : kMetricL2;  // gamma's quantizer is IndexFlat(d, metric)
+  const bool use_tc = tc_enabled() && k >= 64;
   for (int it = 0; it < kp.niter; it++) {
     GB_CUDA(launch_fill_u64(best, n, kKeySentinel, st));
-    GB_CUDA(launch_dist_argmin(x, ldx, (int)n, centroids, ldc, k, dpad, metric, best, 0, st));
+    if (use_tc) {
+      GB_CUDA(launch_dist_argmin_tc(x, ldx, (int)n, centroids, ldc, k, dpad, metric, best, st));
+    } else {
+      GB_CUDA(launch_dist_argmin(x, ldx, (int)n, centroids, ldc, k, dpad, metric, best, 0, st));
+    }
     GB_CUDA(cudaMemcpyAsync(h_best.data(), best, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     // stable counting sort of the points by label (point order inside a cluster = faiss's sum order)
@@ -760,10 +777,91 @@ int IVFFlatIndex::coarse_dev(int nq, const float* xq, int nprobe, int metric, in
   int64_t ldo = round_up(nlist_, 4);
   GB_ALLOC(scores, float, (size_t)nq * ldo, s);
   GB_ALLOC(keys, unsigned long long, (size_t)nq * nprobe, s);
-  GB_CUDA(launch_dist_matrix(xq, dpad_, nq, d_centroids_, dpad_, nlist_, dpad_, metric, scores, ldo, st));
+  if (tc_enabled() && nlist_ >= 64 && nq >= 32) {
+    GB_CUDA(launch_dist_matrix_tc(xq, dpad_, nq, d_centroids_, dpad_, nlist_, dpad_, metric, scores, ldo, st));
+  } else {
+    GB_CUDA(launch_dist_matrix(xq, dpad_, nq, d_centroids_, dpad_, nlist_, dpad_, metric, scores, ldo, st));
+  }
   FilterArgs nf{nullptr, nullptr, -FLT_MAX, FLT_MAX};
   GB_CUDA(launch_select_scores(scores, ldo, nq, nlist_, 0, nprobe, metric, nf, keys, nprobe, st));
   GB_CUDA(launch_split_keys(keys, (int64_t)nq * nprobe, metric, coarse_dis, probe_ids, st));
+  return 0;
+}
+
+// List-major scan: worthwhile when many queries of the batch probe each list.
+// Host side: group the (query, probe) pairs by list (stable counting sort), give every pair a
+// score segment of len(list) floats, cut (list, 128 pairs, 128 rows) tiles; device side: grouped
+// GEMM on tcgen05 + segment select.
+static bool listmajor_enabled() {
+  static int v = [] {
+    const char* e = getenv("GB_LISTMAJOR");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, const float* xq, int k,
+                                     const int32_t* probe_ids, int nprobe, unsigned long long* out_keys, Scratch& s) {
+  if (!tc_enabled() || !listmajor_enabled()) return 1;
+  const int64_t npairs = (int64_t)nq * nprobe;
+  if (npairs < (int64_t)nlist_ * 32 && !getenv("GB_LISTMAJOR_FORCE")) return 1;  // < 32 queries per list on average
+  cudaStream_t st = s.stream();
+  std::vector<int32_t> h_probe(npairs);
+  GB_CUDA(cudaMemcpyAsync(h_probe.data(), probe_ids, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  const std::vector<int>& lens = lists_->lens();
+  std::vector<int32_t> cnt(nlist_ + 1, 0);
+  for (int64_t j = 0; j < npairs; j++) {
+    int l = h_probe[j];
+    if (l >= 0 && l < nlist_ && lens[l] > 0) cnt[l + 1]++;
+  }
+  for (int l = 0; l < nlist_; l++) cnt[l + 1] += cnt[l];
+  const int64_t nvalid = cnt[nlist_];
+  std::vector<int32_t> start(cnt.begin(), cnt.end() - 1), h_pair_q(nvalid);
+  std::vector<int64_t> h_pair_off(nvalid), h_seg_off(npairs, -1);
+  std::vector<int32_t> cur(start);
+  // pair slots in list order; segments are laid out in that same order
+  std::vector<int64_t> slot_of(npairs, -1);
+  for (int64_t j = 0; j < npairs; j++) {
+    int l = h_probe[j];
+    if (l >= 0 && l < nlist_ && lens[l] > 0) {
+      int slot = cur[l]++;
+      h_pair_q[slot] = (int32_t)(j / nprobe);
+      slot_of[j] = slot;
+    }
+  }
+  int64_t total = 0;
+  std::vector<LmTile> tiles;
+  for (int l = 0; l < nlist_; l++) {
+    const int c = cnt[l + 1] - cnt[l];
+    if (!c) continue;
+    const int len = lens[l];
+    for (int i = 0; i < c; i++) {
+      h_pair_off[cnt[l] + i] = total;
+      total += len;
+    }
+    for (int p0 = 0; p0 < c; p0 += 128)
+      for (int r0 = 0; r0 < len; r0 += 128)
+        tiles.push_back({l, cnt[l] + p0, std::min(128, c - p0), r0, std::min(128, len - r0)});
+  }
+  if (total > ((int64_t)3 << 30)) return 1;  // > 12 GiB of scores: let the caller use the query-major scan
+  for (int64_t j = 0; j < npairs; j++)
+    if (slot_of[j] >= 0) h_seg_off[j] = h_pair_off[slot_of[j]];
+  GB_ALLOC(d_pair_q, int32_t, std::max<int64_t>(nvalid, 1), s);
+  GB_ALLOC(d_pair_off, int64_t, std::max<int64_t>(nvalid, 1), s);
+  GB_ALLOC(d_seg_off, int64_t, npairs, s);
+  GB_ALLOC(d_tiles, LmTile, std::max<size_t>(tiles.size(), 1), s);
+  GB_ALLOC(scores, float, std::max<int64_t>(total, 1), s);
+  GB_CUDA(cudaMemcpyAsync(d_pair_q, h_pair_q.data(), (size_t)nvalid * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_pair_off, h_pair_off.data(), (size_t)nvalid * 8, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_seg_off, h_seg_off.data(), (size_t)npairs * 8, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(LmTile), cudaMemcpyHostToDevice, st));
+  scan_timer_begin(st);
+  GB_CUDA(launch_ivf_listmajor_tc(xq, dpad_, dpad_, d_tiles, (int)tiles.size(), d_pair_q, d_pair_off, lists_->directory(),
+                                  metric, scores, st));
+  GB_CUDA(launch_seg_select(scores, d_seg_off, probe_ids, nq, nprobe, lists_->directory(), k, metric, f, out_keys, st));
+  scan_timer_end(st);
+  GB_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope
   return 0;
 }
 
@@ -773,6 +871,10 @@ int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int me
   (void)ctx;
   (void)coarse_dis;
   cudaStream_t st = s.stream();
+  if (type_ == "IVFFLAT") {
+    int lm = scan_listmajor_dev(f, metric, nq, xq, k, probe_ids, nprobe, out_keys, s);
+    if (lm <= 0) return lm;
+  }
   int nparts = ivfflat_scan_nparts(nprobe, lists_->max_len());
   GB_ALLOC(partial, unsigned long long, (size_t)nq * nparts * k, s);
   scan_timer_begin(st);

@@ -255,6 +255,9 @@ class IVFFlatIndex : public Index {
   virtual int scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
                        const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
                        Scratch& s);
+  // list-major IVF-Flat scan on the tensor cores (kernels_tc.cu); returns 1 if not applicable
+  int scan_listmajor_dev(const FilterArgs& f, int metric, int nq, const float* xq, int k, const int32_t* probe_ids,
+                         int nprobe, unsigned long long* out_keys, Scratch& s);
   int assign_dev(const float* x, int64_t ldx, int64_t n, int32_t* assign_dev_out, Scratch& s);
   int resolve_nprobe(const SearchContext& ctx) const;
   virtual int code_bytes() const { return dpad_ * 4; }

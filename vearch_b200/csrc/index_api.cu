@@ -408,17 +408,13 @@ int gb_debug_dist_matrix(int device, const float* x, int n, const float* c, int 
   float* dx = s.alloc_n<float>((size_t)n * dpad);
   float* dc = s.alloc_n<float>((size_t)m * dpad);
   float* dout = s.alloc_n<float>((size_t)n * ldo);
-  float* xn = s.alloc_n<float>(n);
-  float* cn = s.alloc_n<float>(m);
-  if (!dx || !dc || !dout || !xn || !cn) return -1;
+  if (!dx || !dc || !dout) return -1;
   GB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * dpad * 4, st));
   GB_CUDA(cudaMemsetAsync(dc, 0, (size_t)m * dpad * 4, st));
   GB_CUDA(cudaMemcpy2DAsync(dx, (size_t)dpad * 4, x, (size_t)d * 4, (size_t)d * 4, n, cudaMemcpyHostToDevice, st));
   GB_CUDA(cudaMemcpy2DAsync(dc, (size_t)dpad * 4, c, (size_t)d * 4, (size_t)d * 4, m, cudaMemcpyHostToDevice, st));
   if (use_tc) {
-    GB_CUDA(launch_row_norms(dx, dpad, n, dpad, xn, st));
-    GB_CUDA(launch_row_norms(dc, dpad, m, dpad, cn, st));
-    GB_CUDA(launch_dist_matrix_tc(dx, dpad, n, dc, dpad, m, dpad, metric, xn, cn, dout, ldo, st));
+    GB_CUDA(launch_dist_matrix_tc(dx, dpad, n, dc, dpad, m, dpad, metric, dout, ldo, st));
   } else {
     GB_CUDA(launch_dist_matrix(dx, dpad, n, dc, dpad, m, dpad, metric, dout, ldo, st));
   }

@@ -29,16 +29,13 @@ cudaError_t launch_dist_matrix(const float* X, int64_t ldx, int n, const float* 
 cudaError_t launch_dist_argmin(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
                                int metric, unsigned long long* best, int col_base, cudaStream_t st);
 
-// tensor-core (tcgen05, 3xTF32) variants of the two calls above; L2 needs the row norms
-// (launch_row_norms).  Scores agree with the exact kernel to ~1e-6 relative and are bit-equal on
-// integer-valued operands below 2^11.
-cudaError_t launch_row_norms(const float* x, int64_t ldx, int64_t n, int d, float* out, cudaStream_t st);
+// tensor-core (tcgen05, 3xTF32) variants of the two calls above (norms accumulated in-kernel).
+// Scores agree with the exact kernel to ~1e-6 relative and are bit-equal on integer-valued
+// operands below 2^11.
 cudaError_t launch_dist_matrix_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
-                                  int metric, const float* xnorm, const float* cnorm, float* out, int64_t ldo,
-                                  cudaStream_t st);
+                                  int metric, float* out, int64_t ldo, cudaStream_t st);
 cudaError_t launch_dist_argmin_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
-                                  int metric, const float* xnorm, const float* cnorm, unsigned long long* best,
-                                  cudaStream_t st);
+                                  int metric, unsigned long long* best, cudaStream_t st);
 
 // ---- K7: top-k selection / merge ----------------------------------------------------------
 // Per row r: select the k best of m candidates.  Input is either scores (fp32, vid = id_base+col)
@@ -69,6 +66,19 @@ cudaError_t launch_ivfflat_scan(const float* xq, int64_t ldq, int nq, int d, con
                                 ListDirectory dir, int max_list_len, int avg_list_len, int k, int metric, FilterArgs f,
                                 unsigned long long* partial, int* nparts_out, cudaStream_t st);
 int ivfflat_scan_nparts(int nprobe, int max_list_len);
+
+// K3 list-major (tensor cores): (query, probe) pairs grouped by list; tile = 128 pairs x 128 rows.
+struct LmTile {
+  int list, pair0, npairs, row0, nrows;
+};
+// scores[pair_off[j] + r] = score(query pair_q[j], row r of its list)
+cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const LmTile* tiles, int ntiles,
+                                    const int32_t* pair_q, const int64_t* pair_off, ListDirectory dir, int metric,
+                                    float* scores, cudaStream_t st);
+// per query: stream its nprobe score segments (seg_off[q*nprobe+p], -1 = none), filter, top-k -> out_keys[q][k]
+cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const int32_t* probe_ids, int nq, int nprobe,
+                              ListDirectory dir, int k, int metric, FilterArgs f, unsigned long long* out_keys,
+                              cudaStream_t st);
 
 // ---- K4/K5: IVF-PQ look-up tables + ADC scan --------------------------------------------
 // ip[q][m][c] = <x_q|m, pq_m[c]>   (pq.compute_inner_prod_table)

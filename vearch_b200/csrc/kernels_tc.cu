@@ -1,20 +1,29 @@
-// K2 / K6 tensor-core variant: the ONE genuinely dense contraction of the path -- query x centroid
-// (coarse quantiser, gamma_index_ivfflat.cc:568 / gamma_index_ivfpq.cc:595) and point x centroid
-// (k-means assign, faiss Clustering via gamma_index_ivfflat.cc:407 / gamma_index_ivfpq.cc:372) --
-// on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, read back with
-// tcgen05.ld for a fused epilogue (|x|^2 + |c|^2 - 2 x.c, then either the score tile or the row
-// arg-min).  faiss itself evaluates this contraction with sgemm + norms (IndexFlat, >= 20 queries).
+// Tensor-core kernels of the path (tcgen05.mma kind::tf32, accumulators in TMEM, tcgen05.ld epilogue):
 //
-// Precision: every operand is split x = hi + lo with hi = the TF32-representable head (low 13
-// mantissa bits cleared) and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 (error-compensated
-// "3xTF32", relative error ~2^-21).  Integer-valued operands up to 2^11 have lo == 0 and every
-// product and partial sum is exact, so on the SIFT-shaped parity data results are bit-equal to the
-// exact fp32 kernel (kernels_dist.cu), which remains the path for list assignment at add time.
+//  * K2 / K6  dist_tc_kernel: query x centroid (coarse quantiser, gamma_index_ivfflat.cc:568 /
+//    gamma_index_ivfpq.cc:595) and point x centroid (k-means assign, faiss Clustering via
+//    gamma_index_ivfflat.cc:407 / gamma_index_ivfpq.cc:372).  faiss itself evaluates this
+//    contraction as sgemm + norms (IndexFlat, >= 20 queries).
+//  * K3 list-major  ivf_listmajor_tc_kernel: when many queries of a batch probe the same list the
+//    IVF-Flat scan (gamma_index_ivfflat.cc:579-787) IS a dense contraction: the (query, probe) pairs
+//    are grouped by list on the host, one CTA multiplies a 128-query group by a 128-row list tile
+//    and writes the 128 x 128 scores into per-(query, probe) score segments; a segment-select
+//    kernel then applies tombstones / bitmaps / score window and keeps the top-k exactly as
+//    scan_codes does (gamma_index_ivfflat.h:63-91).  The list is read once per 128 queries instead
+//    of once per query.
 //
-// Operand staging: plain coalesced-enough global loads -> st.shared in the canonical no-swizzle
-// K-major UMMA layout (8-row x 16-byte core matrices; LBO = stride between the two K core
-// matrices of one MMA, SBO = stride between 8-row groups), fence.proxy.async, one elected thread
-// issues the MMAs and commits to an mbarrier.  One 128 x 128 output tile per CTA.
+// Precision: every operand is split x = hi + lo, hi = the TF32-representable head (low 13 mantissa
+// bits cleared), and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 (error-compensated
+// "3xTF32", relative error ~2^-21).  Integer-valued operands below 2^11 have lo == 0 and every
+// product and partial sum is exact, so on the SIFT-shaped parity data scores are bit-equal to the
+// exact fp32 kernels.  L2 uses |x|^2 + |y|^2 - 2 x.y with both norms accumulated in-kernel from the
+// staged operands (faiss clamps the expanded form at 0; so do we).
+//
+// Operand staging: global loads -> st.shared in the canonical no-swizzle K-major UMMA layout
+// (8-row x 16-byte core matrices; LBO = stride between the two K core matrices of one MMA,
+// SBO = stride between 8-row groups), fence.proxy.async, one elected thread issues the MMAs and
+// commits to an mbarrier.  Thread t stages row t of both operands, so it also owns |x_t|^2 and
+// |y_t|^2.  One 128 x 128 output tile per CTA.
 #include <float.h>
 
 #include "common.cuh"
@@ -26,6 +35,7 @@ namespace {
 
 constexpr int TC_M = 128, TC_N = 128, TC_BK = 32, TC_NT = 128;
 constexpr int TC_TILE_BYTES = TC_M * TC_BK * 4;  // 16 KiB per operand tile (hi or lo)
+constexpr int TC_SMEM = 4 * TC_TILE_BYTES;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
@@ -50,57 +60,63 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
-template <int METRIC, int EPI_ARGMIN>
-__global__ void __launch_bounds__(TC_NT)
-    dist_tc_kernel(const float* __restrict__ X, int64_t ldx, int n, const float* __restrict__ C, int64_t ldc, int m,
-                   int d, const float* __restrict__ xnorm, const float* __restrict__ cnorm, float* __restrict__ out,
-                   int64_t ldo, unsigned long long* __restrict__ best) {
-  extern __shared__ __align__(1024) unsigned char smem[];
+// One 128 x 128 tile: D[i][j] = <A_i, B_j> over d columns.  arow / brow: row pointers of THIS
+// thread's row of A and B (nullptr => all zeros).  On return the accumulator sits in TMEM at
+// *tmem_out (lane = A row, column = B row), thread t holds |A_t|^2 in *an and cn_s[t] = |B_t|^2.
+// Caller must have 128 threads, TC_SMEM bytes of dynamic smem at `smem`, and must call tc_release().
+struct TcShared {
+  uint64_t mma_bar;
+  uint32_t tmem_base;
+  float cn[TC_N];
+};
+
+__device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const float* __restrict__ arow,
+                                        const float* __restrict__ brow, int d, uint32_t* tmem_out, float* an) {
   unsigned char* a_hi = smem;
   unsigned char* a_lo = smem + TC_TILE_BYTES;
   unsigned char* b_hi = smem + 2 * TC_TILE_BYTES;
   unsigned char* b_lo = smem + 3 * TC_TILE_BYTES;
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_base_s;
-
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row0 = blockIdx.y * TC_M, col0 = blockIdx.x * TC_N;
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "n"(TC_N)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&mma_bar, 1);
+    mbar_init(&sh->mma_bar, 1);
     mbar_fence_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t tmem_d = sh->tmem_base;
 
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
   // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
   // canonical layout: element (r, k) of a 128 x 32 tile lives at (k/4)*(128*16) + (r/8)*128 + (r%8)*16 + (k%4)*4
   const uint32_t LBO = TC_M * 16, SBO = 128;
+  const uint32_t row_off = (uint32_t)(tid >> 3) * SBO + (uint32_t)(tid & 7) * 16;
 
+  float an_acc = 0.f, bn_acc = 0.f;
   uint32_t phase = 0;
   const int nk = (d + TC_BK - 1) / TC_BK;
   for (int kc = 0; kc < nk; kc++) {
     const int k0 = kc * TC_BK;
-    // ---- stage both operand tiles (hi and lo parts) ----
+    // ---- stage this thread's row of both operands (8 float4 each), split into hi / lo ----
 #pragma unroll
-    for (int it = 0; it < (TC_M * TC_BK / 4) / TC_NT; it++) {  // 1024 float4 per operand / 128 threads = 8
-      const int f = it * TC_NT + tid;
-      const int r = f & (TC_M - 1), kb = f >> 7;  // consecutive threads -> consecutive rows: conflict-free st.shared
+    for (int kb = 0; kb < TC_BK / 4; kb++) {
       const int gk = k0 + kb * 4;
-      const uint32_t off = (uint32_t)kb * LBO + (uint32_t)(r >> 3) * SBO + (uint32_t)(r & 7) * 16;
+      const uint32_t off = (uint32_t)kb * LBO + row_off;  // consecutive threads -> consecutive rows: conflict-free
       float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      if (row0 + r < n && gk < d) va = __ldg(reinterpret_cast<const float4*>(X + (int64_t)(row0 + r) * ldx + gk));
-      if (col0 + r < m && gk < d) vb = __ldg(reinterpret_cast<const float4*>(C + (int64_t)(col0 + r) * ldc + gk));
+      if (arow && gk < d) va = __ldg(reinterpret_cast<const float4*>(arow + gk));
+      if (brow && gk < d) vb = __ldg(reinterpret_cast<const float4*>(brow + gk));
+      an_acc = fmaf(va.x, va.x, an_acc), an_acc = fmaf(va.y, va.y, an_acc);
+      an_acc = fmaf(va.z, va.z, an_acc), an_acc = fmaf(va.w, va.w, an_acc);
+      bn_acc = fmaf(vb.x, vb.x, bn_acc), bn_acc = fmaf(vb.y, vb.y, bn_acc);
+      bn_acc = fmaf(vb.z, vb.z, bn_acc), bn_acc = fmaf(vb.w, vb.w, bn_acc);
       auto split = [](float v, float& hi, float& lo) {
         hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         lo = v - hi;
@@ -130,43 +146,75 @@ __global__ void __launch_bounds__(TC_NT)
       }
       // arrives on mma_bar when every MMA issued so far has finished reading smem / writing TMEM
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&mma_bar))
+                       smem_u32(&sh->mma_bar))
                    : "memory");
     }
-    mbar_wait(&mma_bar, phase);
+    mbar_wait(&sh->mma_bar, phase);
     phase ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     __syncthreads();  // smem tiles may be overwritten by the next chunk
   }
+  sh->cn[tid] = bn_acc;
+  __syncthreads();
+  *an = an_acc;
+  *tmem_out = tmem_d;
+}
 
-  // ---- epilogue: thread t owns output row row0 + t (TMEM lane t) ----
+// 32 accumulator columns [c0, c0+32) of this thread's row (TMEM lane = warp*32 + lane)
+__device__ __forceinline__ void tc_load32(uint32_t tmem_d, int c0, uint32_t (&v)[32]) {
+  const uint32_t taddr = tmem_d + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + (uint32_t)c0;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tc_release(uint32_t tmem_d) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_N) : "memory");
+  }
+}
+
+template <int METRIC>
+__device__ __forceinline__ float tc_score(float dot, float xn, float cn) {
+  // faiss IndexFlat clamps the expanded L2 form at 0
+  return METRIC == kMetricL2 ? fmaxf(0.f, fmaf(-2.0f, dot, xn + cn)) : dot;
+}
+
+// ---- K2 / K6: dense score tile or fused row arg-min ----------------------------------------
+template <int METRIC, int EPI_ARGMIN>
+__global__ void __launch_bounds__(TC_NT)
+    dist_tc_kernel(const float* __restrict__ X, int64_t ldx, int n, const float* __restrict__ C, int64_t ldc, int m,
+                   int d, float* __restrict__ out, int64_t ldo, unsigned long long* __restrict__ best) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ TcShared sh;
+  const int tid = threadIdx.x;
+  const int row0 = blockIdx.y * TC_M, col0 = blockIdx.x * TC_N;
+  const float* arow = row0 + tid < n ? X + (int64_t)(row0 + tid) * ldx : nullptr;
+  const float* brow = col0 + tid < m ? C + (int64_t)(col0 + tid) * ldc : nullptr;
+  uint32_t tmem_d;
+  float xn;
+  tc_tile(smem, &sh, arow, brow, d, &tmem_d, &xn);
+
   const int gr = row0 + tid;
-  const float xn = (METRIC == kMetricL2 && gr < n) ? xnorm[gr] : 0.f;
   unsigned long long kbest = kKeySentinel;
 #pragma unroll 1
   for (int c0 = 0; c0 < TC_N; c0 += 32) {
     uint32_t v[32];
-    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tc_load32(tmem_d, c0, v);
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       const int gc = col0 + c0 + j;
-      float dot = __uint_as_float(v[j]);
-      float s = dot;
-      if (METRIC == kMetricL2) {
-        // faiss IndexFlat clamps the expanded form at 0
-        s = fmaxf(0.f, fmaf(-2.0f, dot, xn + __ldg(cnorm + (gc < m ? gc : 0))));
-      }
+      const float s = tc_score<METRIC>(__uint_as_float(v[j]), xn, sh.cn[c0 + j]);
       if (gr < n && gc < m) {
         if (EPI_ARGMIN) {
           unsigned long long key = make_key(score2ord<METRIC>(s), (uint32_t)gc);
@@ -178,41 +226,110 @@ __global__ void __launch_bounds__(TC_NT)
     }
   }
   if (EPI_ARGMIN && gr < n && kbest != kKeySentinel) atomicMin(best + gr, kbest);
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_N) : "memory");
-  }
+  tc_release(tmem_d);
 }
 
-// |x|^2 per row, fixed sequential order per lane then a fixed shuffle tree (deterministic)
-__global__ void row_norms_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d, float* __restrict__ out) {
-  int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (r >= n) return;
-  const float* row = x + r * ldx;
-  float s = 0.f;
-  for (int j = lane; j < d; j += 32) s = fmaf(row[j], row[j], s);
+// ---- K3 list-major: one (list, 128-pair group, 128-row tile) work item per CTA --------------
+template <int METRIC>
+__global__ void __launch_bounds__(TC_NT)
+    ivf_listmajor_tc_kernel(const float* __restrict__ xq, int64_t ldq, int d, const LmTile* __restrict__ tiles,
+                            const int32_t* __restrict__ pair_q, const int64_t* __restrict__ pair_off,
+                            ListDirectory dir, float* __restrict__ scores) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ TcShared sh;
+  const int tid = threadIdx.x;
+  const LmTile t = tiles[blockIdx.x];
+  const float* arow = nullptr;
+  int64_t obase = 0;
+  if (tid < t.npairs) {
+    arow = xq + (int64_t)pair_q[t.pair0 + tid] * ldq;
+    obase = pair_off[t.pair0 + tid] + t.row0;
+  }
+  const float* brow = tid < t.nrows ? dir.vecs[t.list] + (int64_t)(t.row0 + tid) * d : nullptr;
+  uint32_t tmem_d;
+  float xn;
+  tc_tile(smem, &sh, arow, brow, d, &tmem_d, &xn);
+#pragma unroll 1
+  for (int c0 = 0; c0 < TC_N; c0 += 32) {
+    uint32_t v[32];
+    tc_load32(tmem_d, c0, v);
+    if (tid < t.npairs) {
+      float* o = scores + obase + c0;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-  if (lane == 0) out[r] = s;
+      for (int j = 0; j < 32; j++)
+        if (c0 + j < t.nrows) o[j] = tc_score<METRIC>(__uint_as_float(v[j]), xn, sh.cn[c0 + j]);
+    }
+  }
+  tc_release(tmem_d);
+}
+
+// ---- segment select: per query, stream its P score segments, filter, keep the top-k ---------
+constexpr int SEG_NT = 256;
+
+template <int METRIC>
+__global__ void __launch_bounds__(SEG_NT)
+    seg_select_kernel(const float* __restrict__ scores, const int64_t* __restrict__ seg_off,
+                      const int32_t* __restrict__ probe_ids, int nprobe, ListDirectory dir, int k, int KP, int SORTN,
+                      FilterArgs f, unsigned long long* __restrict__ out_keys) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(sel_smem);
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_tau;
+  CandQueue cq{buf, &s_cnt, &s_tau, k, KP, SORTN};
+  cq.init();
+  const int q = blockIdx.x;
+  int est = 0;
+  for (int p = 0; p < nprobe; p++) {
+    const int list = probe_ids[(int64_t)q * nprobe + p];
+    const int64_t off = seg_off[(int64_t)q * nprobe + p];
+    if (list < 0 || list >= dir.nlist || off < 0) continue;  // CTA-uniform
+    const int len = dir.len[list];
+    const float* __restrict__ seg = scores + off;
+    const int64_t* __restrict__ lids = dir.ids[list];
+    for (int base = 0; base < len; base += SEG_NT) {
+      const unsigned long long tau = s_tau;
+      const int j = base + threadIdx.x;
+      bool pred = j < len;
+      unsigned long long key = kKeySentinel;
+      if (pred) {
+        const float s = seg[j];
+        pred = s <= f.max_score && s >= f.min_score;
+        const uint32_t ord = score2ord<METRIC>(s);
+        pred = pred && ord <= (uint32_t)(tau >> 32);
+        if (pred) {
+          const int64_t raw = lids[j];
+          pred = raw >= 0;  // tombstone (gamma_index_ivfflat.h:72)
+          const uint32_t vid = (uint32_t)raw;
+          if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
+          key = make_key(ord, vid);
+          pred = pred && key < tau;
+        }
+      }
+      cq.push_warp(pred, key);
+      est += __syncthreads_count(pred);
+      if (est + SEG_NT > cq.cap()) {
+        cq.flush();
+        est = 0;
+      }
+    }
+  }
+  __syncthreads();
+  cq.flush();
+  for (int i = threadIdx.x; i < k; i += SEG_NT) out_keys[(int64_t)q * k + i] = buf[i];
 }
 
 template <int METRIC, int EPI>
-cudaError_t launch_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d, const float* xnorm,
-                      const float* cnorm, float* out, int64_t ldo, unsigned long long* best, cudaStream_t st) {
-  const size_t smem = 4 * TC_TILE_BYTES;
-  cudaError_t e = cudaFuncSetAttribute(dist_tc_kernel<METRIC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d, float* out,
+                      int64_t ldo, unsigned long long* best, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(dist_tc_kernel<METRIC, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e != cudaSuccess) return e;
   const int max_rows = 65535 * TC_M;
   for (int r0 = 0; r0 < n; r0 += max_rows) {
     int nr = n - r0 < max_rows ? n - r0 : max_rows;
     dim3 grid((m + TC_N - 1) / TC_N, (nr + TC_M - 1) / TC_M);
-    dist_tc_kernel<METRIC, EPI><<<grid, TC_NT, smem, st>>>(X + (int64_t)r0 * ldx, ldx, nr, C, ldc, m, d,
-                                                          xnorm ? xnorm + r0 : nullptr, cnorm,
-                                                          out ? out + (int64_t)r0 * ldo : nullptr, ldo,
-                                                          best ? best + r0 : nullptr);
+    dist_tc_kernel<METRIC, EPI><<<grid, TC_NT, TC_SMEM, st>>>(X + (int64_t)r0 * ldx, ldx, nr, C, ldc, m, d,
+                                                             out ? out + (int64_t)r0 * ldo : nullptr, ldo,
+                                                             best ? best + r0 : nullptr);
     note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -222,29 +339,61 @@ cudaError_t launch_tc(const float* X, int64_t ldx, int n, const float* C, int64_
 
 }  // namespace
 
-cudaError_t launch_row_norms(const float* x, int64_t ldx, int64_t n, int d, float* out, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
-  row_norms_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(x, ldx, n, d, out);
+cudaError_t launch_dist_matrix_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                                  int metric, float* out, int64_t ldo, cudaStream_t st) {
+  if ((d & 3) || (ldx & 3) || (ldc & 3)) return cudaErrorInvalidValue;
+  if (n <= 0 || m <= 0) return cudaSuccess;
+  return metric == kMetricL2 ? launch_tc<kMetricL2, 0>(X, ldx, n, C, ldc, m, d, out, ldo, nullptr, st)
+                             : launch_tc<kMetricIP, 0>(X, ldx, n, C, ldc, m, d, out, ldo, nullptr, st);
+}
+
+cudaError_t launch_dist_argmin_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
+                                  int metric, unsigned long long* best, cudaStream_t st) {
+  if ((d & 3) || (ldx & 3) || (ldc & 3)) return cudaErrorInvalidValue;
+  if (n <= 0 || m <= 0) return cudaSuccess;
+  return metric == kMetricL2 ? launch_tc<kMetricL2, 1>(X, ldx, n, C, ldc, m, d, nullptr, 0, best, st)
+                             : launch_tc<kMetricIP, 1>(X, ldx, n, C, ldc, m, d, nullptr, 0, best, st);
+}
+
+cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const LmTile* tiles, int ntiles,
+                                    const int32_t* pair_q, const int64_t* pair_off, ListDirectory dir, int metric,
+                                    float* scores, cudaStream_t st) {
+  if ((d & 3) || (ldq & 3)) return cudaErrorInvalidValue;
+  if (ntiles <= 0) return cudaSuccess;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(ivf_listmajor_tc_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_tc_kernel<kMetricL2><<<ntiles, TC_NT, TC_SMEM, st>>>(xq, ldq, d, tiles, pair_q, pair_off, dir, scores);
+  } else {
+    e = cudaFuncSetAttribute(ivf_listmajor_tc_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_tc_kernel<kMetricIP><<<ntiles, TC_NT, TC_SMEM, st>>>(xq, ldq, d, tiles, pair_q, pair_off, dir, scores);
+  }
   note_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_dist_matrix_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
-                                  int metric, const float* xnorm, const float* cnorm, float* out, int64_t ldo,
-                                  cudaStream_t st) {
-  if ((d & 3) || (ldx & 3) || (ldc & 3)) return cudaErrorInvalidValue;
-  if (n <= 0 || m <= 0) return cudaSuccess;
-  return metric == kMetricL2 ? launch_tc<kMetricL2, 0>(X, ldx, n, C, ldc, m, d, xnorm, cnorm, out, ldo, nullptr, st)
-                             : launch_tc<kMetricIP, 0>(X, ldx, n, C, ldc, m, d, xnorm, cnorm, out, ldo, nullptr, st);
-}
-
-cudaError_t launch_dist_argmin_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d,
-                                  int metric, const float* xnorm, const float* cnorm, unsigned long long* best,
-                                  cudaStream_t st) {
-  if ((d & 3) || (ldx & 3) || (ldc & 3)) return cudaErrorInvalidValue;
-  if (n <= 0 || m <= 0) return cudaSuccess;
-  return metric == kMetricL2 ? launch_tc<kMetricL2, 1>(X, ldx, n, C, ldc, m, d, xnorm, cnorm, nullptr, 0, best, st)
-                             : launch_tc<kMetricIP, 1>(X, ldx, n, C, ldc, m, d, xnorm, cnorm, nullptr, 0, best, st);
+cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const int32_t* probe_ids, int nq, int nprobe,
+                              ListDirectory dir, int k, int metric, FilterArgs f, unsigned long long* out_keys,
+                              cudaStream_t st) {
+  if (nq <= 0) return cudaSuccess;
+  if (k <= 0 || k > 4096) return cudaErrorInvalidValue;
+  const int KP = next_pow2(k < 16 ? 16 : k);
+  const int SORTN = next_pow2(KP + 2 * SEG_NT);
+  const size_t smem = (size_t)SORTN * 8;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(seg_select_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    seg_select_kernel<kMetricL2><<<nq, SEG_NT, smem, st>>>(scores, seg_off, probe_ids, nprobe, dir, k, KP, SORTN, f, out_keys);
+  } else {
+    e = cudaFuncSetAttribute(seg_select_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    seg_select_kernel<kMetricIP><<<nq, SEG_NT, smem, st>>>(scores, seg_off, probe_ids, nprobe, dir, k, KP, SORTN, f, out_keys);
+  }
+  note_launch();
+  return cudaGetLastError();
 }
 
 }  // namespace gb
