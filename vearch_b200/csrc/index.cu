@@ -806,62 +806,30 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
   const int64_t npairs = (int64_t)nq * nprobe;
   if (npairs < (int64_t)nlist_ * 32 && !getenv("GB_LISTMAJOR_FORCE")) return 1;  // < 32 queries per list on average
   cudaStream_t st = s.stream();
-  std::vector<int32_t> h_probe(npairs);
-  GB_CUDA(cudaMemcpyAsync(h_probe.data(), probe_ids, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
+  ListDirectory dir = lists_->directory();
+  GB_ALLOC(d_cnt, int32_t, nlist_, s);
+  GB_ALLOC(d_start, int32_t, nlist_, s);
+  GB_ALLOC(d_cursor, int32_t, nlist_, s);
+  GB_ALLOC(d_tile_start, int32_t, nlist_, s);
+  GB_ALLOC(d_base_off, int64_t, nlist_, s);
+  GB_ALLOC(d_totals, int64_t, 3, s);
+  GB_CUDA(launch_lm_count_scan(probe_ids, npairs, dir, d_cnt, d_start, d_base_off, d_tile_start, d_totals, st));
+  int64_t h_totals[3] = {0, 0, 0};
+  GB_CUDA(cudaMemcpyAsync(h_totals, d_totals, sizeof(h_totals), cudaMemcpyDeviceToHost, st));
   GB_CUDA(cudaStreamSynchronize(st));
-  const std::vector<int>& lens = lists_->lens();
-  std::vector<int32_t> cnt(nlist_ + 1, 0);
-  for (int64_t j = 0; j < npairs; j++) {
-    int l = h_probe[j];
-    if (l >= 0 && l < nlist_ && lens[l] > 0) cnt[l + 1]++;
-  }
-  for (int l = 0; l < nlist_; l++) cnt[l + 1] += cnt[l];
-  const int64_t nvalid = cnt[nlist_];
-  std::vector<int32_t> start(cnt.begin(), cnt.end() - 1), h_pair_q(nvalid);
-  std::vector<int64_t> h_pair_off(nvalid), h_seg_off(npairs, -1);
-  std::vector<int32_t> cur(start);
-  // pair slots in list order; segments are laid out in that same order
-  std::vector<int64_t> slot_of(npairs, -1);
-  for (int64_t j = 0; j < npairs; j++) {
-    int l = h_probe[j];
-    if (l >= 0 && l < nlist_ && lens[l] > 0) {
-      int slot = cur[l]++;
-      h_pair_q[slot] = (int32_t)(j / nprobe);
-      slot_of[j] = slot;
-    }
-  }
-  int64_t total = 0;
-  std::vector<LmTile> tiles;
-  for (int l = 0; l < nlist_; l++) {
-    const int c = cnt[l + 1] - cnt[l];
-    if (!c) continue;
-    const int len = lens[l];
-    for (int i = 0; i < c; i++) {
-      h_pair_off[cnt[l] + i] = total;
-      total += len;
-    }
-    for (int p0 = 0; p0 < c; p0 += 128)
-      for (int r0 = 0; r0 < len; r0 += 128)
-        tiles.push_back({l, cnt[l] + p0, std::min(128, c - p0), r0, std::min(128, len - r0)});
-  }
-  if (total > ((int64_t)3 << 30)) return 1;  // > 12 GiB of scores: let the caller use the query-major scan
-  for (int64_t j = 0; j < npairs; j++)
-    if (slot_of[j] >= 0) h_seg_off[j] = h_pair_off[slot_of[j]];
-  GB_ALLOC(d_pair_q, int32_t, std::max<int64_t>(nvalid, 1), s);
-  GB_ALLOC(d_pair_off, int64_t, std::max<int64_t>(nvalid, 1), s);
+  const int64_t total = h_totals[0], ntiles = h_totals[1];
+  if (total > ((int64_t)3 << 30) || ntiles > INT32_MAX) return 1;  // > 12 GiB of scores: query-major scan instead
+  GB_ALLOC(d_pair_q, int32_t, npairs, s);
+  GB_ALLOC(d_pair_off, int64_t, npairs, s);
   GB_ALLOC(d_seg_off, int64_t, npairs, s);
-  GB_ALLOC(d_tiles, LmTile, std::max<size_t>(tiles.size(), 1), s);
+  GB_ALLOC(d_tiles, LmTile, std::max<int64_t>(ntiles, 1), s);
   GB_ALLOC(scores, float, std::max<int64_t>(total, 1), s);
-  GB_CUDA(cudaMemcpyAsync(d_pair_q, h_pair_q.data(), (size_t)nvalid * 4, cudaMemcpyHostToDevice, st));
-  GB_CUDA(cudaMemcpyAsync(d_pair_off, h_pair_off.data(), (size_t)nvalid * 8, cudaMemcpyHostToDevice, st));
-  GB_CUDA(cudaMemcpyAsync(d_seg_off, h_seg_off.data(), (size_t)npairs * 8, cudaMemcpyHostToDevice, st));
-  GB_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(LmTile), cudaMemcpyHostToDevice, st));
+  GB_CUDA(launch_lm_assign_tiles(probe_ids, npairs, nprobe, dir, d_cnt, d_start, d_cursor, d_base_off, d_tile_start,
+                                 d_pair_q, d_pair_off, d_seg_off, d_tiles, st));
   scan_timer_begin(st);
-  GB_CUDA(launch_ivf_listmajor_tc(xq, dpad_, dpad_, d_tiles, (int)tiles.size(), d_pair_q, d_pair_off, lists_->directory(),
-                                  metric, scores, st));
-  GB_CUDA(launch_seg_select(scores, d_seg_off, probe_ids, nq, nprobe, lists_->directory(), k, metric, f, out_keys, st));
+  GB_CUDA(launch_ivf_listmajor_tc(xq, dpad_, dpad_, d_tiles, (int)ntiles, d_pair_q, d_pair_off, dir, metric, scores, st));
+  GB_CUDA(launch_seg_select(scores, d_seg_off, probe_ids, nq, nprobe, dir, k, metric, f, out_keys, st));
   scan_timer_end(st);
-  GB_CUDA(cudaStreamSynchronize(st));  // host staging vectors go out of scope
   return 0;
 }
 

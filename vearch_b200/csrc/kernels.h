@@ -75,6 +75,15 @@ struct LmTile {
 cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const LmTile* tiles, int ntiles,
                                     const int32_t* pair_q, const int64_t* pair_off, ListDirectory dir, int metric,
                                     float* scores, cudaStream_t st);
+// device-side grouping of the (query, probe) pairs by list: histogram + scans (totals[0..2] = score
+// floats, tiles, valid pairs), then slot assignment and the tile table
+cudaError_t launch_lm_count_scan(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int32_t* cnt,
+                                 int32_t* start, int64_t* base_off, int32_t* tile_start, int64_t* totals,
+                                 cudaStream_t st);
+cudaError_t launch_lm_assign_tiles(const int32_t* probe_ids, int64_t npairs, int nprobe, ListDirectory dir,
+                                   const int32_t* cnt, const int32_t* start, int32_t* cursor, const int64_t* base_off,
+                                   const int32_t* tile_start, int32_t* pair_q, int64_t* pair_off, int64_t* seg_off,
+                                   LmTile* tiles, cudaStream_t st);
 // per query: stream its nprobe score segments (seg_off[q*nprobe+p], -1 = none), filter, top-k -> out_keys[q][k]
 cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const int32_t* probe_ids, int nq, int nprobe,
                               ListDirectory dir, int k, int metric, FilterArgs f, unsigned long long* out_keys,

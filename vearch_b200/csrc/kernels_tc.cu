@@ -318,6 +318,89 @@ __global__ void __launch_bounds__(SEG_NT)
   for (int i = threadIdx.x; i < k; i += SEG_NT) out_keys[(int64_t)q * k + i] = buf[i];
 }
 
+// ---- list-major grouping on device: histogram -> scan -> slot assignment -> tile table ------
+__global__ void lm_count_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, ListDirectory dir,
+                                int32_t* __restrict__ cnt) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npairs) return;
+  int l = probe_ids[j];
+  if (l >= 0 && l < dir.nlist && dir.len[l] > 0) atomicAdd(cnt + l, 1);
+}
+
+// single CTA: exclusive scans over the lists of (pairs, score floats, tiles); totals[0] = floats,
+// totals[1] = tiles, totals[2] = valid pairs
+__global__ void __launch_bounds__(1024)
+    lm_scan_kernel(const int32_t* __restrict__ cnt, ListDirectory dir, int32_t* __restrict__ start,
+                   int64_t* __restrict__ base_off, int32_t* __restrict__ tile_start, int64_t* __restrict__ totals) {
+  __shared__ long long s_pairs[1024], s_floats[1024], s_tiles[1024];
+  __shared__ long long carry[3];
+  const int tid = threadIdx.x;
+  if (tid == 0) carry[0] = carry[1] = carry[2] = 0;
+  __syncthreads();
+  for (int base = 0; base < dir.nlist; base += 1024) {
+    const int l = base + tid;
+    long long c = 0, fl = 0, tl = 0;
+    if (l < dir.nlist) {
+      c = cnt[l];
+      const long long len = dir.len[l];
+      fl = c * len;
+      tl = ((c + 127) / 128) * ((len + 127) / 128);
+    }
+    s_pairs[tid] = c, s_floats[tid] = fl, s_tiles[tid] = tl;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
+      long long a = 0, b = 0, e = 0;
+      if (tid >= off) a = s_pairs[tid - off], b = s_floats[tid - off], e = s_tiles[tid - off];
+      __syncthreads();
+      s_pairs[tid] += a, s_floats[tid] += b, s_tiles[tid] += e;
+      __syncthreads();
+    }
+    if (l < dir.nlist) {
+      start[l] = (int32_t)(carry[0] + s_pairs[tid] - c);
+      base_off[l] = carry[1] + s_floats[tid] - fl;
+      tile_start[l] = (int32_t)(carry[2] + s_tiles[tid] - tl);
+    }
+    __syncthreads();
+    if (tid == 1023) carry[0] += s_pairs[1023], carry[1] += s_floats[1023], carry[2] += s_tiles[1023];
+    __syncthreads();
+  }
+  if (tid == 0) totals[0] = carry[1], totals[1] = carry[2], totals[2] = carry[0];
+}
+
+__global__ void lm_assign_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, ListDirectory dir,
+                                 const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                                 const int64_t* __restrict__ base_off, int32_t* __restrict__ pair_q,
+                                 int64_t* __restrict__ pair_off, int64_t* __restrict__ seg_off) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npairs) return;
+  int l = probe_ids[j];
+  if (l < 0 || l >= dir.nlist || dir.len[l] <= 0) {
+    seg_off[j] = -1;
+    return;
+  }
+  const int within = atomicAdd(cursor + l, 1);  // slot order inside a list does not affect results
+  const int slot = start[l] + within;
+  const int64_t off = base_off[l] + (int64_t)within * dir.len[l];
+  pair_q[slot] = (int32_t)(j / nprobe);
+  pair_off[slot] = off;
+  seg_off[j] = off;
+}
+
+__global__ void lm_tiles_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ start,
+                                const int32_t* __restrict__ tile_start, ListDirectory dir, LmTile* __restrict__ tiles) {
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= dir.nlist) return;
+  const int c = cnt[l], len = dir.len[l];
+  if (c <= 0 || len <= 0) return;
+  int t = tile_start[l];
+  for (int p0 = 0; p0 < c; p0 += 128)
+    for (int r0 = 0; r0 < len; r0 += 128) {
+      LmTile tl;
+      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(128, c - p0), tl.row0 = r0, tl.nrows = min(128, len - r0);
+      tiles[t++] = tl;
+    }
+}
+
 template <int METRIC, int EPI>
 cudaError_t launch_tc(const float* X, int64_t ldx, int n, const float* C, int64_t ldc, int m, int d, float* out,
                       int64_t ldo, unsigned long long* best, cudaStream_t st) {
@@ -370,6 +453,34 @@ cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const L
     if (e != cudaSuccess) return e;
     ivf_listmajor_tc_kernel<kMetricIP><<<ntiles, TC_NT, TC_SMEM, st>>>(xq, ldq, d, tiles, pair_q, pair_off, dir, scores);
   }
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lm_count_scan(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int32_t* cnt,
+                                 int32_t* start, int64_t* base_off, int32_t* tile_start, int64_t* totals,
+                                 cudaStream_t st) {
+  if (npairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * dir.nlist, st);
+  if (e != cudaSuccess) return e;
+  lm_count_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, dir, cnt);
+  note_launch();
+  lm_scan_kernel<<<1, 1024, 0, st>>>(cnt, dir, start, base_off, tile_start, totals);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lm_assign_tiles(const int32_t* probe_ids, int64_t npairs, int nprobe, ListDirectory dir,
+                                   const int32_t* cnt, const int32_t* start, int32_t* cursor, const int64_t* base_off,
+                                   const int32_t* tile_start, int32_t* pair_q, int64_t* pair_off, int64_t* seg_off,
+                                   LmTile* tiles, cudaStream_t st) {
+  if (npairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * dir.nlist, st);
+  if (e != cudaSuccess) return e;
+  lm_assign_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, dir, start, cursor, base_off,
+                                                                    pair_q, pair_off, seg_off);
+  note_launch();
+  lm_tiles_kernel<<<(dir.nlist + 255) / 256, 256, 0, st>>>(cnt, start, tile_start, dir, tiles);
   note_launch();
   return cudaGetLastError();
 }
