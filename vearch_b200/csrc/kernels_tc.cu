@@ -249,22 +249,34 @@ __global__ void __launch_bounds__(TC_NT)
   uint32_t tmem_d;
   float xn;
   tc_tile(smem, &sh, arow, brow, d, &tmem_d, &xn);
+  // Epilogue.  Thread t owns accumulator row t, but its row lands in a score segment far away from
+  // its neighbours' rows, so writing straight from registers would touch 32 different cache lines
+  // per store.  Each warp therefore transposes its 32 x 32 block through shared memory (operand
+  // tiles are free by now; row stride 33 floats => conflict-free both ways) and writes every row
+  // as one contiguous 128-byte run.
+  float* stile = reinterpret_cast<float*>(smem) + (size_t)(tid >> 5) * 32 * 33;
+  const int lane = tid & 31, wrow0 = (tid >> 5) * 32;
 #pragma unroll 1
   for (int c0 = 0; c0 < TC_N; c0 += 32) {
     uint32_t v[32];
     tc_load32(tmem_d, c0, v);
-    if (tid < t.npairs) {
-      float* o = scores + obase + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j++)
-        if (c0 + j < t.nrows) o[j] = tc_score<METRIC>(__uint_as_float(v[j]), xn, sh.cn[c0 + j]);
+    for (int j = 0; j < 32; j++) stile[lane * 33 + j] = tc_score<METRIC>(__uint_as_float(v[j]), xn, sh.cn[c0 + j]);
+    __syncwarp();
+    const bool colok = c0 + lane < t.nrows;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; rr++) {
+      const long long ob = __shfl_sync(0xffffffffu, (long long)obase, rr);
+      if (wrow0 + rr < t.npairs && colok) scores[ob + c0 + lane] = stile[rr * 33 + lane];
     }
+    __syncwarp();
   }
   tc_release(tmem_d);
 }
 
 // ---- segment select: per query, stream its P score segments, filter, keep the top-k ---------
 constexpr int SEG_NT = 256;
+constexpr int SEG_ITEMS = 4;
 
 template <int METRIC>
 __global__ void __launch_bounds__(SEG_NT)
@@ -286,15 +298,22 @@ __global__ void __launch_bounds__(SEG_NT)
     const int len = dir.len[list];
     const float* __restrict__ seg = scores + off;
     const int64_t* __restrict__ lids = dir.ids[list];
-    for (int base = 0; base < len; base += SEG_NT) {
+    for (int base = 0; base < len; base += SEG_NT * SEG_ITEMS) {
       const unsigned long long tau = s_tau;
-      const int j = base + threadIdx.x;
-      bool pred = j < len;
-      unsigned long long key = kKeySentinel;
-      if (pred) {
-        const float s = seg[j];
-        pred = s <= f.max_score && s >= f.min_score;
-        const uint32_t ord = score2ord<METRIC>(s);
+      float sv[SEG_ITEMS];
+#pragma unroll
+      for (int u = 0; u < SEG_ITEMS; u++) {
+        const int j = base + u * SEG_NT + threadIdx.x;
+        sv[u] = j < len ? seg[j] : 0.f;
+      }
+      int pushed = 0;
+#pragma unroll
+      for (int u = 0; u < SEG_ITEMS; u++) {
+        const int j = base + u * SEG_NT + threadIdx.x;
+        const float sc = sv[u];
+        bool pred = j < len && sc <= f.max_score && sc >= f.min_score;
+        unsigned long long key = kKeySentinel;
+        const uint32_t ord = score2ord<METRIC>(sc);
         pred = pred && ord <= (uint32_t)(tau >> 32);
         if (pred) {
           const int64_t raw = lids[j];
@@ -304,10 +323,11 @@ __global__ void __launch_bounds__(SEG_NT)
           key = make_key(ord, vid);
           pred = pred && key < tau;
         }
+        cq.push_warp(pred, key);
+        pushed |= pred ? 1 : 0;
       }
-      cq.push_warp(pred, key);
-      est += __syncthreads_count(pred);
-      if (est + SEG_NT > cq.cap()) {
+      est += __syncthreads_count(pushed) * SEG_ITEMS;
+      if (est + SEG_NT * SEG_ITEMS > cq.cap()) {
         cq.flush();
         est = 0;
       }
@@ -491,7 +511,7 @@ cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const
   if (nq <= 0) return cudaSuccess;
   if (k <= 0 || k > 4096) return cudaErrorInvalidValue;
   const int KP = next_pow2(k < 16 ? 16 : k);
-  const int SORTN = next_pow2(KP + 2 * SEG_NT);
+  const int SORTN = next_pow2(KP + 2 * SEG_NT * SEG_ITEMS);
   const size_t smem = (size_t)SORTN * 8;
   cudaError_t e;
   if (metric == kMetricL2) {
