@@ -76,6 +76,8 @@ int gb_index_search_device(gb_index *index, int nq, const float *x_dev, int64_t 
 /* device time of the dominant scan kernel(s) of the last search, ms (0 unless timing enabled) */
 void gb_index_set_scan_timing(gb_index *index, int on);
 float gb_index_last_scan_ms(gb_index *index);
+/* name of the scan kernel(s) that served the last search (bench roofline label) */
+const char *gb_index_last_scan_kernel(gb_index *index);
 
 /* ---- index-state exchange (parity tests share centroids / codebooks / lists with the oracle,
  * SURVEY.md 8c; also the substrate for Dump/Load) ---- */

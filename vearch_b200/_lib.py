@@ -55,6 +55,8 @@ def _declare(l):
     l.gb_index_set_scan_timing.argtypes = [vp, i32]
     l.gb_index_last_scan_ms.restype = f32
     l.gb_index_last_scan_ms.argtypes = [vp]
+    l.gb_index_last_scan_kernel.restype = cstr
+    l.gb_index_last_scan_kernel.argtypes = [vp]
     l.gb_index_nlist.argtypes = [vp]
     l.gb_index_set_centroids.argtypes = [vp, vp, i32]
     l.gb_index_get_centroids.argtypes = [vp, vp]

@@ -461,6 +461,7 @@ int Index::flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int me
     partial = s.alloc_n<unsigned long long>((size_t)nq * nch * k);
     if (!partial) return -1;
   }
+  last_scan_kernel_ = "dist_tile_kernel+select_rows_kernel";
   scan_timer_begin(st);
   for (int q0 = 0; q0 < nq; q0 += QB) {
     int qb = std::min(QB, nq - q0);
@@ -826,6 +827,7 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
   GB_ALLOC(scores, float, std::max<int64_t>(total, 1), s);
   GB_CUDA(launch_lm_assign_tiles(probe_ids, npairs, nprobe, dir, d_cnt, d_start, d_cursor, d_base_off, d_tile_start,
                                  d_pair_q, d_pair_off, d_seg_off, d_tiles, st));
+  last_scan_kernel_ = "ivf_listmajor_tc_kernel+seg_select_kernel";
   scan_timer_begin(st);
   GB_CUDA(launch_ivf_listmajor_tc(xq, dpad_, dpad_, d_tiles, (int)ntiles, d_pair_q, d_pair_off, dir, metric, scores, st));
   GB_CUDA(launch_seg_select(scores, d_seg_off, probe_ids, nq, nprobe, dir, k, metric, f, out_keys, st));
@@ -845,6 +847,7 @@ int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int me
   }
   int nparts = ivfflat_scan_nparts(nprobe, lists_->max_len());
   GB_ALLOC(partial, unsigned long long, (size_t)nq * nparts * k, s);
+  last_scan_kernel_ = "ivfflat_scan_warp_kernel";
   scan_timer_begin(st);
   int avg_len = (int)(lists_->total() / std::max(1, nlist_));
   GB_CUDA(launch_ivfflat_scan(xq, dpad_, nq, dpad_, probe_ids, nprobe, lists_->directory(), lists_->max_len(), avg_len, k,
@@ -1066,6 +1069,7 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
   int pg = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)nprobe * nq / (148 * 32)));
   int ngroups = (nprobe + pg - 1) / pg;
   GB_ALLOC(partial, unsigned long long, (size_t)nq * ngroups * kk, s);
+  last_scan_kernel_ = "ivfpq_scan_kernel";
   scan_timer_begin(st);
   GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, pg, lists_->directory(), M_, d_table_, kk, metric, f,
                             partial, st));

@@ -182,6 +182,7 @@ class Index {
   // roofline: CUDA events recorded on the launching stream around the scan launches, read here.
   float last_scan_ms();
   void set_time_scan(bool on) { time_scan_ = on; }
+  const char* last_scan_kernel() const { return last_scan_kernel_; }
 
  protected:
   // GammaFLATIndex::Search (gamma_index_flat.cc:130-370) over rows [0, nrows)
@@ -205,6 +206,7 @@ class Index {
   std::mutex ev_mu_;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events_;
   bool time_scan_ = false;
+  const char* last_scan_kernel_ = "";  // which scan path served the last search (bench roofline label)
 };
 
 class FlatIndex : public Index {

@@ -228,6 +228,9 @@ int gb_index_search_device(gb_index* index, int nq, const float* x_dev, int64_t 
 void gb_index_set_scan_timing(gb_index* index, int on) {
   if (index && index->impl) index->impl->set_time_scan(on != 0);
 }
+const char* gb_index_last_scan_kernel(gb_index* index) {
+  return index && index->impl ? index->impl->last_scan_kernel() : "";
+}
 float gb_index_last_scan_ms(gb_index* index) { return index && index->impl ? index->impl->last_scan_ms() : 0.f; }
 
 static IVFFlatIndex* as_ivf(gb_index* index) {

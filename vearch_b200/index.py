@@ -173,6 +173,10 @@ class GammaIndex:
     def last_scan_ms(self):
         return float(_lib.lib().gb_index_last_scan_ms(self._h))
 
+    @property
+    def last_scan_kernel(self):
+        return _lib.lib().gb_index_last_scan_kernel(self._h).decode()
+
     # ---- index-state exchange (parity tests) -------------------------------------------
     def set_centroids(self, c):
         c = _f32(c)
