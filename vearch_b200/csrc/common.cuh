@@ -158,9 +158,13 @@ struct CandQueue {
   // all threads; must be preceded by a __syncthreads() after the last push
   __device__ __forceinline__ void flush() {
     int c = *cnt;
-    for (int i = KP + c + threadIdx.x; i < SORTN; i += blockDim.x) buf[i] = kKeySentinel;
+    // only the occupied prefix needs sorting: everything behind it is (made) sentinel
+    int n = KP;
+    while (n < KP + c) n <<= 1;
+    if (n < 2 * KP && n < SORTN) n = 2 * KP;
+    for (int i = KP + c + threadIdx.x; i < n; i += blockDim.x) buf[i] = kKeySentinel;
     __syncthreads();
-    block_bitonic_sort(buf, SORTN);
+    block_bitonic_sort(buf, n);
     if (threadIdx.x == 0) {
       *cnt = 0;
       *tau = buf[k - 1];

@@ -285,7 +285,54 @@ Index::Index(const std::string& type, int d, const ModelParams& mp, int device, 
   cudaStreamCreateWithFlags(&build_stream_, cudaStreamNonBlocking);
 }
 Index::~Index() {
+  for (auto& b : big_) {
+    cudaFree(b.p);
+    cudaEventDestroy(b.done);
+  }
   if (build_stream_) cudaStreamDestroy(build_stream_);
+}
+void* Index::big_acquire(size_t bytes, cudaStream_t st) {
+  std::lock_guard<std::mutex> g(big_mu_);
+  int best = -1;
+  for (size_t i = 0; i < big_.size(); i++)
+    if (!big_[i].busy && big_[i].cap >= bytes && (best < 0 || big_[i].cap < big_[best].cap)) best = (int)i;
+  if (best < 0) {
+    for (size_t i = 0; i < big_.size();) {  // drop idle buffers that are too small before growing
+      if (!big_[i].busy) {
+        cudaEventSynchronize(big_[i].done);
+        cudaFree(big_[i].p);
+        cudaEventDestroy(big_[i].done);
+        big_.erase(big_.begin() + i);
+      } else {
+        i++;
+      }
+    }
+    BigBuf b;
+    b.cap = bytes + bytes / 4;
+    b.busy = false;
+    if (cudaMalloc(&b.p, b.cap) != cudaSuccess) {
+      b.cap = bytes;
+      if (cudaMalloc(&b.p, b.cap) != cudaSuccess) {
+        set_last_error("cudaMalloc(" + std::to_string(bytes) + ") failed for scan scratch");
+        return nullptr;
+      }
+    }
+    cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming);
+    cudaEventRecord(b.done, st);
+    big_.push_back(b);
+    best = (int)big_.size() - 1;
+  }
+  big_[best].busy = true;
+  cudaStreamWaitEvent(st, big_[best].done, 0);  // previous user's kernels (possibly on another stream)
+  return big_[best].p;
+}
+void Index::big_release(void* p, cudaStream_t st) {
+  std::lock_guard<std::mutex> g(big_mu_);
+  for (auto& b : big_)
+    if (b.p == p) {
+      cudaEventRecord(b.done, st);
+      b.busy = false;
+    }
 }
 void Index::scan_timer_begin(cudaStream_t st) {
   if (!time_scan_) return;
@@ -824,7 +871,10 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
   GB_ALLOC(d_pair_off, int64_t, npairs, s);
   GB_ALLOC(d_seg_off, int64_t, npairs, s);
   GB_ALLOC(d_tiles, LmTile, std::max<int64_t>(ntiles, 1), s);
-  GB_ALLOC(scores, float, std::max<int64_t>(total, 1), s);
+  float* scores = static_cast<float*>(big_acquire((size_t)std::max<int64_t>(total, 1) * 4, st));
+  if (!scores) return -1;
+  auto rel_fn = [this, scores, st](void*) { big_release(scores, st); };
+  std::unique_ptr<void, decltype(rel_fn)> rel(scores, rel_fn);  // released (event-stamped) on every exit path
   GB_CUDA(launch_lm_assign_tiles(probe_ids, npairs, nprobe, dir, d_cnt, d_start, d_cursor, d_base_off, d_tile_start,
                                  d_pair_q, d_pair_off, d_seg_off, d_tiles, st));
   last_scan_kernel_ = "ivf_listmajor_tc_kernel+seg_select_kernel";

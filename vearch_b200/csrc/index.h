@@ -201,6 +201,18 @@ class Index {
   mutable std::shared_mutex mu_;  // searches shared, index mutation exclusive
   std::mutex build_mu_;           // serialises train / add_pending / update_vector (one writer at a time)
   cudaStream_t build_stream_ = nullptr;
+  // grow-only cache of multi-GB scratch (list-major score segments): stream-ordered pools re-map
+  // such blocks on every search when the caller's stream is the legacy default stream
+  void* big_acquire(size_t bytes, cudaStream_t st);
+  void big_release(void* p, cudaStream_t st);
+  struct BigBuf {
+    void* p;
+    size_t cap;
+    bool busy;
+    cudaEvent_t done;
+  };
+  std::mutex big_mu_;
+  std::vector<BigBuf> big_;
   void scan_timer_begin(cudaStream_t st);
   void scan_timer_end(cudaStream_t st);
   std::mutex ev_mu_;

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(SEG_NT)
   cq.init();
   const int q = blockIdx.x;
   int est = 0;
+  const int flush_at = max(SEG_NT * SEG_ITEMS - KP, 4 * KP);
   for (int p = 0; p < nprobe; p++) {
     const int list = probe_ids[(int64_t)q * nprobe + p];
     const int64_t off = seg_off[(int64_t)q * nprobe + p];
@@ -326,11 +327,14 @@ __global__ void __launch_bounds__(SEG_NT)
         cq.push_warp(pred, key);
         pushed |= pred ? 1 : 0;
       }
-      est += __syncthreads_count(pushed) * SEG_ITEMS;
-      if (est + SEG_NT * SEG_ITEMS > cq.cap()) {
-        cq.flush();
-        est = 0;
-      }
+      // exact fill after a barrier pair (one more barrier than an upper bound, but flushes -- block
+      // bitonic sorts -- are what this kernel spends its instructions on): flush early so tau
+      // tightens after the first ~1k candidates, and whenever the next round might overflow
+      (void)pushed;
+      __syncthreads();
+      est = s_cnt;
+      __syncthreads();
+      if (est >= flush_at || est + SEG_NT * SEG_ITEMS > cq.cap()) cq.flush();
     }
   }
   __syncthreads();
