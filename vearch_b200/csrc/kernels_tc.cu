@@ -33,9 +33,10 @@ namespace gb {
 
 namespace {
 
-constexpr int TC_M = 128, TC_N = 128, TC_BK = 32, TC_NT = 128;
-constexpr int TC_TILE_BYTES = TC_M * TC_BK * 4;  // 16 KiB per operand tile (hi or lo)
-constexpr int TC_SMEM = 4 * TC_TILE_BYTES;
+constexpr int TC_M = 128, TC_N = 128, TC_BK = 16, TC_NT = 128, TC_STAGES = 2;
+constexpr int TC_TILE_BYTES = TC_M * TC_BK * 4;          // 8 KiB per operand part (hi or lo) per stage
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // a_hi, a_lo, b_hi, b_lo
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES;      // 64 KiB
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
@@ -62,22 +63,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 
 // One 128 x 128 tile: D[i][j] = <A_i, B_j> over d columns.  arow / brow: row pointers of THIS
 // thread's row of A and B (nullptr => all zeros).  On return the accumulator sits in TMEM at
-// *tmem_out (lane = A row, column = B row), thread t holds |A_t|^2 in *an and cn_s[t] = |B_t|^2.
+// *tmem_out (lane = A row, column = B row), thread t holds |A_t|^2 in *an and sh->cn[t] = |B_t|^2.
 // Caller must have 128 threads, TC_SMEM bytes of dynamic smem at `smem`, and must call tc_release().
+//
+// Pipeline: two smem stages of K = 16.  While the tensor core works on stage s (asynchronously,
+// completion signalled by tcgen05.commit on mma_bar[s]) the threads already hold the NEXT chunk in
+// registers (global loads issued one chunk ahead) and write it into the other stage, so neither the
+// global-load latency nor the MMA latency sits on the critical path.
 struct TcShared {
-  uint64_t mma_bar;
+  uint64_t mma_bar[TC_STAGES];
   uint32_t tmem_base;
   float cn[TC_N];
 };
 
 __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const float* __restrict__ arow,
                                         const float* __restrict__ brow, int d, uint32_t* tmem_out, float* an) {
-  unsigned char* a_hi = smem;
-  unsigned char* a_lo = smem + TC_TILE_BYTES;
-  unsigned char* b_hi = smem + 2 * TC_TILE_BYTES;
-  unsigned char* b_lo = smem + 3 * TC_TILE_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5;
-
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "n"(TC_N)
@@ -85,7 +86,7 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(&sh->mma_bar, 1);
+    for (int s = 0; s < TC_STAGES; s++) mbar_init(&sh->mma_bar[s], 1);
     mbar_fence_init();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -96,23 +97,39 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
   // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-  // canonical layout: element (r, k) of a 128 x 32 tile lives at (k/4)*(128*16) + (r/8)*128 + (r%8)*16 + (k%4)*4
+  // canonical layout: element (r, k) of a 128 x 16 tile lives at (k/4)*(128*16) + (r/8)*128 + (r%8)*16 + (k%4)*4
   const uint32_t LBO = TC_M * 16, SBO = 128;
   const uint32_t row_off = (uint32_t)(tid >> 3) * SBO + (uint32_t)(tid & 7) * 16;
+  constexpr int NV = TC_BK / 4;  // float4 per operand row per chunk
 
   float an_acc = 0.f, bn_acc = 0.f;
-  uint32_t phase = 0;
   const int nk = (d + TC_BK - 1) / TC_BK;
-  for (int kc = 0; kc < nk; kc++) {
-    const int k0 = kc * TC_BK;
-    // ---- stage this thread's row of both operands (8 float4 each), split into hi / lo ----
+  float4 pa[NV], pb[NV];
+  auto prefetch = [&](int kc) {
 #pragma unroll
-    for (int kb = 0; kb < TC_BK / 4; kb++) {
-      const int gk = k0 + kb * 4;
+    for (int kb = 0; kb < NV; kb++) {
+      const int gk = kc * TC_BK + kb * 4;
+      pa[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[kb] = pa[kb];
+      if (arow && gk < d) pa[kb] = __ldg(reinterpret_cast<const float4*>(arow + gk));
+      if (brow && gk < d) pb[kb] = __ldg(reinterpret_cast<const float4*>(brow + gk));
+    }
+  };
+  prefetch(0);
+  for (int kc = 0; kc < nk; kc++) {
+    const int s = kc & 1;
+    unsigned char* a_hi = smem + (size_t)s * TC_STAGE_BYTES;
+    unsigned char* a_lo = a_hi + TC_TILE_BYTES;
+    unsigned char* b_hi = a_hi + 2 * TC_TILE_BYTES;
+    unsigned char* b_lo = a_hi + 3 * TC_TILE_BYTES;
+    if (kc >= TC_STAGES) {  // the MMAs of chunk kc-2 must have finished reading this stage
+      mbar_wait(&sh->mma_bar[s], (uint32_t)((kc / TC_STAGES - 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+#pragma unroll
+    for (int kb = 0; kb < NV; kb++) {
       const uint32_t off = (uint32_t)kb * LBO + row_off;  // consecutive threads -> consecutive rows: conflict-free
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      if (arow && gk < d) va = __ldg(reinterpret_cast<const float4*>(arow + gk));
-      if (brow && gk < d) vb = __ldg(reinterpret_cast<const float4*>(brow + gk));
+      const float4 va = pa[kb], vb = pb[kb];
       an_acc = fmaf(va.x, va.x, an_acc), an_acc = fmaf(va.y, va.y, an_acc);
       an_acc = fmaf(va.z, va.z, an_acc), an_acc = fmaf(va.w, va.w, an_acc);
       bn_acc = fmaf(vb.x, vb.x, bn_acc), bn_acc = fmaf(vb.y, vb.y, bn_acc);
@@ -129,6 +146,7 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
       *reinterpret_cast<float4*>(b_hi + off) = bh;
       *reinterpret_cast<float4*>(b_lo + off) = bl;
     }
+    if (kc + 1 < nk) prefetch(kc + 1);  // global loads for the next chunk fly during this chunk's MMAs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async (tensor) proxy
     __syncthreads();
     if (tid == 0) {
@@ -144,16 +162,15 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
         tc_mma_tf32(tmem_d, dah, dbl, idesc, 1);
         tc_mma_tf32(tmem_d, dal, dbh, idesc, 1);
       }
-      // arrives on mma_bar when every MMA issued so far has finished reading smem / writing TMEM
+      // arrives on mma_bar[s] when every MMA issued so far has finished reading smem / writing TMEM
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(&sh->mma_bar))
+                       smem_u32(&sh->mma_bar[s]))
                    : "memory");
     }
-    mbar_wait(&sh->mma_bar, phase);
-    phase ^= 1;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __syncthreads();  // smem tiles may be overwritten by the next chunk
   }
+  // the last commit covers every MMA of the tile
+  mbar_wait(&sh->mma_bar[(nk - 1) & 1], (uint32_t)(((nk - 1) / TC_STAGES) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   sh->cn[tid] = bn_acc;
   __syncthreads();
   *an = an_acc;
