@@ -478,6 +478,38 @@ def test_tensor_core_distance_kernel(metric, n, m, d):
     assert np.abs(tc - exact).max() <= 2e-5 * scale
 
 
+def test_request_coalescing_matches_direct_search(ivf_state, ivfflat_index):
+    """Many concurrent nq=1..3 Search calls are merged into device batches by the index's worker
+    thread (reference: gamma_index_ivfflat_gpu.cc:302-396); every caller must get exactly the rows
+    a direct search returns."""
+    import threading
+    s = ivf_state
+    xq = s["xq"]
+    ref_d, ref_i = ivfflat_index.search(xq, 10, params={"nprobe": 8})  # nq = 48 > 16: not coalesced
+    slices = [(i, min(i + 1 + (i % 3), len(xq))) for i in range(0, len(xq), 2)]
+    out = {}
+    errs = []
+
+    def work(a, b):
+        try:
+            for _ in range(5):
+                out[(a, b)] = ivfflat_index.search(xq[a:b], 10, params={"nprobe": 8})
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=ab) for ab in slices]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs
+    for (a, b), (d, i) in out.items():
+        assert np.array_equal(d, ref_d[a:b]) and np.array_equal(i, ref_i[a:b])
+    # a different k / params must not be merged into the same batch
+    d5, i5 = ivfflat_index.search(xq[:2], 5, params={"nprobe": 8})
+    assert np.array_equal(d5, ref_d[:2, :5]) and np.array_equal(i5, ref_i[:2, :5])
+
+
 @pytest.mark.parametrize("metric", [L2, IP])
 def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric):
     """Many queries per list => the list-major grouped-GEMM scan (kernels_tc.cu) is selected.

@@ -285,6 +285,12 @@ Index::Index(const std::string& type, int d, const ModelParams& mp, int device, 
   cudaStreamCreateWithFlags(&build_stream_, cudaStreamNonBlocking);
 }
 Index::~Index() {
+  {
+    std::lock_guard<std::mutex> lk(co_mu_);
+    co_stop_ = true;
+  }
+  co_cv_.notify_all();
+  if (co_thread_.joinable()) co_thread_.join();
   for (auto& b : big_) {
     cudaFree(b.p);
     cudaEventDestroy(b.done);
@@ -445,7 +451,108 @@ int Index::search_device(const SearchContext& ctx, int nq, const float* x_dev, i
   return 0;
 }
 
+static bool coalesce_enabled() {
+  static int v = [] {
+    const char* e = getenv("GB_COALESCE");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+static constexpr int kCoalesceMaxNq = 16;     // requests at most this large are merged
+static constexpr int kCoalesceMaxBatch = 512;  // queries per merged device batch (reference kMaxBatch)
+
+bool Index::coalescable(const SearchContext& ctx, int nq) const {
+  return coalesce_enabled() && nq <= kCoalesceMaxNq && !ctx.del_bitmap && !ctx.filter_bitmap;
+}
+
+static bool same_signature(const SearchContext& a, int ka, const SearchContext& b, int kb) {
+  return ka == kb && a.min_score == b.min_score && a.max_score == b.max_score && a.params.nprobe == b.params.nprobe &&
+         a.params.metric == b.params.metric && a.params.recall_num == b.params.recall_num &&
+         a.params.brute_force == b.params.brute_force;
+}
+
+void Index::coalesce_loop() {
+  cudaSetDevice(device_);
+  std::vector<CoReq*> batch;
+  std::vector<float> xs, dd;
+  std::vector<int64_t> ii;
+  for (;;) {
+    batch.clear();
+    {
+      std::unique_lock<std::mutex> lk(co_mu_);
+      co_cv_.wait(lk, [this] { return co_stop_ || !co_queue_.empty(); });
+      if (co_stop_ && co_queue_.empty()) return;
+      CoReq* first = co_queue_.front();
+      int total = 0;
+      for (size_t i = 0; i < co_queue_.size();) {  // whatever piled up while the previous batch ran
+        CoReq* r = co_queue_[i];
+        if (total + r->nq <= kCoalesceMaxBatch && same_signature(*first->ctx, first->k, *r->ctx, r->k)) {
+          batch.push_back(r);
+          total += r->nq;
+          co_queue_.erase(co_queue_.begin() + i);
+        } else {
+          i++;
+        }
+      }
+    }
+    int total = 0;
+    for (CoReq* r : batch) total += r->nq;
+    const int k = batch[0]->k;
+    int rc;
+    if (batch.size() == 1) {
+      rc = search_direct(*batch[0]->ctx, batch[0]->nq, batch[0]->x, k, batch[0]->out_dis, batch[0]->out_ids);
+    } else {
+      xs.resize((size_t)total * d_);
+      dd.resize((size_t)total * k);
+      ii.resize((size_t)total * k);
+      size_t o = 0;
+      for (CoReq* r : batch) {
+        memcpy(xs.data() + o * d_, r->x, (size_t)r->nq * d_ * 4);
+        o += r->nq;
+      }
+      rc = search_direct(*batch[0]->ctx, total, xs.data(), k, dd.data(), ii.data());
+      o = 0;
+      for (CoReq* r : batch) {
+        if (rc == 0) {
+          memcpy(r->out_dis, dd.data() + o * k, (size_t)r->nq * k * 4);
+          memcpy(r->out_ids, ii.data() + o * k, (size_t)r->nq * k * 8);
+        }
+        o += r->nq;
+      }
+    }
+    std::string err = rc ? last_error() : "";
+    {
+      std::lock_guard<std::mutex> lk(co_mu_);
+      for (CoReq* r : batch) {
+        r->rc = rc;
+        r->err = err;
+        r->done = true;
+      }
+    }
+    co_done_cv_.notify_all();
+  }
+}
+
 int Index::search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids) {
+  if (nq <= 0) return 0;
+  if (!coalescable(ctx, nq)) return search_direct(ctx, nq, x, k, out_dis, out_ids);
+  CoReq req;
+  req.ctx = &ctx, req.nq = nq, req.k = k, req.x = x, req.out_dis = out_dis, req.out_ids = out_ids;
+  {
+    std::unique_lock<std::mutex> lk(co_mu_);
+    if (!co_started_) {
+      co_started_ = true;
+      co_thread_ = std::thread(&Index::coalesce_loop, this);
+    }
+    co_queue_.push_back(&req);
+    co_cv_.notify_one();
+    co_done_cv_.wait(lk, [&req] { return req.done; });
+  }
+  if (req.rc) set_last_error(req.err);
+  return req.rc;
+}
+
+int Index::search_direct(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids) {
   if (nq <= 0) return 0;
   cudaSetDevice(device_);
   cudaStream_t st = thread_stream(device_);

@@ -8,8 +8,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <condition_variable>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <shared_mutex>
 #include <string>
 #include <vector>
@@ -175,6 +177,8 @@ class Index {
   // IndexModel::Search (index_model.h:296): x = nq x d floats; out = nq x k, unfilled id -1.
   // Returns 0, -1 on error (last_error), -2 if killed.  x/out pointers are host unless *_dev.
   int search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
+  // one H2D -> kernels -> D2H round trip on the calling thread's stream
+  int search_direct(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
   int search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
                     int64_t* out_ids_dev, cudaStream_t st);
   virtual int64_t index_mem_bytes() const { return 0; }
@@ -200,6 +204,28 @@ class Index {
   bool trained_ = false;
   mutable std::shared_mutex mu_;  // searches shared, index mutation exclusive
   std::mutex build_mu_;           // serialises train / add_pending / update_vector (one writer at a time)
+
+  // Request coalescing (reference: the batching thread of its GPU index,
+  // index/impl/gpu/gamma_index_ivfflat_gpu.cc:302-396): concurrent small Search calls with the
+  // same (k, retrieval params, score window, no bitmaps) are merged into one device batch by a
+  // worker thread; callers block until their slice of the result is ready.
+  struct CoReq {
+    const SearchContext* ctx;
+    int nq, k;
+    const float* x;
+    float* out_dis;
+    int64_t* out_ids;
+    int rc = 0;
+    bool done = false;
+    std::string err;
+  };
+  void coalesce_loop();
+  bool coalescable(const SearchContext& ctx, int nq) const;
+  std::mutex co_mu_;
+  std::condition_variable co_cv_, co_done_cv_;
+  std::vector<CoReq*> co_queue_;
+  std::thread co_thread_;
+  bool co_stop_ = false, co_started_ = false;
   cudaStream_t build_stream_ = nullptr;
   // grow-only cache of multi-GB scratch (list-major score segments): stream-ordered pools re-map
   // such blocks on every search when the caller's stream is the legacy default stream
