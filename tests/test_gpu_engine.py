@@ -235,6 +235,35 @@ def test_kill_switch_and_config(tmp_path, data):
     e.close()
 
 
+def test_enable_realtime_searches_unindexed_tail(tmp_path, data):
+    """table.enable_realtime: documents that are stored but not yet picked up by the indexing thread
+    are searched brute-force and merged (vector_manager.cc:854-889, 971-1053)."""
+    db, xq = data
+    e = eng_mod().GammaEngine(str(tmp_path), space_name="rt")
+    e.create_table("rt", D, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 2000},
+                   refresh_interval=600000, enable_realtime=True)  # the indexing loop sleeps 10 min between passes
+    add_all(e, db[:2000])
+    e.wait_indexed(2000)
+    add_all(e, db[2000:2300], start=2000)  # these stay un-indexed during the test
+    assert e.status()["min_indexed_num"] == 2000
+    res = e.search(db[2100:2104], 1, index_params={"nprobe": 16})
+    assert keys_of(res) == [[f"doc{i}"] for i in range(2100, 2104)] and all(s[0] == 0.0 for s in scores_of(res))
+    res = e.search(xq, 10, index_params={"nprobe": 16})
+    do, io = orc.flat_search(db[:2300], xq, 10, L2)
+    assert keys_of(res) == [[f"doc{i}" for i in row] for row in io]  # nprobe == nlist + tail => exact
+    e.close()
+    # without enable_realtime the tail is invisible until the next indexing pass (reference behaviour)
+    e2 = eng_mod().GammaEngine(str(tmp_path / "b"), space_name="nrt")
+    e2.create_table("nrt", D, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 2000},
+                    refresh_interval=600000)
+    add_all(e2, db[:2000])
+    e2.wait_indexed(2000)
+    add_all(e2, db[2000:2300], start=2000)
+    res = e2.search(db[2100:2101], 1, index_params={"nprobe": 16})
+    assert keys_of(res) != [["doc2100"]]
+    e2.close()
+
+
 def test_concurrent_search_while_adding(tmp_path, data):
     db, xq = data
     e = make_engine(tmp_path, "IVFFLAT", {"ncentroids": 16, "nprobe": 8, "metric_type": "L2", "training_threshold": 1000})

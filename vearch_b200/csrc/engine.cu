@@ -397,6 +397,7 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   std::string err;
   if (!parse_retrieval_params(req.index_params, &ctx.params, &err)) return Status::Make(kInvalidArgument, err);
   ctx.params.brute_force = brute != 0;
+  ctx.search_unindexed_tail = enable_realtime_;
   // proto3 drops zero-valued doubles; the router always sends a window (doc_query.go:1220-1226)
   ctx.min_score = vq.has_min ? (float)std::max(vq.min_score, -(double)FLT_MAX) : (vq.has_max ? 0.f : -FLT_MAX);
   ctx.max_score = vq.has_max ? (float)std::min(vq.max_score, (double)FLT_MAX) : (vq.has_min ? 0.f : FLT_MAX);

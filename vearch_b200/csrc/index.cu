@@ -445,6 +445,21 @@ int Index::search_device(const SearchContext& ctx, int nq, const float* x_dev, i
     rc = flat_search_dev(ctx, f, metric, nq, xq, k, store_->size(), keys, s);
   } else {
     rc = search_keys_dev(ctx, f, metric, nq, xq, k, keys, s);
+    // enable_realtime (vector_manager.cc:854-889, 971-1053): vectors stored but not yet indexed are
+    // searched brute-force (the reference's MemoryBuffer FLAT index) and merged by score
+    const int64_t tail0 = indexed_count_, tail1 = store_->size();
+    if (rc == 0 && ctx.search_unindexed_tail && tail1 > tail0) {
+      GB_ALLOC(both, unsigned long long, (size_t)nq * 2 * k, s);
+      GB_CUDA(cudaMemcpy2DAsync(both, (size_t)2 * k * 8, keys, (size_t)k * 8, (size_t)k * 8, nq,
+                                cudaMemcpyDeviceToDevice, st));
+      GB_ALLOC(tailk, unsigned long long, (size_t)nq * k, s);
+      rc = flat_search_dev(ctx, f, metric, nq, xq, k, tail1, tailk, s, tail0);
+      if (rc == 0) {
+        GB_CUDA(cudaMemcpy2DAsync(both + k, (size_t)2 * k * 8, tailk, (size_t)k * 8, (size_t)k * 8, nq,
+                                  cudaMemcpyDeviceToDevice, st));
+        GB_CUDA(launch_select_keys(both, (int64_t)2 * k, nq, 2 * k, k, keys, k, st));
+      }
+    }
   }
   if (rc) return rc;
   GB_CUDA(launch_decode_keys(keys, k, nq, k, metric, out_dis_dev, out_ids_dev, 0, st));
@@ -468,7 +483,7 @@ bool Index::coalescable(const SearchContext& ctx, int nq) const {
 static bool same_signature(const SearchContext& a, int ka, const SearchContext& b, int kb) {
   return ka == kb && a.min_score == b.min_score && a.max_score == b.max_score && a.params.nprobe == b.params.nprobe &&
          a.params.metric == b.params.metric && a.params.recall_num == b.params.recall_num &&
-         a.params.brute_force == b.params.brute_force;
+         a.params.brute_force == b.params.brute_force && a.search_unindexed_tail == b.search_unindexed_tail;
 }
 
 void Index::coalesce_loop() {
@@ -589,10 +604,11 @@ int Index::search_direct(const SearchContext& ctx, int nq, const float* x, int k
 
 // GammaFLATIndex::Search (gamma_index_flat.cc:130-370): every stored row, filters before top-k.
 int Index::flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
-                           int64_t nrows, unsigned long long* out_keys, Scratch& s) {
+                           int64_t nrows, unsigned long long* out_keys, Scratch& s, int64_t row_begin) {
   (void)ctx;
   cudaStream_t st = s.stream();
-  if (nrows <= 0) return launch_fill_u64(out_keys, (int64_t)nq * k, kKeySentinel, st) == cudaSuccess ? 0 : -1;
+  const int64_t flat_row_begin_ = row_begin;
+  if (nrows <= row_begin) return launch_fill_u64(out_keys, (int64_t)nq * k, kKeySentinel, st) == cudaSuccess ? 0 : -1;
   const int64_t CC = std::min<int64_t>(131072, store_->seg_rows());  // DB rows per distance block
   struct Chunk {
     const float* base;
@@ -600,14 +616,14 @@ int Index::flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int me
     int cnt;
   };
   std::vector<Chunk> chunks;
-  for (int64_t r = 0; r < nrows;) {
+  for (int64_t r = flat_row_begin_; r < nrows;) {
     int64_t si = r >> store_->seg_shift(), off = r & (store_->seg_rows() - 1);
     int64_t cnt = std::min<int64_t>(std::min(nrows - r, store_->seg_rows() - off), CC);
     chunks.push_back({store_->seg((int)si) + off * dpad_, r, (int)cnt});
     r += cnt;
   }
   const int nch = (int)chunks.size();
-  int64_t ldo = round_up(std::min<int64_t>(CC, nrows), 4);
+  int64_t ldo = round_up(std::min<int64_t>(CC, nrows - row_begin), 4);
   int QB = (int)std::max<int64_t>(1, std::min<int64_t>(nq, ((int64_t)1 << 28) / ldo));  // <= 1 GiB of scores
   GB_ALLOC(scores, float, (size_t)QB * ldo, s);
   unsigned long long* partial = out_keys;

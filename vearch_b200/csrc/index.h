@@ -147,6 +147,7 @@ struct SearchContext {  // RetrievalContext / SearchCondition (common/gamma_comm
   const uint8_t* filter_bitmap = nullptr;  // host, bit set => allowed (nullptr => no filter)
   int64_t bitmap_bits = 0;
   float min_score = -3.4028235e38f, max_score = 3.4028235e38f;
+  bool search_unindexed_tail = false;  // table.enable_realtime: brute-force the not-yet-indexed vectors too
   RetrievalParams params;
 };
 
@@ -191,7 +192,7 @@ class Index {
  protected:
   // GammaFLATIndex::Search (gamma_index_flat.cc:130-370) over rows [0, nrows)
   int flat_search_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
-                      int64_t nrows, unsigned long long* out_keys, Scratch& s);
+                      int64_t nrows, unsigned long long* out_keys, Scratch& s, int64_t row_begin = 0);
   virtual int search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
                               unsigned long long* out_keys, Scratch& s) = 0;
   int upload_bitmaps(const SearchContext& ctx, FilterArgs* f, Scratch& s);
