@@ -155,9 +155,15 @@ struct CandQueue {
       if (pred) buf[KP + base + __popc(mask & ((1u << lane) - 1u))] = key;
     }
   }
-  // all threads; must be preceded by a __syncthreads() after the last push
-  __device__ __forceinline__ void flush() {
+  // all threads; must be preceded by a __syncthreads() after the last push.  Small buffers are
+  // sorted (bitonic, occupied prefix only); big ones go through an MSB radix select, whose cost is
+  // linear in the fill.  final_sort: leave buf[0, KP) sorted ascending (the kernel's result).
+  __device__ __forceinline__ void flush(bool final_sort = false) {
     int c = *cnt;
+    if (KP + c > kSelectMin) {
+      flush_select(c, final_sort);
+      return;
+    }
     // only the occupied prefix needs sorting: everything behind it is (made) sentinel
     int n = KP;
     while (n < KP + c) n <<= 1;
@@ -170,6 +176,110 @@ struct CandQueue {
       *tau = buf[k - 1];
     }
     __syncthreads();
+  }
+
+  static constexpr int kSelectMin = 1024;
+
+  // Radix-select flush.  Finds the byte prefix P (most significant bytes first) such that exactly
+  // k valid keys are <= P|11..1, compacts those keys to buf[0, k) in place (unordered), pads
+  // buf[k, KP) with sentinels and sets tau = P|11..1.  That tau is >= the true k-th best key and
+  // < every discarded key, so the "key < tau" admission test stays exact.  Keys are unique
+  // (one vid appears once per query), which bounds the loop at 8 byte passes.
+  __device__ __forceinline__ void flush_select(int c, bool final_sort) {
+    __shared__ int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_done, s_valid, s_pos;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int n = KP + c;
+    if (tid == 0) {
+      s_valid = 0;
+      s_pos = 0;
+    }
+    unsigned long long prefix = 0, tup = kKeySentinel;
+    int need = k;
+    bool all_valid = false;
+    for (int shift = 56;; shift -= 8) {
+      for (int i = tid; i < 256; i += nt) s_hist[i] = 0;
+      __syncthreads();
+      int myvalid = 0;
+      for (int i = tid; i < n; i += nt) {
+        unsigned long long key = buf[i];
+        bool match;
+        if (shift == 56) {
+          myvalid += key != kKeySentinel;
+          match = true;
+        } else {
+          match = (key >> (shift + 8)) == prefix;
+        }
+        if (match) atomicAdd(&s_hist[(int)(key >> shift) & 255], 1);
+      }
+      if (shift == 56) {
+        myvalid = __reduce_add_sync(0xffffffffu, myvalid);
+        if (lane == 0 && myvalid) atomicAdd(&s_valid, myvalid);
+      }
+      __syncthreads();
+      if (shift == 56 && s_valid <= k) {
+        all_valid = true;
+        break;
+      }
+      if (tid < 32) {
+        int h[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          h[j] = s_hist[lane * 8 + j];
+          sum += h[j];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          int v = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += v;
+        }
+        int before = incl - sum;
+        if (before < need && need <= incl) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (before < need && need <= before + h[j]) {
+              s_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
+              s_need = need - before;
+              s_done = (h[j] == need - before) ? 1 : 0;
+            }
+            before += h[j];
+          }
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      need = s_need;
+      if (s_done || shift == 0) {
+        tup = shift == 0 ? prefix : ((prefix << shift) | ((1ull << shift) - 1ull));
+        break;
+      }
+    }
+    // in-place compaction: a chunk is read, then (after the barrier) its survivors are written to
+    // positions below the number of keys read so far
+    for (int base = 0; base < n; base += nt) {
+      int i = base + tid;
+      unsigned long long key = i < n ? buf[i] : kKeySentinel;
+      __syncthreads();
+      bool keep = key != kKeySentinel && (all_valid || key <= tup);
+      unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (mask) {
+        int leader = __ffs(mask) - 1, pos = 0;
+        if (lane == leader) pos = atomicAdd(&s_pos, __popc(mask));
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (keep) buf[pos + __popc(mask & ((1u << lane) - 1u))] = key;
+      }
+    }
+    __syncthreads();
+    const int kept = s_pos;
+    for (int i = kept + tid; i < KP; i += nt) buf[i] = kKeySentinel;
+    if (tid == 0) {
+      *cnt = 0;
+      if (!all_valid) *tau = tup;
+    }
+    __syncthreads();
+    if (final_sort) block_bitonic_sort(buf, KP);
   }
 };
 

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(IVF_NT)
     __syncthreads();  // everyone holds the same c_now before any warp pushes again
     if (t + 1 < ntiles && c_now + g.T > cq.cap()) cq.flush();
   }
-  cq.flush();
+  cq.flush(true);
   for (int i = tid; i < k; i += IVF_NT) out[i] = buf[i];
 }
 
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(IVF_NT)
     }
   }
   __syncthreads();
-  cq.flush();
+  cq.flush(true);
   for (int i = tid; i < k; i += IVF_NT) out[i] = buf[i];
 }
 

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(PQ_NT)
     }
   }
   __syncthreads();
-  cq.flush();
+  cq.flush(true);
   for (int i = tid; i < k; i += PQ_NT) out[i] = buf[i];
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(SEL_NT)
     __syncthreads();  // same snapshot in every thread before any warp pushes again
     if (base + per_round < m && c_now + per_round > cq.cap()) cq.flush();
   }
-  cq.flush();
+  cq.flush(true);
   for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[row * out_stride + i] = buf[i];
 }
 

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(SEG_NT)
     }
   }
   __syncthreads();
-  cq.flush();
+  cq.flush(true);
   for (int i = threadIdx.x; i < k; i += SEG_NT) out_keys[(int64_t)q * k + i] = buf[i];
 }
 
