@@ -511,10 +511,15 @@ def test_request_coalescing_matches_direct_search(ivf_state, ivfflat_index):
 
 
 @pytest.mark.parametrize("metric", [L2, IP])
-def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric):
-    """Many queries per list => the list-major grouped-GEMM scan (kernels_tc.cu) is selected.
+@pytest.mark.parametrize("nlist,k,kernel", [(16, 10, "ivf_listmajor_topk_kernel"),
+                                            (6, 10, "ivf_listmajor_topk_kernel"),  # lists > 2048 rows: row segments
+                                            (16, 64, "ivf_listmajor_topk_kernel"),
+                                            (16, 100, "ivf_listmajor_tc_kernel+seg_select_kernel")])
+def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric, nlist, k, kernel):
+    """Many queries per list => the list-major grouped-GEMM scan (kernels_tc.cu) is selected: fused
+    top-k epilogue for k <= 64, dense score segments + segment select above.
     Integer data: scores bit-equal to the oracle; filters and tombstones honoured."""
-    d, n, nlist, nq, nprobe, k = 64, 30000, 16, 700, 6, 10
+    d, n, nq, nprobe = 64, 30000, 700, 6
     db = synth.sift_like(n, d, seed=95)
     xq = synth.sift_like(nq, d, seed=96)
     cent, _, _ = orc.kmeans(db[:4000], nlist, niter=5)
@@ -533,6 +538,7 @@ def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric):
     ids2 = ids.copy()
     ids2[0] |= orc.DEL_MASK
     dg, ig = idx.search_preassigned(xq, k, keys, cd, del_bitmap=delb)
+    assert idx.last_scan_kernel == kernel
     do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, xq, k, keys, metric, del_bitmap=delb)
     assert_same_results(dg, ig, do, io)
     lo, hi = float(min(do[0, 1], do[0, 6])), float(max(do[0, 1], do[0, 6]))

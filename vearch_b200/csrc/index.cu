@@ -963,13 +963,15 @@ int IVFFlatIndex::coarse_dev(int nq, const float* xq, int nprobe, int metric, in
 // Host side: group the (query, probe) pairs by list (stable counting sort), give every pair a
 // score segment of len(list) floats, cut (list, 128 pairs, 128 rows) tiles; device side: grouped
 // GEMM on tcgen05 + segment select.
-static bool listmajor_enabled() {
+// GB_LISTMAJOR: 0 = off, 1 = on (fused top-k epilogue when k allows), 2 = on, always the dense-score variant
+static int listmajor_mode() {
   static int v = [] {
     const char* e = getenv("GB_LISTMAJOR");
     return e ? atoi(e) : 1;
   }();
-  return v != 0;
+  return v;
 }
+static bool listmajor_enabled() { return listmajor_mode() != 0; }
 
 int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, const float* xq, int k,
                                      const int32_t* probe_ids, int nprobe, unsigned long long* out_keys, Scratch& s) {
@@ -978,6 +980,33 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
   if (npairs < (int64_t)nlist_ * 32 && !getenv("GB_LISTMAJOR_FORCE")) return 1;  // < 32 queries per list on average
   cudaStream_t st = s.stream();
   ListDirectory dir = lists_->directory();
+  if (k <= kLmkMaxK && listmajor_mode() != 2) {
+    // fused top-k epilogue: no score round trip through HBM, no host synchronisation
+    const int nseg = (int)std::min<int64_t>(8, std::max<int64_t>(1, (lists_->max_len() + kLmkSegRows - 1) / kLmkSegRows));
+    const int64_t max_items = (npairs / 128 + nlist_) * nseg;
+    if (max_items > INT32_MAX) return 1;
+    GB_ALLOC(d_cnt, int32_t, nlist_, s);
+    GB_ALLOC(d_start, int32_t, nlist_, s);
+    GB_ALLOC(d_cursor, int32_t, nlist_, s);
+    GB_ALLOC(d_item_start, int32_t, nlist_, s);
+    GB_ALLOC(d_totals, int64_t, 3, s);
+    GB_ALLOC(d_pair_j, int64_t, npairs, s);
+    GB_ALLOC(d_items, LmTile, max_items, s);
+    GB_ALLOC(d_tau, unsigned long long, nq, s);
+    const size_t nout = (size_t)npairs * nseg * k;
+    GB_ALLOC(d_out, unsigned long long, nout, s);
+    GB_CUDA(cudaMemsetAsync(d_tau, 0xFF, sizeof(unsigned long long) * nq, st));
+    GB_CUDA(cudaMemsetAsync(d_out, 0xFF, sizeof(unsigned long long) * nout, st));
+    GB_CUDA(launch_lmk_group(probe_ids, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_totals, d_pair_j,
+                             d_items, st));
+    last_scan_kernel_ = "ivf_listmajor_topk_kernel";
+    scan_timer_begin(st);
+    GB_CUDA(launch_ivf_listmajor_topk(xq, dpad_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe, dir, k, nseg,
+                                      metric, f, d_tau, d_out, st));
+    scan_timer_end(st);
+    GB_CUDA(launch_select_keys(d_out, (int64_t)nprobe * nseg * k, nq, nprobe * nseg * k, k, out_keys, k, st));
+    return 0;
+  }
   GB_ALLOC(d_cnt, int32_t, nlist_, s);
   GB_ALLOC(d_start, int32_t, nlist_, s);
   GB_ALLOC(d_cursor, int32_t, nlist_, s);

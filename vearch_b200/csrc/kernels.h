@@ -69,7 +69,7 @@ int ivfflat_scan_nparts(int nprobe, int max_list_len);
 
 // K3 list-major (tensor cores): (query, probe) pairs grouped by list; tile = 128 pairs x 128 rows.
 struct LmTile {
-  int list, pair0, npairs, row0, nrows;
+  int list, pair0, npairs, row0, nrows, seg;
 };
 // scores[pair_off[j] + r] = score(query pair_q[j], row r of its list)
 cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const LmTile* tiles, int ntiles,
@@ -88,6 +88,21 @@ cudaError_t launch_lm_assign_tiles(const int32_t* probe_ids, int64_t npairs, int
 cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const int32_t* probe_ids, int nq, int nprobe,
                               ListDirectory dir, int k, int metric, FilterArgs f, unsigned long long* out_keys,
                               cudaStream_t st);
+
+// K3 list-major with a fused top-k epilogue (k <= kLmkMaxK): work item = (list, 128 pairs, row segment);
+// the CTA walks the segment's 128-row tiles, every thread keeps the k best keys of its (query, list)
+// pair in shared memory and admits candidates against a per-query bound shared through tau_g.
+// out[(j * nseg_max + seg) * k + i], j = q * nprobe + p; unused slots must be pre-set to the sentinel.
+constexpr int kLmkMaxK = 64;
+constexpr int kLmkSegRows = 2048;
+// grouping: cnt/start/cursor/item_start: [nlist] ints, totals[1] = number of items (device side)
+cudaError_t launch_lmk_group(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int nseg_max, int32_t* cnt,
+                             int32_t* start, int32_t* cursor, int32_t* item_start, int64_t* totals, int64_t* pair_j,
+                             LmTile* items, cudaStream_t st);
+cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const LmTile* items, int max_items,
+                                      const int64_t* totals, const int64_t* pair_j, int nprobe, ListDirectory dir, int k,
+                                      int nseg_max, int metric, FilterArgs f, unsigned long long* tau_g,
+                                      unsigned long long* out, cudaStream_t st);
 
 // ---- K4/K5: IVF-PQ look-up tables + ADC scan --------------------------------------------
 // ip[q][m][c] = <x_q|m, pq_m[c]>   (pq.compute_inner_prod_table)

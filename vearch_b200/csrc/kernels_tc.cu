@@ -76,8 +76,8 @@ struct TcShared {
   float cn[TC_N];
 };
 
-__device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const float* __restrict__ arow,
-                                        const float* __restrict__ brow, int d, uint32_t* tmem_out, float* an) {
+// allocate TMEM (TC_N fp32 columns), initialise the stage barriers; returns the TMEM base address
+__device__ __forceinline__ uint32_t tc_begin(TcShared* sh) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
@@ -92,8 +92,17 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = sh->tmem_base;
+  return sh->tmem_base;
+}
 
+// One tile on an allocated accumulator.  gc = number of K chunks this CTA has pushed through the
+// stage ring so far (barrier phases continue across tiles); returns the updated count.  A caller
+// that runs several tiles must make every thread execute tcgen05.fence::before_thread_sync after
+// its last tcgen05.ld of the previous tile (the first chunk's __syncthreads orders the rest).
+__device__ __forceinline__ uint32_t tc_tile_run(unsigned char* smem, TcShared* sh, uint32_t tmem_d, uint32_t gc0,
+                                                const float* __restrict__ arow, const float* __restrict__ brow, int d,
+                                                float* an) {
+  const int tid = threadIdx.x;
   // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10),
   // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -117,13 +126,14 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
   };
   prefetch(0);
   for (int kc = 0; kc < nk; kc++) {
-    const int s = kc & 1;
+    const uint32_t g = gc0 + (uint32_t)kc;
+    const int s = (int)(g & 1u);
     unsigned char* a_hi = smem + (size_t)s * TC_STAGE_BYTES;
     unsigned char* a_lo = a_hi + TC_TILE_BYTES;
     unsigned char* b_hi = a_hi + 2 * TC_TILE_BYTES;
     unsigned char* b_lo = a_hi + 3 * TC_TILE_BYTES;
-    if (kc >= TC_STAGES) {  // the MMAs of chunk kc-2 must have finished reading this stage
-      mbar_wait(&sh->mma_bar[s], (uint32_t)((kc / TC_STAGES - 1) & 1));
+    if (g >= (uint32_t)TC_STAGES) {  // the MMAs of chunk g-2 must have finished reading this stage
+      mbar_wait(&sh->mma_bar[s], ((g >> 1) - 1u) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 #pragma unroll
@@ -169,11 +179,19 @@ __device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const
     }
   }
   // the last commit covers every MMA of the tile
-  mbar_wait(&sh->mma_bar[(nk - 1) & 1], (uint32_t)(((nk - 1) / TC_STAGES) & 1));
+  const uint32_t gl = gc0 + (uint32_t)nk - 1u;
+  mbar_wait(&sh->mma_bar[gl & 1u], (gl >> 1) & 1u);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   sh->cn[tid] = bn_acc;
   __syncthreads();
   *an = an_acc;
+  return gc0 + (uint32_t)nk;
+}
+
+__device__ __forceinline__ void tc_tile(unsigned char* smem, TcShared* sh, const float* __restrict__ arow,
+                                        const float* __restrict__ brow, int d, uint32_t* tmem_out, float* an) {
+  const uint32_t tmem_d = tc_begin(sh);
+  tc_tile_run(smem, sh, tmem_d, 0u, arow, brow, d, an);
   *tmem_out = tmem_d;
 }
 
@@ -289,6 +307,219 @@ __global__ void __launch_bounds__(TC_NT)
     __syncwarp();
   }
   tc_release(tmem_d);
+}
+
+// ---- K3 list-major, fused top-k epilogue -----------------------------------------------------
+// Thread t of the CTA owns pair t of the item for the whole row segment: accumulator row t, a k-slot
+// key set in shared memory (slot-major, thread-minor: conflict-free) and a register bound tau.  The
+// hot loop is  score -> one float compare against the bound;  everything else (row validity, score
+// window, tombstone, bitmaps, exact 64-bit key compare, set update) sits behind that compare in a
+// non-inlined function, as rare as in the query-major kernels (expected k ln(n/k) hits per query).
+// tau_g[q] carries the best bound any CTA has published for query q: a key is only dropped when it
+// is >= the k-th best of k valid keys of the same query, so the union of the per-pair sets always
+// contains the query's true top-k, whatever the CTA schedule.
+struct LmkCtx {
+  const int64_t* lids;
+  const uint32_t* del_bits;
+  const uint32_t* filter_bits;
+  float min_score, max_score;
+  int row_end, k;
+};
+
+// float image of the bound: a score can only matter if it is on the good side of it.  The two
+// sentinels (no bound yet / thread without a pair) map to +-inf / NaN so the compare does the right thing.
+template <int METRIC>
+__device__ __forceinline__ float lmk_bound(unsigned long long tau) {
+  const uint32_t hi = (uint32_t)(tau >> 32);
+  if (METRIC == kMetricL2) return hi >= 0xFF800000u ? __int_as_float(0x7F800000) : ord2f(hi);
+  const uint32_t x = ~hi;
+  return x <= 0x007FFFFFu ? __int_as_float(0xFF800000) : ord2f(x);
+}
+
+struct LmkState {
+  unsigned long long tau;  // admission bound (exclusive)
+  int n;                   // keys held, <= k
+};
+
+template <int METRIC>
+__device__ __noinline__ LmkState lmk_consider(const LmkCtx* c, unsigned long long* hk, int row, float sc, LmkState st) {
+  if (row >= c->row_end) return st;  // zero-padded rows of a partial tile
+  if (!(sc <= c->max_score && sc >= c->min_score)) return st;
+  const int64_t raw = c->lids[row];
+  if (raw < 0) return st;  // tombstone (gamma_index_ivfflat.h:72)
+  const uint32_t vid = (uint32_t)raw;
+  if (!ctx_is_valid(c->del_bits, c->filter_bits, vid)) return st;
+  const unsigned long long key = make_key(score2ord<METRIC>(sc), vid);
+  if (key >= st.tau) return st;
+  const int k = c->k;
+  if (st.n < k) {
+    hk[st.n * TC_NT] = key;
+    if (++st.n < k) return st;
+    unsigned long long mx = 0;
+    for (int i = 0; i < k; i++) {
+      const unsigned long long v = hk[i * TC_NT];
+      mx = v > mx ? v : mx;
+    }
+    if (mx < st.tau) st.tau = mx;
+    return st;
+  }
+  unsigned long long mx = 0, mx2 = 0;
+  int pos = 0;
+  for (int i = 0; i < k; i++) {
+    const unsigned long long v = hk[i * TC_NT];
+    if (v > mx) {
+      mx2 = mx, mx = v, pos = i;
+    } else if (v > mx2) {
+      mx2 = v;
+    }
+  }
+  unsigned long long nm = mx;
+  if (key < mx) {
+    hk[pos * TC_NT] = key;
+    nm = key > mx2 ? key : mx2;
+  }
+  if (nm < st.tau) st.tau = nm;
+  return st;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(TC_NT)
+    ivf_listmajor_topk_kernel(const float* __restrict__ xq, int64_t ldq, int d, const LmTile* __restrict__ items,
+                              const int64_t* __restrict__ totals, const int64_t* __restrict__ pair_j, int nprobe,
+                              ListDirectory dir, int k, int nseg_max, FilterArgs f, unsigned long long* tau_g,
+                              unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ TcShared sh;
+  __shared__ LmkCtx ctx;
+  if ((int64_t)blockIdx.x >= totals[1]) return;
+  const int tid = threadIdx.x;
+  const LmTile t = items[blockIdx.x];
+  unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem + TC_SMEM) + tid;
+  const bool valid = tid < t.npairs;
+  int64_t j = 0;
+  int q = 0;
+  const float* arow = nullptr;
+  LmkState st{0ull, 0};
+  if (valid) {
+    j = pair_j[t.pair0 + tid];
+    q = (int)(j / nprobe);
+    arow = xq + (int64_t)q * ldq;
+    st.tau = __ldcg(tau_g + q);
+  }
+  if (tid == 0) {
+    ctx.lids = dir.ids[t.list];
+    ctx.del_bits = f.del_bits, ctx.filter_bits = f.filter_bits;
+    ctx.min_score = f.min_score, ctx.max_score = f.max_score;
+    ctx.row_end = t.row0 + t.nrows, ctx.k = k;
+  }
+  const uint32_t tmem_d = tc_begin(&sh);  // __syncthreads inside: ctx visible
+  uint32_t gc = 0;
+  const float* lvecs = dir.vecs[t.list];
+  float bound = lmk_bound<METRIC>(st.tau);
+  for (int r0 = t.row0; r0 < t.row0 + t.nrows; r0 += TC_N) {
+    const float* brow = r0 + tid < t.row0 + t.nrows ? lvecs + (int64_t)(r0 + tid) * d : nullptr;
+    float xn;
+    gc = tc_tile_run(smem, &sh, tmem_d, gc, arow, brow, d, &xn);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_N; c0 += 32) {
+      uint32_t v[32];
+      tc_load32(tmem_d, c0, v);
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        const float s = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[c0 + jj]);
+        if (METRIC == kMetricL2 ? s <= bound : s >= bound) {
+          st = lmk_consider<METRIC>(&ctx, hk, r0 + c0 + jj, s, st);
+          bound = lmk_bound<METRIC>(st.tau);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // next tile's MMAs overwrite the accumulator
+    if (valid) {  // exchange bounds with the other CTAs working on this query
+      const unsigned long long tg = __ldcg(tau_g + q);
+      if (tg < st.tau) {
+        st.tau = tg;
+        bound = lmk_bound<METRIC>(st.tau);
+      } else if (st.tau < tg) {
+        atomicMin(tau_g + q, st.tau);
+      }
+    }
+  }
+  if (valid) {
+    unsigned long long* o = out + ((int64_t)j * nseg_max + t.seg) * k;
+    for (int i = 0; i < k; i++) o[i] = i < st.n ? hk[i * TC_NT] : kKeySentinel;
+  }
+  tc_release(tmem_d);
+}
+
+// ---- grouping for the fused kernel: histogram (lm_count_kernel) -> scan -> slots -> items ----
+__device__ __forceinline__ int lmk_nseg(int len, int nseg_max) {
+  int n = (len + kLmkSegRows - 1) / kLmkSegRows;
+  return n < 1 ? 1 : (n > nseg_max ? nseg_max : n);
+}
+
+__global__ void __launch_bounds__(1024)
+    lmk_scan_kernel(const int32_t* __restrict__ cnt, ListDirectory dir, int nseg_max, int32_t* __restrict__ start,
+                    int32_t* __restrict__ item_start, int64_t* __restrict__ totals) {
+  __shared__ long long s_pairs[1024], s_items[1024];
+  __shared__ long long carry[2];
+  const int tid = threadIdx.x;
+  if (tid == 0) carry[0] = carry[1] = 0;
+  __syncthreads();
+  for (int base = 0; base < dir.nlist; base += 1024) {
+    const int l = base + tid;
+    long long c = 0, it = 0;
+    if (l < dir.nlist) {
+      c = cnt[l];
+      const int len = dir.len[l];
+      if (c > 0 && len > 0) it = ((c + TC_M - 1) / TC_M) * lmk_nseg(len, nseg_max);
+    }
+    s_pairs[tid] = c, s_items[tid] = it;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      long long a = 0, b = 0;
+      if (tid >= off) a = s_pairs[tid - off], b = s_items[tid - off];
+      __syncthreads();
+      s_pairs[tid] += a, s_items[tid] += b;
+      __syncthreads();
+    }
+    if (l < dir.nlist) {
+      start[l] = (int32_t)(carry[0] + s_pairs[tid] - c);
+      item_start[l] = (int32_t)(carry[1] + s_items[tid] - it);
+    }
+    __syncthreads();
+    if (tid == 1023) carry[0] += s_pairs[1023], carry[1] += s_items[1023];
+    __syncthreads();
+  }
+  if (tid == 0) totals[0] = 0, totals[1] = carry[1], totals[2] = carry[0];
+}
+
+__global__ void lmk_assign_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, ListDirectory dir,
+                                  const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                                  int64_t* __restrict__ pair_j) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npairs) return;
+  const int l = probe_ids[j];
+  if (l < 0 || l >= dir.nlist || dir.len[l] <= 0) return;
+  pair_j[start[l] + atomicAdd(cursor + l, 1)] = j;  // slot order inside a list does not affect results
+}
+
+__global__ void lmk_items_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ start,
+                                 const int32_t* __restrict__ item_start, ListDirectory dir, int nseg_max,
+                                 LmTile* __restrict__ items) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= dir.nlist) return;
+  const int c = cnt[l], len = dir.len[l];
+  if (c <= 0 || len <= 0) return;
+  const int nseg = lmk_nseg(len, nseg_max);
+  const int seglen = (((len + nseg - 1) / nseg) + TC_N - 1) / TC_N * TC_N;
+  int it = item_start[l];
+  for (int p0 = 0; p0 < c; p0 += TC_M)
+    for (int sg = 0; sg < nseg; sg++) {
+      LmTile tl;
+      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(TC_M, c - p0);
+      tl.row0 = sg * seglen, tl.nrows = max(0, min(seglen, len - tl.row0)), tl.seg = sg;
+      items[it++] = tl;
+    }
 }
 
 // ---- segment select: per query, stream its P score segments, filter, keep the top-k ---------
@@ -437,7 +668,7 @@ __global__ void lm_tiles_kernel(const int32_t* __restrict__ cnt, const int32_t* 
   for (int p0 = 0; p0 < c; p0 += 128)
     for (int r0 = 0; r0 < len; r0 += 128) {
       LmTile tl;
-      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(128, c - p0), tl.row0 = r0, tl.nrows = min(128, len - r0);
+      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(128, c - p0), tl.row0 = r0, tl.nrows = min(128, len - r0), tl.seg = 0;
       tiles[t++] = tl;
     }
 }
@@ -522,6 +753,49 @@ cudaError_t launch_lm_assign_tiles(const int32_t* probe_ids, int64_t npairs, int
                                                                     pair_q, pair_off, seg_off);
   note_launch();
   lm_tiles_kernel<<<(dir.nlist + 255) / 256, 256, 0, st>>>(cnt, start, tile_start, dir, tiles);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lmk_group(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int nseg_max, int32_t* cnt,
+                             int32_t* start, int32_t* cursor, int32_t* item_start, int64_t* totals, int64_t* pair_j,
+                             LmTile* items, cudaStream_t st) {
+  if (npairs <= 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * dir.nlist, st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(cursor, 0, sizeof(int32_t) * dir.nlist, st);
+  if (e != cudaSuccess) return e;
+  const unsigned nb = (unsigned)((npairs + 255) / 256);
+  lm_count_kernel<<<nb, 256, 0, st>>>(probe_ids, npairs, dir, cnt);
+  note_launch();
+  lmk_scan_kernel<<<1, 1024, 0, st>>>(cnt, dir, nseg_max, start, item_start, totals);
+  note_launch();
+  lmk_assign_kernel<<<nb, 256, 0, st>>>(probe_ids, npairs, dir, start, cursor, pair_j);
+  note_launch();
+  lmk_items_kernel<<<(dir.nlist + 255) / 256, 256, 0, st>>>(cnt, start, item_start, dir, nseg_max, items);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const LmTile* items, int max_items,
+                                      const int64_t* totals, const int64_t* pair_j, int nprobe, ListDirectory dir, int k,
+                                      int nseg_max, int metric, FilterArgs f, unsigned long long* tau_g,
+                                      unsigned long long* out, cudaStream_t st) {
+  if ((d & 3) || (ldq & 3) || k <= 0 || k > kLmkMaxK) return cudaErrorInvalidValue;
+  if (max_items <= 0) return cudaSuccess;
+  const size_t smem = (size_t)TC_SMEM + (size_t)k * TC_NT * 8;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(ivf_listmajor_topk_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_topk_kernel<kMetricL2><<<max_items, TC_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir, k,
+                                                                        nseg_max, f, tau_g, out);
+  } else {
+    e = cudaFuncSetAttribute(ivf_listmajor_topk_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_topk_kernel<kMetricIP><<<max_items, TC_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir, k,
+                                                                        nseg_max, f, tau_g, out);
+  }
   note_launch();
   return cudaGetLastError();
 }
