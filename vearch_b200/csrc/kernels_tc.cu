@@ -113,8 +113,11 @@ __device__ __forceinline__ uint32_t tc_tile_run(unsigned char* smem, TcShared* s
 
   float an_acc = 0.f, bn_acc = 0.f;
   const int nk = (d + TC_BK - 1) / TC_BK;
-  float4 pa[NV], pb[NV];
-  auto prefetch = [&](int kc) {
+  // two register sets: the loads of chunk kc + 2 are issued as soon as chunk kc has been written to
+  // shared memory, so a full chunk period (barrier + MMA issue + the other set's stores) plus the
+  // MMA time covers the L2 latency
+  float4 pa0[NV], pb0[NV], pa1[NV], pb1[NV];
+  auto prefetch = [&](int kc, float4 (&pa)[NV], float4 (&pb)[NV]) {
 #pragma unroll
     for (int kb = 0; kb < NV; kb++) {
       const int gk = kc * TC_BK + kb * 4;
@@ -124,8 +127,7 @@ __device__ __forceinline__ uint32_t tc_tile_run(unsigned char* smem, TcShared* s
       if (brow && gk < d) pb[kb] = __ldg(reinterpret_cast<const float4*>(brow + gk));
     }
   };
-  prefetch(0);
-  for (int kc = 0; kc < nk; kc++) {
+  auto chunk = [&](int kc, float4 (&pa)[NV], float4 (&pb)[NV]) {
     const uint32_t g = gc0 + (uint32_t)kc;
     const int s = (int)(g & 1u);
     unsigned char* a_hi = smem + (size_t)s * TC_STAGE_BYTES;
@@ -156,7 +158,7 @@ __device__ __forceinline__ uint32_t tc_tile_run(unsigned char* smem, TcShared* s
       *reinterpret_cast<float4*>(b_hi + off) = bh;
       *reinterpret_cast<float4*>(b_lo + off) = bl;
     }
-    if (kc + 1 < nk) prefetch(kc + 1);  // global loads for the next chunk fly during this chunk's MMAs
+    if (kc + 2 < nk) prefetch(kc + 2, pa, pb);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async (tensor) proxy
     __syncthreads();
     if (tid == 0) {
@@ -177,6 +179,12 @@ __device__ __forceinline__ uint32_t tc_tile_run(unsigned char* smem, TcShared* s
                        smem_u32(&sh->mma_bar[s]))
                    : "memory");
     }
+  };
+  prefetch(0, pa0, pb0);
+  if (nk > 1) prefetch(1, pa1, pb1);
+  for (int kc = 0; kc < nk; kc += 2) {
+    chunk(kc, pa0, pb0);
+    if (kc + 1 < nk) chunk(kc + 1, pa1, pb1);
   }
   // the last commit covers every MMA of the tile
   const uint32_t gl = gc0 + (uint32_t)nk - 1u;
@@ -318,14 +326,6 @@ __global__ void __launch_bounds__(TC_NT)
 // tau_g[q] carries the best bound any CTA has published for query q: a key is only dropped when it
 // is >= the k-th best of k valid keys of the same query, so the union of the per-pair sets always
 // contains the query's true top-k, whatever the CTA schedule.
-struct LmkCtx {
-  const int64_t* lids;
-  const uint32_t* del_bits;
-  const uint32_t* filter_bits;
-  float min_score, max_score;
-  int row_end, k;
-};
-
 // float image of the bound: a score can only matter if it is on the good side of it.  The two
 // sentinels (no bound yet / thread without a pair) map to +-inf / NaN so the compare does the right thing.
 template <int METRIC>
@@ -340,18 +340,15 @@ struct LmkState {
   unsigned long long tau;  // admission bound (exclusive)
   int n;                   // keys held, <= k
 };
+constexpr uint32_t kLmkNoVid = 0xFFFFFFFFu;
 
 template <int METRIC>
-__device__ __noinline__ LmkState lmk_consider(const LmkCtx* c, unsigned long long* hk, int row, float sc, LmkState st) {
-  if (row >= c->row_end) return st;  // zero-padded rows of a partial tile
-  if (!(sc <= c->max_score && sc >= c->min_score)) return st;
-  const int64_t raw = c->lids[row];
-  if (raw < 0) return st;  // tombstone (gamma_index_ivfflat.h:72)
-  const uint32_t vid = (uint32_t)raw;
-  if (!ctx_is_valid(c->del_bits, c->filter_bits, vid)) return st;
+__device__ __noinline__ LmkState lmk_consider(unsigned long long* hk, int k, uint32_t vid, float sc, float min_score,
+                                              float max_score, LmkState st) {
+  if (vid == kLmkNoVid) return st;  // padding row, tombstone, deleted or filtered out
+  if (!(sc <= max_score && sc >= min_score)) return st;
   const unsigned long long key = make_key(score2ord<METRIC>(sc), vid);
   if (key >= st.tau) return st;
-  const int k = c->k;
   if (st.n < k) {
     hk[st.n * TC_NT] = key;
     if (++st.n < k) return st;
@@ -390,11 +387,13 @@ __global__ void __launch_bounds__(TC_NT)
                               unsigned long long* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ TcShared sh;
-  __shared__ LmkCtx ctx;
   if ((int64_t)blockIdx.x >= totals[1]) return;
   const int tid = threadIdx.x;
   const LmTile t = items[blockIdx.x];
   unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem + TC_SMEM) + tid;
+  // the operand stages are idle between a tile's last MMA and the next tile's first store: the
+  // epilogue keeps the tile's row ids there (vid, or kLmkNoVid for rows that can never be returned)
+  uint32_t* s_vid = reinterpret_cast<uint32_t*>(smem);
   const bool valid = tid < t.npairs;
   int64_t j = 0;
   int q = 0;
@@ -406,20 +405,24 @@ __global__ void __launch_bounds__(TC_NT)
     arow = xq + (int64_t)q * ldq;
     st.tau = __ldcg(tau_g + q);
   }
-  if (tid == 0) {
-    ctx.lids = dir.ids[t.list];
-    ctx.del_bits = f.del_bits, ctx.filter_bits = f.filter_bits;
-    ctx.min_score = f.min_score, ctx.max_score = f.max_score;
-    ctx.row_end = t.row0 + t.nrows, ctx.k = k;
-  }
-  const uint32_t tmem_d = tc_begin(&sh);  // __syncthreads inside: ctx visible
+  const uint32_t tmem_d = tc_begin(&sh);
   uint32_t gc = 0;
   const float* lvecs = dir.vecs[t.list];
+  const int64_t* __restrict__ lids = dir.ids[t.list];
+  const int row_end = t.row0 + t.nrows;
   float bound = lmk_bound<METRIC>(st.tau);
-  for (int r0 = t.row0; r0 < t.row0 + t.nrows; r0 += TC_N) {
-    const float* brow = r0 + tid < t.row0 + t.nrows ? lvecs + (int64_t)(r0 + tid) * d : nullptr;
+  for (int r0 = t.row0; r0 < row_end; r0 += TC_N) {
+    const float* brow = nullptr;
+    uint32_t myvid = kLmkNoVid;  // validity of row r0 + tid, resolved while the tile is being multiplied
+    if (r0 + tid < row_end) {
+      brow = lvecs + (int64_t)(r0 + tid) * d;
+      const int64_t raw = lids[r0 + tid];
+      if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw)) myvid = (uint32_t)raw;  // tombstone: ivfflat.h:72
+    }
     float xn;
     gc = tc_tile_run(smem, &sh, tmem_d, gc, arow, brow, d, &xn);
+    s_vid[tid] = myvid;
+    __syncthreads();
 #pragma unroll 1
     for (int c0 = 0; c0 < TC_N; c0 += 32) {
       uint32_t v[32];
@@ -428,7 +431,7 @@ __global__ void __launch_bounds__(TC_NT)
       for (int jj = 0; jj < 32; jj++) {
         const float s = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[c0 + jj]);
         if (METRIC == kMetricL2 ? s <= bound : s >= bound) {
-          st = lmk_consider<METRIC>(&ctx, hk, r0 + c0 + jj, s, st);
+          st = lmk_consider<METRIC>(hk, k, s_vid[c0 + jj], s, f.min_score, f.max_score, st);
           bound = lmk_bound<METRIC>(st.tau);
         }
       }
@@ -443,6 +446,7 @@ __global__ void __launch_bounds__(TC_NT)
         atomicMin(tau_g + q, st.tau);
       }
     }
+    __syncthreads();  // s_vid is overwritten by the next tile's operand stores
   }
   if (valid) {
     unsigned long long* o = out + ((int64_t)j * nseg_max + t.seg) * k;
