@@ -93,6 +93,14 @@ int gb_index_code_size(gb_index *index);
 /* copy one inverted list to the host: codes = len x code_size bytes, ids = len int64 */
 int gb_index_get_list(gb_index *index, int list, uint8_t *codes, int64_t *ids);
 int gb_index_tombstone(gb_index *index, int list, int pos);
+/* IndexModel::Dump / Load (index/index_model.h) in gamma's own file formats -- "IvFl" / "IwPQ" header,
+ * IndexFlat quantizer, "ilar" inverted lists (index/impl/gamma_index_ivfflat.cc:807-892,
+ * gamma_index_ivfpq.cc:1019-1116, index/index_io.cc:108-194): <dir>/<abs_name>/{ivfflat,ivfpq}.index.
+ * dump: 0 on success (also when untrained: nothing written, like the reference).  load: the vectors
+ * the file indexes must already be in the store (gb_index_add); *load_num = vectors covered, 0 if
+ * there is no file.  FLAT indexes: both are no-ops. */
+int gb_index_dump(gb_index *index, const char *dir, const char *abs_name);
+int gb_index_load(gb_index *index, const char *dir, const char *abs_name, int64_t *load_num);
 /* quantizer->search (gamma_index_ivfflat.cc:568) */
 int gb_index_coarse_search(gb_index *index, int nq, const float *x, int nprobe, float *out_dis, int64_t *out_ids);
 /* search_preassigned (gamma_index_ivfflat.cc:579, gamma_index_ivfpq.cc:730) with caller-given

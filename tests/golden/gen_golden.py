@@ -155,3 +155,20 @@ def gen_flat_golden():
 
 if __name__ == "__main__":
     gen_flat_golden()
+
+
+def gen_index_file_golden():
+    """ivfflat_tiny.index: gamma's IVF-Flat dump format (index/index_io.cc, gamma_index_ivfflat.cc:807-839)
+    written by the independent struct.pack restatement in tests/gamma_index_file.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import gamma_index_file as gif
+    import test_index_file as tif
+    d, nlist, cent, off, vecs, ids = tif.tiny_state()
+    with open(os.path.join(HERE, "ivfflat_tiny.index"), "wb") as f:
+        f.write(gif.write_ivfflat(d, gif.METRIC_L2, 2, cent, off, vecs, ids, 5))
+
+
+if __name__ == "__main__":
+    gen_index_file_golden()

@@ -5,6 +5,7 @@
 // vector/vector_manager.cc.  No CPU compute path exists here: every Search/Train/Add call runs
 // CUDA kernels and fails if the device is unavailable.
 #pragma once
+#include <stdio.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -105,6 +106,9 @@ class IvfLists {
   int tombstone(int list, int pos, cudaStream_t st);
   // host copies for dump / parity tests
   int download_list(int l, std::vector<uint8_t>* codes, std::vector<int64_t>* ids) const;
+  // append position of list l (valid after reserve): where the next entry's code / id goes
+  void* list_data(int l) const { return static_cast<char*>(h_data_[l]) + (size_t)h_len_[l] * code_bytes_; }
+  int64_t* list_ids(int l) const { return h_ids_[l] + h_len_[l]; }
   int64_t mem_bytes() const { return bytes_; }
 
  private:
@@ -288,8 +292,15 @@ class IVFFlatIndex : public Index {
   // search_preassigned with caller-provided (keys, coarse_dis): host in/out
   virtual int search_preassigned_host(const SearchContext& ctx, int nq, const float* x, int k, const int64_t* keys,
                                       const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids);
+  // gamma's own index files (index_io.cu): <dir>/<abs_name>/{ivfflat,ivfpq}.index.  load: the vector
+  // store must already hold the vectors the file indexes; *load_num = IndexModel::Load's load_num
+  int dump_gamma(const std::string& dir, const std::string& abs_name);
+  int load_gamma(const std::string& dir, const std::string& abs_name, int64_t* load_num);
 
  protected:
+  virtual const char* gamma_file_name() const;
+  virtual int dump_gamma_extra(FILE* f) { (void)f; return 0; }
+  virtual int load_gamma_extra(FILE* f) { (void)f; return 0; }
   int search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
                       unsigned long long* out_keys, Scratch& s) override;
   int coarse_dev(int nq, const float* xq, int nprobe, int metric, int32_t* probe_ids, float* coarse_dis, Scratch& s);
@@ -335,6 +346,9 @@ class IVFPQIndex : public IVFFlatIndex {
                const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
                Scratch& s) override;
   int code_bytes() const override { return M_; }
+  const char* gamma_file_name() const override;
+  int dump_gamma_extra(FILE* f) override;
+  int load_gamma_extra(FILE* f) override;
   int append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
                    const int32_t* d_assign, Scratch& s) override;
   int train_extra(const float* xtrain, int64_t n, Scratch& s) override;

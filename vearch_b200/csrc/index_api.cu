@@ -282,6 +282,19 @@ int gb_index_get_precomputed_table(gb_index* index, float* table) {
   PQ_OR_FAIL(pq, index);
   return pq->get_precomputed_table(table);
 }
+int gb_index_dump(gb_index* index, const char* dir, const char* abs_name) {
+  IDX_OR_FAIL(index);
+  if (!dir || !abs_name) return -1;
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index->impl);
+  return ivf ? ivf->dump_gamma(dir, abs_name) : 0;
+}
+int gb_index_load(gb_index* index, const char* dir, const char* abs_name, int64_t* load_num) {
+  IDX_OR_FAIL(index);
+  if (!dir || !abs_name || !load_num) return -1;
+  *load_num = 0;
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index->impl);
+  return ivf ? ivf->load_gamma(dir, abs_name, load_num) : 0;
+}
 int gb_index_list_len(gb_index* index, int list) {
   IVF_OR_FAIL(ivf, index);
   if (!ivf->lists() || list < 0 || list >= ivf->nlist()) return 0;

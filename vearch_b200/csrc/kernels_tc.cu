@@ -25,6 +25,7 @@
 // commits to an mbarrier.  Thread t stages row t of both operands, so it also owns |x_t|^2 and
 // |y_t|^2.  One 128 x 128 output tile per CTA.
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -455,6 +456,239 @@ __global__ void __launch_bounds__(TC_NT)
   tc_release(tmem_d);
 }
 
+// ---- K3 list-major, warp-specialised pipeline -------------------------------------------------
+// Same work item and the same results as ivf_listmajor_topk_kernel, but the three stages of a tile run
+// concurrently in dedicated warps, synchronised by mbarriers only:
+//   warps 4-7  producers: thread p stages row p of the query group and of the list tile, one K = 16
+//              chunk at a time, into a ring of LW_STAGES operand stages (hi/lo TF32 split, canonical
+//              K-major layout), two chunks of global loads in flight per thread;
+//   warp  8    one lane issues the tcgen05 MMAs of a chunk as soon as its stage is full; tcgen05.commit
+//              frees the stage, and after a tile's last chunk hands the accumulator to the epilogue;
+//   warps 0-3  epilogue: tcgen05.ld the 128 x 128 accumulator of tile i (TMEM buffer i & 1) and run
+//              the bound test / key-set update while the MMAs of tile i + 1 fill the other buffer.
+constexpr int LW_STAGES = 3;
+constexpr int LW_NT = 288;
+constexpr int LW_RING = LW_STAGES * TC_STAGE_BYTES;
+
+struct LwShared {
+  uint64_t full[LW_STAGES], empty[LW_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+  float cn[2][TC_N];      // |y|^2 of the tile's rows
+  uint32_t vid[2][TC_N];  // ids of the tile's rows, kLmkNoVid = can never be returned
+  float xn[TC_M];         // |x|^2 of the group's queries
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(LW_NT, 2)
+    ivf_listmajor_pipe_kernel(const float* __restrict__ xq, int64_t ldq, int d, const LmTile* __restrict__ items,
+                              const int64_t* __restrict__ totals, const int64_t* __restrict__ pair_j, int nprobe,
+                              ListDirectory dir, int k, int nseg_max, FilterArgs f, unsigned long long* tau_g,
+                              unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ LwShared sh;
+  if ((int64_t)blockIdx.x >= totals[1]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const LmTile t = items[blockIdx.x];
+  const int row_end = t.row0 + t.nrows;
+  const int ntiles = (t.nrows + TC_N - 1) / TC_N;
+  const int nk = (d + TC_BK - 1) / TC_BK;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                 "n"(2 * TC_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < LW_STAGES; s++) {
+      mbar_init(&sh.full[s], TC_M);  // every producer thread arrives
+      mbar_init(&sh.empty[s], 1);    // tcgen05.commit
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&sh.acc_full[b], 1);      // tcgen05.commit
+      mbar_init(&sh.acc_empty[b], TC_M);  // every epilogue thread arrives
+    }
+    mbar_fence_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = sh.tmem_base;
+  const uint32_t LBO = TC_M * 16, SBO = 128;
+
+  if (warp < 4) {
+    // ======================= epilogue =======================
+    unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem + LW_RING) + tid;
+    const bool valid = tid < t.npairs;
+    int64_t j = 0;
+    int q = 0;
+    LmkState st{0ull, 0};
+    if (valid) {
+      j = pair_j[t.pair0 + tid];
+      q = (int)(j / nprobe);
+      st.tau = __ldcg(tau_g + q);
+    }
+    float bound = lmk_bound<METRIC>(st.tau);
+    float xn = 0.f;
+    for (int i = 0; i < ntiles; i++) {
+      const int b = i & 1;
+      mbar_wait(&sh.acc_full[b], (uint32_t)((i >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (i == 0) xn = sh.xn[tid];
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_N; c0 += 32) {
+        uint32_t v[32];
+        tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; jj++) {
+          const float sc = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[b][c0 + jj]);
+          if (METRIC == kMetricL2 ? sc <= bound : sc >= bound) {
+            st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], sc, f.min_score, f.max_score, st);
+            bound = lmk_bound<METRIC>(st.tau);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&sh.acc_empty[b]);  // accumulator b, cn[b], vid[b] may be overwritten
+      if (valid) {                    // exchange bounds with the other CTAs working on this query
+        const unsigned long long tg = __ldcg(tau_g + q);
+        if (tg < st.tau) {
+          st.tau = tg;
+          bound = lmk_bound<METRIC>(st.tau);
+        } else if (st.tau < tg) {
+          atomicMin(tau_g + q, st.tau);
+        }
+      }
+    }
+    if (valid) {
+      unsigned long long* o = out + ((int64_t)j * nseg_max + t.seg) * k;
+      for (int i = 0; i < k; i++) o[i] = i < st.n ? hk[i * TC_NT] : kKeySentinel;
+    }
+  } else if (warp < 8) {
+    // ======================= producers =======================
+    const int p = tid - TC_M;
+    const float* arow = nullptr;
+    if (p < t.npairs) arow = xq + (pair_j[t.pair0 + p] / nprobe) * ldq;
+    const float* lvecs = dir.vecs[t.list];
+    const int64_t* __restrict__ lids = dir.ids[t.list];
+    const uint32_t row_off = (uint32_t)(p >> 3) * SBO + (uint32_t)(p & 7) * 16;
+    constexpr int NV = TC_BK / 4;
+    const int T = ntiles * nk;
+    float an_acc = 0.f, bn_acc = 0.f;
+    uint32_t myvid = kLmkNoVid;
+    float4 pa0[NV], pb0[NV], pa1[NV], pb1[NV];
+    auto prefetch = [&](int n, float4 (&pa)[NV], float4 (&pb)[NV]) {
+      const int i = n / nk, kc = n - i * nk;
+      const int row = t.row0 + i * TC_N + p;
+      const float* brow = row < row_end ? lvecs + (int64_t)row * d : nullptr;
+#pragma unroll
+      for (int kb = 0; kb < NV; kb++) {
+        const int gk = kc * TC_BK + kb * 4;
+        pa[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[kb] = pa[kb];
+        if (arow && gk < d) pa[kb] = __ldg(reinterpret_cast<const float4*>(arow + gk));
+        if (brow && gk < d) pb[kb] = __ldg(reinterpret_cast<const float4*>(brow + gk));
+      }
+    };
+    auto chunk = [&](int n, float4 (&pa)[NV], float4 (&pb)[NV]) {
+      const int i = n / nk, kc = n - i * nk;
+      const int s = n % LW_STAGES;
+      if (kc == 0) {  // new tile: row validity is resolved while the tile's chunks stream through
+        bn_acc = 0.f;
+        myvid = kLmkNoVid;
+        const int row = t.row0 + i * TC_N + p;
+        if (row < row_end) {
+          const int64_t raw = lids[row];  // tombstone: gamma_index_ivfflat.h:72
+          if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw)) myvid = (uint32_t)raw;
+        }
+      }
+      mbar_wait(&sh.empty[s], (uint32_t)(((n / LW_STAGES) & 1) ^ 1));
+      unsigned char* a_hi = smem + (size_t)s * TC_STAGE_BYTES;
+      unsigned char* a_lo = a_hi + TC_TILE_BYTES;
+      unsigned char* b_hi = a_hi + 2 * TC_TILE_BYTES;
+      unsigned char* b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+      for (int kb = 0; kb < NV; kb++) {
+        const uint32_t off = (uint32_t)kb * LBO + row_off;
+        const float4 va = pa[kb], vb = pb[kb];
+        an_acc = fmaf(va.x, va.x, an_acc), an_acc = fmaf(va.y, va.y, an_acc);
+        an_acc = fmaf(va.z, va.z, an_acc), an_acc = fmaf(va.w, va.w, an_acc);
+        bn_acc = fmaf(vb.x, vb.x, bn_acc), bn_acc = fmaf(vb.y, vb.y, bn_acc);
+        bn_acc = fmaf(vb.z, vb.z, bn_acc), bn_acc = fmaf(vb.w, vb.w, bn_acc);
+        auto split = [](float v, float& hi, float& lo) {
+          hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+          lo = v - hi;
+        };
+        float4 ah, al, bh, bl;
+        split(va.x, ah.x, al.x), split(va.y, ah.y, al.y), split(va.z, ah.z, al.z), split(va.w, ah.w, al.w);
+        split(vb.x, bh.x, bl.x), split(vb.y, bh.y, bl.y), split(vb.z, bh.z, bl.z), split(vb.w, bh.w, bl.w);
+        *reinterpret_cast<float4*>(a_hi + off) = ah;
+        *reinterpret_cast<float4*>(a_lo + off) = al;
+        *reinterpret_cast<float4*>(b_hi + off) = bh;
+        *reinterpret_cast<float4*>(b_lo + off) = bl;
+      }
+      if (n + 2 < T) prefetch(n + 2, pa, pb);
+      if (kc == nk - 1) {  // tile complete: publish its per-row scalars for the epilogue
+        const int b = i & 1;
+        mbar_wait(&sh.acc_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));  // epilogue of tile i-2 is done with them
+        sh.cn[b][p] = bn_acc;
+        sh.vid[b][p] = myvid;
+        if (i == 0) sh.xn[p] = an_acc;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core proxy
+      mbar_arrive(&sh.full[s]);
+    };
+    if (T > 0) prefetch(0, pa0, pb0);
+    if (T > 1) prefetch(1, pa1, pb1);
+    for (int n = 0; n < T; n += 2) {
+      chunk(n, pa0, pb0);
+      if (n + 1 < T) chunk(n + 1, pa1, pb1);
+    }
+  } else if (lane == 0) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    for (int i = 0; i < ntiles; i++) {
+      const int b = i & 1;
+      mbar_wait(&sh.acc_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_d + (uint32_t)(b * TC_N);
+      for (int kc = 0; kc < nk; kc++) {
+        const int n = i * nk + kc;
+        const int s = n % LW_STAGES;
+        mbar_wait(&sh.full[s], (uint32_t)((n / LW_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+        const uint32_t a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ks++) {
+          const uint32_t koff = (uint32_t)ks * 2 * LBO;
+          const uint64_t dah = make_smem_desc(a_hi + koff, LBO, SBO), dal = make_smem_desc(a_lo + koff, LBO, SBO);
+          const uint64_t dbh = make_smem_desc(b_hi + koff, LBO, SBO), dbl = make_smem_desc(b_lo + koff, LBO, SBO);
+          tc_mma_tf32(acc, dah, dbh, idesc, (kc | ks) != 0);
+          tc_mma_tf32(acc, dah, dbl, idesc, 1);
+          tc_mma_tf32(acc, dal, dbh, idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&sh.empty[s]))
+                     : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&sh.acc_full[b]))
+                   : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * TC_N) : "memory");
+  }
+}
+
 // ---- grouping for the fused kernel: histogram (lm_count_kernel) -> scan -> slots -> items ----
 __device__ __forceinline__ int lmk_nseg(int len, int nseg_max) {
   int n = (len + kLmkSegRows - 1) / kLmkSegRows;
@@ -787,6 +1021,27 @@ cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const
                                       unsigned long long* out, cudaStream_t st) {
   if ((d & 3) || (ldq & 3) || k <= 0 || k > kLmkMaxK) return cudaErrorInvalidValue;
   if (max_items <= 0) return cudaSuccess;
+  static const int pipe = [] {
+    const char* e = getenv("GB_LM_PIPE");
+    return e ? atoi(e) : 1;
+  }();
+  if (pipe && d > TC_BK) {  // the ring's phase arithmetic assumes >= 2 chunks per tile
+    const size_t smem = (size_t)LW_RING + (size_t)k * TC_NT * 8;
+    cudaError_t e;
+    if (metric == kMetricL2) {
+      e = cudaFuncSetAttribute(ivf_listmajor_pipe_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      ivf_listmajor_pipe_kernel<kMetricL2><<<max_items, LW_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir,
+                                                                          k, nseg_max, f, tau_g, out);
+    } else {
+      e = cudaFuncSetAttribute(ivf_listmajor_pipe_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      ivf_listmajor_pipe_kernel<kMetricIP><<<max_items, LW_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir,
+                                                                          k, nseg_max, f, tau_g, out);
+    }
+    note_launch();
+    return cudaGetLastError();
+  }
   const size_t smem = (size_t)TC_SMEM + (size_t)k * TC_NT * 8;
   cudaError_t e;
   if (metric == kMetricL2) {

@@ -232,6 +232,16 @@ class GammaIndex:
                 ids[off[l]:off[l + 1]] = i
         return off, codes, ids
 
+    def dump(self, directory, abs_name):
+        """IndexModel::Dump in gamma's own format: <directory>/<abs_name>/{ivfflat,ivfpq}.index."""
+        _check(_lib.lib().gb_index_dump(self._h, str(directory).encode(), abs_name.encode()), "dump")
+
+    def load(self, directory, abs_name):
+        """IndexModel::Load; returns load_num (0: no file).  The vectors must already be in the store."""
+        n = np.zeros(1, np.int64)
+        _check(_lib.lib().gb_index_load(self._h, str(directory).encode(), abs_name.encode(), _ptr(n)), "load")
+        return int(n[0])
+
     def tombstone(self, l, pos):
         _check(_lib.lib().gb_index_tombstone(self._h, l, pos), "tombstone")
 
