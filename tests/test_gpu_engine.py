@@ -206,8 +206,17 @@ def test_dump_load_roundtrip(tmp_path, data):
     before = e.search(xq, 10, index_params={"nprobe": 4})
     assert e.dump() == 0
     e.close()
+    # the index travels in gamma's own file format (gamma_index_ivfflat.cc:807-839), readable by the
+    # independent restatement of that format
+    import gamma_index_file as gif
+    with open(tmp_path / "retrieval_model_index" / "emb.000" / "ivfflat.index", "rb") as fh:
+        dumped = gif.read_index_file(fh.read())
+    assert dumped["kind"] == "IvFl" and dumped["nlist"] == 16 and dumped["indexed_count"] == 2000
+    assert len(dumped["ids"]) == 2000 and sorted(dumped["ids"].tolist()) == list(range(2000))
     e2 = make_engine(tmp_path, "IVFFLAT", params)  # gammacb.New: CreateTable then Load (gamma.go:104-130)
     assert e2.load() == 0
+    st = e2.status()  # lists came from the file: indexed before the indexing thread has done anything
+    assert st["min_indexed_num"] == 2000 and st["index_status"] == 2
     e2.wait_indexed(2000)
     assert e2.status()["doc_num"] == 1999
     after = e2.search(xq, 10, index_params={"nprobe": 4})

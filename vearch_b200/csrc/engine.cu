@@ -646,6 +646,9 @@ int Engine::Dump() {
     }
   }
   f.close();
+  // the index itself in gamma's own format (IndexModel::Dump via VectorManager::Dump,
+  // vector_manager.cc:1155-1170): <dir>/<vector name>.000/{ivfflat,ivfpq}.index
+  if (trained && ivf && ivf->dump_gamma(dir, vec_name_ + ".000")) return -1;
   std::ofstream done(dir + "/dump.done");
   done << "ok";
   return f.fail() ? -1 : 0;
@@ -704,8 +707,14 @@ int Engine::Load() {
       if (pq->set_pq_centroids(p.data())) return -1;
     }
   }
+  if (trained && ivf) {
+    // IndexModel::Load: take the inverted lists from the index file when it matches this table; a
+    // missing or refused file only means the indexing thread re-adds the vectors itself
+    int64_t load_num = 0;
+    if (ivf->load_gamma(dir, vec_name_ + ".000", &load_num) == 0 && load_num > 0) index_status_.store(2);
+  }
   lk.unlock();
-  if (trained) BuildIndex();  // train() is a no-op on a trained index; the loop re-adds the vectors
+  if (trained) BuildIndex();  // train() is a no-op on a trained index; the loop adds what the file did not cover
   return 0;
 }
 

@@ -207,6 +207,7 @@ int IVFFlatIndex::load_gamma(const std::string& dir, const std::string& abs_name
   std::vector<uint8_t> codes, padded;
   std::vector<int64_t> ids;
   int64_t live = 0, max_vid = -1;
+  std::vector<uint64_t> v2p;  // vid_bucket_no_pos_, installed only if the whole file loads
   const size_t my_cb = (size_t)code_bytes();
   for (int l = 0; l < nlist_; l++) {
     const size_t len = sizes[l];
@@ -228,15 +229,10 @@ int IVFFlatIndex::load_gamma(const std::string& dir, const std::string& abs_name
       if (id < 0) continue;             // deleted_nums_[bno]++ (index_io.cc:178-181)
       live++;
       max_vid = std::max(max_vid, id);
-      if ((size_t)id >= vid2pos_.size()) vid2pos_.resize(std::max<size_t>((size_t)id + 1, vid2pos_.size() * 2), ~(uint64_t)0);
-      vid2pos_[id] = (uint64_t)l << 32 | (uint64_t)pos;  // vid_bucket_no_pos_
+      if ((size_t)id >= v2p.size()) v2p.resize(std::max<size_t>((size_t)id + 1, v2p.size() * 2), ~(uint64_t)0);
+      v2p[id] = (uint64_t)l << 32 | (uint64_t)pos;
     }
   }
-  {
-    std::unique_lock<std::shared_mutex> lk(mu_);
-    if (lists_->commit(add, st)) return -1;
-  }
-  GB_CUDA(cudaStreamSynchronize(st));
   int64_t indexed = live;  // IwPQ: ReadInvertedLists' running count (total - tombstones)
   if (!is_pq) {
     int32_t cnt = 0;
@@ -246,6 +242,12 @@ int IVFFlatIndex::load_gamma(const std::string& dir, const std::string& abs_name
   if (indexed > store_->size() || max_vid >= store_->size())
     return fail("index file covers " + std::to_string(std::max(indexed, max_vid + 1)) + " vectors, the vector store holds " +
                 std::to_string(store_->size()));
+  {  // publish: nothing above this point changed what a search can see
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    if (lists_->commit(add, st)) return -1;
+  }
+  GB_CUDA(cudaStreamSynchronize(st));
+  vid2pos_.swap(v2p);
   indexed_count_ = indexed;
   *load_num = indexed;
   return 0;
