@@ -41,7 +41,8 @@ void gb_index_destroy(gb_index *index);
 /* VectorManager::AddToStore (vector_manager.cc:455): append n raw vectors (n x d fp32). */
 int gb_index_add_vectors(gb_index *index, int64_t n, const float *x);
 int gb_index_add_vectors_device(gb_index *index, int64_t n, const float *x_dev, int64_t ld);
-/* RawVector update in place (engine.cc:736 Update path) */
+/* Engine::Update (search/engine.cc:774-850): RawVector update in place + IndexModel::Update (old list
+ * entry tombstoned, vector re-appended to its new list; realtime_mem_data.cc:298-320) */
 int gb_index_update_vector(gb_index *index, int64_t vid, const float *x);
 int gb_index_get_vector(gb_index *index, int64_t vid, float *out);
 int gb_index_get_vectors(gb_index *index, int64_t start, int64_t n, float *out); /* n x d */

@@ -174,7 +174,7 @@ int gb_index_add_vectors_device(gb_index* index, int64_t n, const float* x_dev, 
 int gb_index_update_vector(gb_index* index, int64_t vid, const float* x) {
   IDX_OR_FAIL(index);
   cudaSetDevice(index->impl->device());
-  return index->impl->store().update_host(vid, x, nullptr);
+  return index->impl->update_vector(vid, x);  // RawVector update + IndexModel::Update
 }
 int gb_index_get_vector(gb_index* index, int64_t vid, float* out) {
   IDX_OR_FAIL(index);

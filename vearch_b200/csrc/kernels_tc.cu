@@ -471,11 +471,11 @@ constexpr int LW_NT = 288;
 constexpr int LW_RING = LW_STAGES * TC_STAGE_BYTES;
 
 struct LwShared {
+  alignas(16) float cn[2][TC_N];  // |y|^2 of the tile's rows (read as float4)
+  uint32_t vid[2][TC_N];          // ids of the tile's rows, kLmkNoVid = can never be returned
+  float xn[TC_M];                 // |x|^2 of the group's queries
   uint64_t full[LW_STAGES], empty[LW_STAGES], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
-  float cn[2][TC_N];      // |y|^2 of the tile's rows
-  uint32_t vid[2][TC_N];  // ids of the tile's rows, kLmkNoVid = can never be returned
-  float xn[TC_M];         // |x|^2 of the group's queries
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -543,13 +543,27 @@ __global__ void __launch_bounds__(LW_NT, 2)
       for (int c0 = 0; c0 < TC_N; c0 += 32) {
         uint32_t v[32];
         tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
+        // branch-free pass over the 32 columns: scores in place, one bit per column that beats the
+        // bound this block started with (the rare path re-checks against the live bound)
+        uint32_t hit = 0;
 #pragma unroll
-        for (int jj = 0; jj < 32; jj++) {
-          const float sc = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[b][c0 + jj]);
-          if (METRIC == kMetricL2 ? sc <= bound : sc >= bound) {
-            st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], sc, f.min_score, f.max_score, st);
-            bound = lmk_bound<METRIC>(st.tau);
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(&sh.cn[b][c0 + j4]);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const float sc = tc_score<METRIC>(__uint_as_float(v[j4 + u]), xn, cc[u]);
+            v[j4 + u] = __float_as_uint(sc);
+            hit |= (METRIC == kMetricL2 ? sc <= bound : sc >= bound) ? (1u << (j4 + u)) : 0u;
           }
+        }
+        if (hit) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj++) {
+            if (hit & (1u << jj))
+              st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
+          }
+          bound = lmk_bound<METRIC>(st.tau);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -631,7 +645,6 @@ __global__ void __launch_bounds__(LW_NT, 2)
         *reinterpret_cast<float4*>(b_hi + off) = bh;
         *reinterpret_cast<float4*>(b_lo + off) = bl;
       }
-      if (n + 2 < T) prefetch(n + 2, pa, pb);
       if (kc == nk - 1) {  // tile complete: publish its per-row scalars for the epilogue
         const int b = i & 1;
         mbar_wait(&sh.acc_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));  // epilogue of tile i-2 is done with them
@@ -641,6 +654,8 @@ __global__ void __launch_bounds__(LW_NT, 2)
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core proxy
       mbar_arrive(&sh.full[s]);
+      // after the arrive: a release-arrive waits for the thread's outstanding loads
+      if (n + 2 < T) prefetch(n + 2, pa, pb);
     };
     if (T > 0) prefetch(0, pa0, pb0);
     if (T > 1) prefetch(1, pa1, pb1);
