@@ -546,3 +546,27 @@ def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric, nlist, k, ker
     do, io = orc.ivfflat_search_preassigned(off, vecs, ids2, xq, k, keys, metric, min_score=lo, max_score=hi)
     assert_same_results(dg, ig, do, io)
     idx.close()
+
+
+@pytest.mark.parametrize("metric", [L2, IP])
+@pytest.mark.parametrize("d", [96, 200])
+def test_ivfflat_listmajor_float_data_within_tolerance(metric, d):
+    """General fp32 data (unit-norm embeddings, every mantissa bit in use): the error-compensated
+    3xTF32 contraction must stay within 1e-5 relative of the fp32 oracle -- a tensor-core path that
+    dropped or mis-rounded the low 13 mantissa bits would be off by ~5e-4."""
+    n, nlist, nq, nprobe, k = 20000, 8, 600, 4, 10
+    db = synth.embed_like(n, d, seed=97, n_clusters=32)
+    xq = synth.embed_like(nq, d, seed=98, n_clusters=32)
+    cent, _, _ = orc.kmeans(db[:3000], nlist, niter=5)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": nprobe, "metric_type": mt(metric)})
+    idx.set_centroids(cent)
+    idx.add_vectors(db)
+    idx.add_pending()
+    off, codes, ids = idx.export_lists()
+    vecs = codes.view(np.float32).reshape(len(ids), -1)[:, :d]
+    cd, keys = orc.coarse_search(cent, xq, nprobe, metric)
+    dg, ig = idx.search_preassigned(xq, k, keys, cd)
+    assert idx.last_scan_kernel == "ivf_listmajor_topk_kernel"
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids, xq, k, keys, metric)
+    assert_same_results(dg, ig, do, io, bit_exact=False, rtol=1e-5)
+    idx.close()
