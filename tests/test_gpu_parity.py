@@ -552,8 +552,10 @@ def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric, nlist, k, ker
 @pytest.mark.parametrize("d", [96, 200])
 def test_ivfflat_listmajor_float_data_within_tolerance(metric, d):
     """General fp32 data (unit-norm embeddings, every mantissa bit in use): the error-compensated
-    3xTF32 contraction must stay within 1e-5 relative of the fp32 oracle -- a tensor-core path that
-    dropped or mis-rounded the low 13 mantissa bits would be off by ~5e-4."""
+    3xTF32 contraction must stay within 1e-5 relative of the fp32 oracle on inner products -- a
+    tensor-core path that dropped or mis-rounded the low 13 mantissa bits would be off by ~5e-4.
+    L2 goes through |x|^2 + |y|^2 - 2 x.y (as faiss's own blocked path does), so near neighbours of
+    unit vectors lose digits to cancellation: the north-star tolerance 1e-4 applies there."""
     n, nlist, nq, nprobe, k = 20000, 8, 600, 4, 10
     db = synth.embed_like(n, d, seed=97, n_clusters=32)
     xq = synth.embed_like(nq, d, seed=98, n_clusters=32)
@@ -568,5 +570,5 @@ def test_ivfflat_listmajor_float_data_within_tolerance(metric, d):
     dg, ig = idx.search_preassigned(xq, k, keys, cd)
     assert idx.last_scan_kernel == "ivf_listmajor_topk_kernel"
     do, io = orc.ivfflat_search_preassigned(off, vecs, ids, xq, k, keys, metric)
-    assert_same_results(dg, ig, do, io, bit_exact=False, rtol=1e-5)
+    assert_same_results(dg, ig, do, io, bit_exact=False, rtol=1e-5 if metric == IP else 1e-4)
     idx.close()

@@ -459,17 +459,14 @@ __global__ void __launch_bounds__(TC_NT)
 // ---- K3 list-major, warp-specialised pipeline -------------------------------------------------
 // Same work item and the same results as ivf_listmajor_topk_kernel, but the three stages of a tile run
 // concurrently in dedicated warps, synchronised by mbarriers only:
-//   warps 4-7  producers: global -> shared with cp.async (16-byte units written straight into the
-//              canonical K-major operand tiles of a ring of LW_STAGES stages, LW_DEPTH chunks in
-//              flight per thread, no registers and no scoreboard held by the loads); when a chunk has
-//              landed each thread splits its own units in place into the TF32 head and the fp32
-//              remainder tile and accumulates the row norms;
+//   warps 4-7  producers: thread p stages row p of the query group and of the list tile, one K = 16
+//              chunk at a time, into a ring of LW_STAGES operand stages (hi/lo TF32 split, canonical
+//              K-major layout), two chunks of global loads in flight per thread;
 //   warp  8    one lane issues the tcgen05 MMAs of a chunk as soon as its stage is full; tcgen05.commit
 //              frees the stage, and after a tile's last chunk hands the accumulator to the epilogue;
 //   warps 0-3  epilogue: tcgen05.ld the 128 x 128 accumulator of tile i (TMEM buffer i & 1) and run
 //              the bound test / key-set update while the MMAs of tile i + 1 fill the other buffer.
-constexpr int LW_STAGES = 5;
-constexpr int LW_DEPTH = 3;  // chunks whose cp.async groups may still be in flight behind the one being split
+constexpr int LW_STAGES = 3;
 constexpr int LW_NT = 288;
 constexpr int LW_RING = LW_STAGES * TC_STAGE_BYTES;
 
@@ -486,11 +483,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(LW_NT, 1)
+__global__ void __launch_bounds__(LW_NT, 2)
     ivf_listmajor_pipe_kernel(const float* __restrict__ xq, int64_t ldq, int d, const LmTile* __restrict__ items,
                               const int64_t* __restrict__ totals, const int64_t* __restrict__ pair_j, int nprobe,
                               ListDirectory dir, int k, int nseg_max, FilterArgs f, unsigned long long* tau_g,
-                              unsigned long long* __restrict__ out, int dbg) {
+                              unsigned long long* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ LwShared sh;
   if ((int64_t)blockIdx.x >= totals[1]) return;
@@ -543,7 +540,7 @@ __global__ void __launch_bounds__(LW_NT, 1)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (i == 0) xn = sh.xn[tid];
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((dbg & 1) ? 0 : TC_N); c0 += 32) {
+      for (int c0 = 0; c0 < TC_N; c0 += 32) {
         uint32_t v[32];
         tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
         // branch-free pass over the 32 columns: scores in place, one bit per column that beats the
@@ -587,57 +584,35 @@ __global__ void __launch_bounds__(LW_NT, 1)
     }
   } else if (warp < 8) {
     // ======================= producers =======================
-    // One K chunk of one operand is 128 rows x 64 bytes = 512 16-byte units; unit (row, k4) lives at
-    // k4 * LBO + row * 16 of its tile.  Lane l of producer warp w owns, for u = 0..3, the unit
-    // (row u*32 + w*8 + l/4, k4 = l%4): a warp copy touches 8 rows x 64 contiguous bytes.
-    const int p = tid - TC_M, pw = warp - 4;
-    const int lq = lane & 3, lr = lane >> 2;
+    const int p = tid - TC_M;
+    const float* arow = nullptr;
+    if (p < t.npairs) arow = xq + (pair_j[t.pair0 + p] / nprobe) * ldq;
     const float* lvecs = dir.vecs[t.list];
     const int64_t* __restrict__ lids = dir.ids[t.list];
-    const float* arow[4];
-    uint32_t uoff[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int r = u * 32 + pw * 8 + lr;
-      arow[u] = r < t.npairs ? xq + (pair_j[t.pair0 + r] / nprobe) * ldq + lq * 4 : nullptr;
-      uoff[u] = (uint32_t)lq * LBO + (uint32_t)r * 16;
-    }
+    const uint32_t row_off = (uint32_t)(p >> 3) * SBO + (uint32_t)(p & 7) * 16;
+    constexpr int NV = TC_BK / 4;
     const int T = ntiles * nk;
-    const uint32_t ring = smem_u32(smem);
-    auto issue = [&](int m) {  // start the copies of chunk m (always commits, so group n == chunk n)
-      if (m < T) {
-        const int i = m / nk, kc = m - i * nk;
-        const int s = m % LW_STAGES;
-        mbar_wait(&sh.empty[s], (uint32_t)(((m / LW_STAGES) & 1) ^ 1));
-        const uint32_t a_hi = ring + (uint32_t)s * TC_STAGE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES;
-        const bool kok = !(dbg & 2) && kc * TC_BK + lq * 4 < d;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int row = t.row0 + i * TC_N + u * 32 + pw * 8 + lr;
-          const bool aok = kok && arow[u] != nullptr, bok = kok && row < row_end;
-          const float* asrc = aok ? arow[u] + kc * TC_BK : xq;  // src-size 0 => the unit is zero-filled
-          const float* bsrc = bok ? lvecs + (int64_t)row * d + kc * TC_BK + lq * 4 : xq;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(a_hi + uoff[u]), "l"(asrc),
-                       "r"(aok ? 16 : 0)
-                       : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(b_hi + uoff[u]), "l"(bsrc),
-                       "r"(bok ? 16 : 0)
-                       : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    float an_acc[4] = {0.f, 0.f, 0.f, 0.f}, bn_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float an_acc = 0.f, bn_acc = 0.f;
     uint32_t myvid = kLmkNoVid;
-#pragma unroll 1
-    for (int m = 0; m < LW_DEPTH; m++) issue(m);
-#pragma unroll 1
-    for (int n = 0; n < T; n++) {
+    float4 pa0[NV], pb0[NV], pa1[NV], pb1[NV];
+    auto prefetch = [&](int n, float4 (&pa)[NV], float4 (&pb)[NV]) {
+      const int i = n / nk, kc = n - i * nk;
+      const int row = t.row0 + i * TC_N + p;
+      const float* brow = row < row_end ? lvecs + (int64_t)row * d : nullptr;
+#pragma unroll
+      for (int kb = 0; kb < NV; kb++) {
+        const int gk = kc * TC_BK + kb * 4;
+        pa[kb] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pb[kb] = pa[kb];
+        if (arow && gk < d) pa[kb] = __ldg(reinterpret_cast<const float4*>(arow + gk));
+        if (brow && gk < d) pb[kb] = __ldg(reinterpret_cast<const float4*>(brow + gk));
+      }
+    };
+    auto chunk = [&](int n, float4 (&pa)[NV], float4 (&pb)[NV]) {
       const int i = n / nk, kc = n - i * nk;
       const int s = n % LW_STAGES;
-      if (kc == 0) {  // new tile: thread p resolves the validity of row p while the chunks stream through
-#pragma unroll
-        for (int u = 0; u < 4; u++) bn_acc[u] = 0.f;
+      if (kc == 0) {  // new tile: row validity is resolved while the tile's chunks stream through
+        bn_acc = 0.f;
         myvid = kLmkNoVid;
         const int row = t.row0 + i * TC_N + p;
         if (row < row_end) {
@@ -645,20 +620,19 @@ __global__ void __launch_bounds__(LW_NT, 1)
           if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw)) myvid = (uint32_t)raw;
         }
       }
-      issue(n + LW_DEPTH);
-      asm volatile("cp.async.wait_group %0;" ::"n"(LW_DEPTH) : "memory");  // this thread's units of chunk n have landed
+      mbar_wait(&sh.empty[s], (uint32_t)(((n / LW_STAGES) & 1) ^ 1));
       unsigned char* a_hi = smem + (size_t)s * TC_STAGE_BYTES;
       unsigned char* a_lo = a_hi + TC_TILE_BYTES;
       unsigned char* b_hi = a_hi + 2 * TC_TILE_BYTES;
       unsigned char* b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const float4 va = *reinterpret_cast<const float4*>(a_hi + uoff[u]);
-        const float4 vb = *reinterpret_cast<const float4*>(b_hi + uoff[u]);
-        an_acc[u] = fmaf(va.x, va.x, an_acc[u]), an_acc[u] = fmaf(va.y, va.y, an_acc[u]);
-        an_acc[u] = fmaf(va.z, va.z, an_acc[u]), an_acc[u] = fmaf(va.w, va.w, an_acc[u]);
-        bn_acc[u] = fmaf(vb.x, vb.x, bn_acc[u]), bn_acc[u] = fmaf(vb.y, vb.y, bn_acc[u]);
-        bn_acc[u] = fmaf(vb.z, vb.z, bn_acc[u]), bn_acc[u] = fmaf(vb.w, vb.w, bn_acc[u]);
+      for (int kb = 0; kb < NV; kb++) {
+        const uint32_t off = (uint32_t)kb * LBO + row_off;
+        const float4 va = pa[kb], vb = pb[kb];
+        an_acc = fmaf(va.x, va.x, an_acc), an_acc = fmaf(va.y, va.y, an_acc);
+        an_acc = fmaf(va.z, va.z, an_acc), an_acc = fmaf(va.w, va.w, an_acc);
+        bn_acc = fmaf(vb.x, vb.x, bn_acc), bn_acc = fmaf(vb.y, vb.y, bn_acc);
+        bn_acc = fmaf(vb.z, vb.z, bn_acc), bn_acc = fmaf(vb.w, vb.w, bn_acc);
         auto split = [](float v, float& hi, float& lo) {
           hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
           lo = v - hi;
@@ -666,31 +640,29 @@ __global__ void __launch_bounds__(LW_NT, 1)
         float4 ah, al, bh, bl;
         split(va.x, ah.x, al.x), split(va.y, ah.y, al.y), split(va.z, ah.z, al.z), split(va.w, ah.w, al.w);
         split(vb.x, bh.x, bl.x), split(vb.y, bh.y, bl.y), split(vb.z, bh.z, bl.z), split(vb.w, bh.w, bl.w);
-        *reinterpret_cast<float4*>(a_hi + uoff[u]) = ah;
-        *reinterpret_cast<float4*>(a_lo + uoff[u]) = al;
-        *reinterpret_cast<float4*>(b_hi + uoff[u]) = bh;
-        *reinterpret_cast<float4*>(b_lo + uoff[u]) = bl;
+        *reinterpret_cast<float4*>(a_hi + off) = ah;
+        *reinterpret_cast<float4*>(a_lo + off) = al;
+        *reinterpret_cast<float4*>(b_hi + off) = bh;
+        *reinterpret_cast<float4*>(b_lo + off) = bl;
       }
       if (kc == nk - 1) {  // tile complete: publish its per-row scalars for the epilogue
         const int b = i & 1;
         mbar_wait(&sh.acc_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));  // epilogue of tile i-2 is done with them
-#pragma unroll
-        for (int u = 0; u < 4; u++) {  // a row's norm is spread over the 4 lanes that share the row
-          float bn = bn_acc[u], an = an_acc[u];
-          bn += __shfl_xor_sync(0xffffffffu, bn, 1), an += __shfl_xor_sync(0xffffffffu, an, 1);
-          bn += __shfl_xor_sync(0xffffffffu, bn, 2), an += __shfl_xor_sync(0xffffffffu, an, 2);
-          if (lq == 0) {
-            const int r = u * 32 + pw * 8 + lr;
-            sh.cn[b][r] = bn;
-            if (i == 0) sh.xn[r] = an;
-          }
-        }
+        sh.cn[b][p] = bn_acc;
         sh.vid[b][p] = myvid;
+        if (i == 0) sh.xn[p] = an_acc;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core proxy
       mbar_arrive(&sh.full[s]);
+      // after the arrive: a release-arrive waits for the thread's outstanding loads
+      if (n + 2 < T) prefetch(n + 2, pa, pb);
+    };
+    if (T > 0) prefetch(0, pa0, pb0);
+    if (T > 1) prefetch(1, pa1, pb1);
+    for (int n = 0; n < T; n += 2) {
+      chunk(n, pa0, pb0);
+      if (n + 1 < T) chunk(n + 1, pa1, pb1);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (lane == 0) {
     // ======================= MMA issuer =======================
     const uint32_t idesc =
@@ -1068,23 +1040,19 @@ cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const
     const char* e = getenv("GB_LM_PIPE");
     return e ? atoi(e) : 1;
   }();
-  static const int dbg = [] {
-    const char* e = getenv("GB_LM_DBG");
-    return e ? atoi(e) : 0;
-  }();
-  if (pipe && d > TC_BK && k <= 32) {  // ring phase arithmetic: >= 2 chunks per tile; smem: ring + k KiB of key sets
+  if (pipe && d > TC_BK) {  // the ring's phase arithmetic assumes >= 2 chunks per tile
     const size_t smem = (size_t)LW_RING + (size_t)k * TC_NT * 8;
     cudaError_t e;
     if (metric == kMetricL2) {
       e = cudaFuncSetAttribute(ivf_listmajor_pipe_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       ivf_listmajor_pipe_kernel<kMetricL2><<<max_items, LW_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir,
-                                                                          k, nseg_max, f, tau_g, out, dbg);
+                                                                          k, nseg_max, f, tau_g, out);
     } else {
       e = cudaFuncSetAttribute(ivf_listmajor_pipe_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       ivf_listmajor_pipe_kernel<kMetricIP><<<max_items, LW_NT, smem, st>>>(xq, ldq, d, items, totals, pair_j, nprobe, dir,
-                                                                          k, nseg_max, f, tau_g, out, dbg);
+                                                                          k, nseg_max, f, tau_g, out);
     }
     note_launch();
     return cudaGetLastError();
