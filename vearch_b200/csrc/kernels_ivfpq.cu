@@ -75,11 +75,17 @@ __global__ void __launch_bounds__(KSUB)
 
 // ---------------- ADC scan ------------------------------------------------------------------
 constexpr int PQ_NT = 256;
-constexpr int PQ_NST = 4;
+constexpr int PQ_NST = 2;
 constexpr int PQ_MAX_PG = 32;  // probes per CTA
 
+// entries per thread per tile for the vector-load code layouts (MW = M / 4 code words per entry):
+// 16 KiB tiles, two stages in flight; per-tile bookkeeping (barrier, tau reload, fill estimate, refill)
+// is paid once per PT entries
+__host__ __device__ constexpr int pq_pt(int MW) { return MW == 2 || MW == 4 ? 4 : (MW == 8 ? 2 : 1); }
+
 __host__ __device__ inline int pq_tile_entries(int M) {
-  int e = 8192 / M;
+  if (M == 8 || M == 16 || M == 32 || M == 64) return pq_pt(M / 4) * PQ_NT;
+  int e = 16384 / M;
   e = (e / PQ_NT) * PQ_NT;
   if (e < PQ_NT) e = PQ_NT;
   if (e > 1024) e = 1024;
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(PQ_NT)
   const int64_t* __restrict__ lids = nullptr;
   // entries per thread per tile: compile-time for the vector-load code layouts (gives the
   // compiler PT independent ADC chains to interleave), runtime for the generic layout
-  constexpr int PT = MW == 2 ? 4 : (MW == 4 ? 2 : 1);
+  constexpr int PT = pq_pt(MW);
   const int per_thread = MW > 0 ? PT : tile_e / PQ_NT;
   int est = 0;  // upper bound of the queue fill, identical in every thread
 
