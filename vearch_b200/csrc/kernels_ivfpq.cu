@@ -81,7 +81,7 @@ constexpr int PQ_MAX_PG = 32;  // probes per CTA
 // entries per thread per tile for the vector-load code layouts (MW = M / 4 code words per entry):
 // 16 KiB tiles, two stages in flight; per-tile bookkeeping (barrier, tau reload, fill estimate, refill)
 // is paid once per PT entries
-__host__ __device__ constexpr int pq_pt(int MW) { return MW == 2 || MW == 4 ? 4 : (MW == 8 ? 2 : 1); }
+__host__ __device__ constexpr int pq_pt(int MW) { return MW == 2 ? 4 : (MW == 4 ? 2 : (MW == 8 ? 2 : 1)); }
 
 __host__ __device__ inline int pq_tile_entries(int M) {
   if (M == 8 || M == 16 || M == 32 || M == 64) return pq_pt(M / 4) * PQ_NT;
