@@ -511,15 +511,18 @@ def test_request_coalescing_matches_direct_search(ivf_state, ivfflat_index):
 
 
 @pytest.mark.parametrize("metric", [L2, IP])
-@pytest.mark.parametrize("nlist,k,kernel", [(16, 10, "ivf_listmajor_topk_kernel"),
-                                            (6, 10, "ivf_listmajor_topk_kernel"),  # lists > 2048 rows: row segments
-                                            (16, 64, "ivf_listmajor_topk_kernel"),
-                                            (16, 100, "ivf_listmajor_tc_kernel+seg_select_kernel")])
-def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric, nlist, k, kernel):
+@pytest.mark.parametrize("nlist,k,d,kernel", [
+    (16, 10, 64, "ivf_listmajor_tma_kernel"),   # TMA-fed pipeline over the pre-tiled mirror
+    (6, 10, 64, "ivf_listmajor_tma_kernel"),    # lists > 2048 rows: row segments
+    (16, 10, 72, "ivf_listmajor_tma_kernel"),   # d not a multiple of the K chunk: zero-padded tail
+    (16, 64, 64, "ivf_listmajor_topk_kernel"),  # 32 < k <= 64: register-staged pipeline
+    (16, 10, 16, "ivf_listmajor_topk_kernel"),  # a single K chunk per tile: the plain fused kernel
+    (16, 100, 64, "ivf_listmajor_tc_kernel+seg_select_kernel")])
+def test_ivfflat_listmajor_tensor_core_scan_matches_oracle(metric, nlist, k, d, kernel):
     """Many queries per list => the list-major grouped-GEMM scan (kernels_tc.cu) is selected: fused
-    top-k epilogue for k <= 64, dense score segments + segment select above.
-    Integer data: scores bit-equal to the oracle; filters and tombstones honoured."""
-    d, n, nq, nprobe = 64, 30000, 700, 6
+    top-k epilogue for k <= 64 (fed by TMA from the mirror for k <= 32), dense score segments +
+    segment select above.  Integer data: scores bit-equal to the oracle; filters and tombstones honoured."""
+    n, nq, nprobe = 30000, 700, 6
     db = synth.sift_like(n, d, seed=95)
     xq = synth.sift_like(nq, d, seed=96)
     cent, _, _ = orc.kmeans(db[:4000], nlist, niter=5)
@@ -568,7 +571,14 @@ def test_ivfflat_listmajor_float_data_within_tolerance(metric, d):
     vecs = codes.view(np.float32).reshape(len(ids), -1)[:, :d]
     cd, keys = orc.coarse_search(cent, xq, nprobe, metric)
     dg, ig = idx.search_preassigned(xq, k, keys, cd)
-    assert idx.last_scan_kernel == "ivf_listmajor_topk_kernel"
+    assert idx.last_scan_kernel == "ivf_listmajor_tma_kernel"
     do, io = orc.ivfflat_search_preassigned(off, vecs, ids, xq, k, keys, metric)
     assert_same_results(dg, ig, do, io, bit_exact=False, rtol=1e-5 if metric == IP else 1e-4)
+    # the mirror follows the lists: vectors added after it was built are found by the next search
+    more = synth.embed_like(300, d, seed=99, n_clusters=32)
+    idx.add_vectors(more)
+    idx.add_pending()
+    dg2, ig2 = idx.search_preassigned(more[:40], 1, *reversed(orc.coarse_search(cent, more[:40], nlist, metric)))
+    assert idx.last_scan_kernel == "ivf_listmajor_tma_kernel"
+    assert np.array_equal(ig2[:, 0], n + np.arange(40))
     idx.close()

@@ -780,7 +780,10 @@ IVFFlatIndex::IVFFlatIndex(int d, const ModelParams& mp, int device, int seg_shi
   cudaMalloc(&d_centroids_, (size_t)nlist_ * dpad_ * 4);
   cudaMemset(d_centroids_, 0, (size_t)nlist_ * dpad_ * 4);
 }
-IVFFlatIndex::~IVFFlatIndex() { cudaFree(d_centroids_); }
+IVFFlatIndex::~IVFFlatIndex() {
+  if (mirror_.base) cudaFree(mirror_.base);
+  if (mirror_.norms) cudaFree(mirror_.norms);
+  if (mirror_.d_tile0) cudaFree(mirror_.d_tile0); cudaFree(d_centroids_); }
 
 int IVFFlatIndex::training_threshold() const {
   // gamma_index_ivfflat.cc:239: default nlist * 200 ; Indexing() clamps to [39, 256] * nlist (:350-375)
@@ -972,6 +975,64 @@ static int listmajor_mode() {
   return v;
 }
 static bool listmajor_enabled() { return listmajor_mode() != 0; }
+static bool tma_enabled() {  // GB_TC_MIRROR=0: never build the pre-tiled mirror (register-staged kernel)
+  static int v = [] {
+    const char* e = getenv("GB_TC_MIRROR");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+int IVFFlatIndex::ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStream_t st) {
+  if (type_ != "IVFFLAT" || !lists_) return 1;
+  lk.lock();
+  if (mirror_.disabled) return 1;
+  if (mirror_.base && mirror_.lens == lists_->lens()) return 0;
+  lk.unlock();
+  {
+    std::unique_lock<std::shared_mutex> x(mirror_rw_);
+    if (!mirror_.disabled && !(mirror_.base && mirror_.lens == lists_->lens())) {
+      const std::vector<int>& lens = lists_->lens();
+      std::vector<int64_t> tile0(nlist_ + 1, 0);
+      for (int l = 0; l < nlist_; l++) tile0[l + 1] = tile0[l] + (lens[l] + 127) / 128;
+      const int64_t tiles = tile0[nlist_];
+      const int k16 = (int)round_up(dpad_, 16);
+      const size_t tile_bytes = (size_t)tc_mirror_tile_floats(k16) * 4;
+      cudaDeviceSynchronize();  // kernels of other searches may still be reading the mirror
+      if (tiles > mirror_.cap_tiles) {
+        if (mirror_.base) cudaFree(mirror_.base);
+        if (mirror_.norms) cudaFree(mirror_.norms);
+        mirror_.base = mirror_.norms = nullptr;
+        mirror_.cap_tiles = 0;
+        const int64_t cap = tiles + tiles / 8 + 16;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t need = (size_t)cap * (tile_bytes + 512);
+        if (need + ((size_t)4 << 30) > free_b || cudaMalloc(&mirror_.base, (size_t)cap * tile_bytes) != cudaSuccess ||
+            cudaMalloc(&mirror_.norms, (size_t)cap * 512) != cudaSuccess) {
+          if (mirror_.base) cudaFree(mirror_.base);
+          mirror_.base = nullptr;
+          cudaGetLastError();
+          mirror_.disabled = true;  // HBM too full for a second, doubled copy of the lists
+        } else {
+          mirror_.cap_tiles = cap;
+        }
+      }
+      if (!mirror_.disabled) {
+        if (!mirror_.d_tile0 && cudaMalloc(&mirror_.d_tile0, sizeof(int64_t) * (nlist_ + 1)) != cudaSuccess) return -1;
+        GB_CUDA(cudaMemcpyAsync(mirror_.d_tile0, tile0.data(), sizeof(int64_t) * (nlist_ + 1), cudaMemcpyHostToDevice, st));
+        GB_CUDA(launch_tc_mirror_build(lists_->directory(), dpad_, k16, mirror_.d_tile0, tiles, mirror_.base, mirror_.norms,
+                                       st));
+        GB_CUDA(cudaStreamSynchronize(st));  // tile0 is a stack vector; other streams may use the mirror next
+        mirror_.tiles = tiles;
+        mirror_.lens = lens;
+      }
+    }
+  }
+  lk.lock();
+  if (mirror_.disabled) return 1;
+  return (mirror_.base && mirror_.lens == lists_->lens()) ? 0 : 1;
+}
 
 int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, const float* xq, int k,
                                      const int32_t* probe_ids, int nprobe, unsigned long long* out_keys, Scratch& s) {
@@ -989,6 +1050,7 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
     GB_ALLOC(d_start, int32_t, nlist_, s);
     GB_ALLOC(d_cursor, int32_t, nlist_, s);
     GB_ALLOC(d_item_start, int32_t, nlist_, s);
+    GB_ALLOC(d_grp_start, int32_t, nlist_, s);
     GB_ALLOC(d_totals, int64_t, 3, s);
     GB_ALLOC(d_pair_j, int64_t, npairs, s);
     GB_ALLOC(d_items, LmTile, max_items, s);
@@ -997,13 +1059,35 @@ int IVFFlatIndex::scan_listmajor_dev(const FilterArgs& f, int metric, int nq, co
     GB_ALLOC(d_out, unsigned long long, nout, s);
     GB_CUDA(cudaMemsetAsync(d_tau, 0xFF, sizeof(unsigned long long) * nq, st));
     GB_CUDA(cudaMemsetAsync(d_out, 0xFF, sizeof(unsigned long long) * nout, st));
-    GB_CUDA(launch_lmk_group(probe_ids, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_totals, d_pair_j,
-                             d_items, st));
-    last_scan_kernel_ = "ivf_listmajor_topk_kernel";
-    scan_timer_begin(st);
-    GB_CUDA(launch_ivf_listmajor_topk(xq, dpad_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe, dir, k, nseg,
-                                      metric, f, d_tau, d_out, st));
-    scan_timer_end(st);
+    GB_CUDA(launch_lmk_group(probe_ids, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
+                             d_pair_j, d_items, st));
+    const int k16 = (int)round_up(dpad_, 16);
+    const int64_t max_groups = npairs / 128 + nlist_;
+    const size_t slot_bytes = (size_t)128 * k16 * 8, a_bytes = (size_t)max_groups * (slot_bytes + 128 * 4);
+    std::shared_lock<std::shared_mutex> mlk(mirror_rw_, std::defer_lock);
+    bool tma = tma_enabled() && k <= 32 && k16 > 16 && a_bytes <= ((size_t)8 << 30) && ensure_mirror(mlk, st) == 0;
+    if (tma) {
+      float* a_scratch = static_cast<float*>(big_acquire(a_bytes, st));
+      if (!a_scratch) return -1;
+      auto rel_fn = [this, a_scratch, st](void*) { big_release(a_scratch, st); };
+      std::unique_ptr<void, decltype(rel_fn)> rel(a_scratch, rel_fn);
+      float* a_norms = reinterpret_cast<float*>(reinterpret_cast<char*>(a_scratch) + (size_t)max_groups * slot_bytes);
+      TcMirrorView mv{mirror_.base, mirror_.d_tile0, mirror_.norms, k16};
+      last_scan_kernel_ = "ivf_listmajor_tma_kernel";
+      scan_timer_begin(st);
+      GB_CUDA(launch_lm_stage_queries(xq, dpad_, dpad_, k16, d_items, (int)max_items, d_totals, d_pair_j, nprobe, a_scratch,
+                                      a_norms, st));
+      GB_CUDA(launch_ivf_listmajor_tma(a_scratch, a_norms, mv, d_items, (int)max_items, d_totals, d_pair_j, nprobe, dir, k,
+                                       nseg, metric, f, d_tau, d_out, st));
+      scan_timer_end(st);
+    } else {
+      last_scan_kernel_ = "ivf_listmajor_topk_kernel";
+      scan_timer_begin(st);
+      GB_CUDA(launch_ivf_listmajor_topk(xq, dpad_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe, dir, k, nseg,
+                                        metric, f, d_tau, d_out, st));
+      scan_timer_end(st);
+    }
+    if (mlk.owns_lock()) mlk.unlock();
     GB_CUDA(launch_select_keys(d_out, (int64_t)nprobe * nseg * k, nq, nprobe * nseg * k, k, out_keys, k, st));
     return 0;
   }

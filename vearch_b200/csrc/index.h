@@ -324,6 +324,22 @@ class IVFFlatIndex : public Index {
   float* d_centroids_ = nullptr;  // [nlist][dpad]
   std::unique_ptr<IvfLists> lists_;
   std::vector<uint64_t> vid2pos_;  // vid -> (list << 32 | pos), ~0 = not in a list (vid_bucket_no_pos_)
+
+  // Tensor-core mirror of the lists (IVFFLAT only; kernels_tc.cu): every list once more, pre-split and
+  // pre-tiled in the shared-memory operand layout so the list-major kernel is fed by cp.async.bulk.
+  // Rebuilt lazily by the first list-major search after the lists grew; users hold mirror_rw_ shared
+  // from the freshness check until their kernels are enqueued, the rebuilder takes it exclusively and
+  // drains the device first.  Skipped (register-staged kernel instead) when HBM is too full for it.
+  struct TcMirror {
+    float* base = nullptr;
+    float* norms = nullptr;
+    int64_t* d_tile0 = nullptr;
+    int64_t tiles = 0, cap_tiles = 0;
+    std::vector<int> lens;
+    bool disabled = false;
+  } mirror_;
+  std::shared_mutex mirror_rw_;
+  int ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStream_t st);  // 0 = usable and current
 };
 
 class IVFPQIndex : public IVFFlatIndex {

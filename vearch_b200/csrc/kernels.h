@@ -70,6 +70,7 @@ int ivfflat_scan_nparts(int nprobe, int max_list_len);
 // K3 list-major (tensor cores): (query, probe) pairs grouped by list; tile = 128 pairs x 128 rows.
 struct LmTile {
   int list, pair0, npairs, row0, nrows, seg;
+  int grp;  // ordinal of this (list, pair group): its slot in the staged-query scratch
 };
 // scores[pair_off[j] + r] = score(query pair_q[j], row r of its list)
 cudaError_t launch_ivf_listmajor_tc(const float* xq, int64_t ldq, int d, const LmTile* tiles, int ntiles,
@@ -95,10 +96,30 @@ cudaError_t launch_seg_select(const float* scores, const int64_t* seg_off, const
 // out[(j * nseg_max + seg) * k + i], j = q * nprobe + p; unused slots must be pre-set to the sentinel.
 constexpr int kLmkMaxK = 64;
 constexpr int kLmkSegRows = 2048;
-// grouping: cnt/start/cursor/item_start: [nlist] ints, totals[1] = number of items (device side)
+// grouping: cnt/start/cursor/item_start/grp_start: [nlist] ints; totals = {groups, items, pairs} (device side)
 cudaError_t launch_lmk_group(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int nseg_max, int32_t* cnt,
-                             int32_t* start, int32_t* cursor, int32_t* item_start, int64_t* totals, int64_t* pair_j,
-                             LmTile* items, cudaStream_t st);
+                             int32_t* start, int32_t* cursor, int32_t* item_start, int32_t* grp_start, int64_t* totals,
+                             int64_t* pair_j, LmTile* items, cudaStream_t st);
+// TMA-fed variant (kernels_tc.cu, "mirror"): the lists are kept a second time pre-split (TF32 head +
+// fp32 remainder) and pre-tiled in the exact shared-memory operand layout, so a K chunk of a 128-row
+// tile is one contiguous 16 KiB block a single cp.async.bulk brings in; row norms are precomputed.
+struct TcMirrorView {
+  const float* base;     // tile t of the index at base + t * tile_floats(k16)
+  const int64_t* tile0;  // [nlist + 1] first tile of every list
+  const float* norms;    // [total_tiles * 128] |y|^2, 0 for padding rows
+  int k16;               // row length rounded up to the K chunk (16)
+};
+inline int64_t tc_mirror_tile_floats(int k16) { return (int64_t)128 * k16 * 2; }
+cudaError_t launch_tc_mirror_build(ListDirectory dir, int d, int k16, const int64_t* tile0, int64_t total_tiles,
+                                   float* mirror, float* norms, cudaStream_t st);
+// a_scratch: per pair group nk chunks of 16 KiB (hi, lo) of the group's 128 queries; a_norms: [group][128]
+cudaError_t launch_lm_stage_queries(const float* xq, int64_t ldq, int d, int k16, const LmTile* items, int max_items,
+                                    const int64_t* totals, const int64_t* pair_j, int nprobe, float* a_scratch,
+                                    float* a_norms, cudaStream_t st);
+cudaError_t launch_ivf_listmajor_tma(const float* a_scratch, const float* a_norms, TcMirrorView mv, const LmTile* items,
+                                     int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
+                                     ListDirectory dir, int k, int nseg_max, int metric, FilterArgs f,
+                                     unsigned long long* tau_g, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const LmTile* items, int max_items,
                                       const int64_t* totals, const int64_t* pair_j, int nprobe, ListDirectory dir, int k,
                                       int nseg_max, int metric, FilterArgs f, unsigned long long* tau_g,

@@ -704,6 +704,251 @@ __global__ void __launch_bounds__(LW_NT, 2)
   }
 }
 
+// ---- K3 list-major, TMA-fed pipeline over the pre-tiled mirror ---------------------------------
+// Same work items, same epilogue and the same results as ivf_listmajor_pipe_kernel; what changes is
+// who feeds the tensor core.  Both operands already sit in global memory in the canonical operand
+// layout (lists: the mirror built by tc_mirror_build_kernel; queries: staged per pair group by
+// lm_stage_queries_kernel), so one thread issues two 16 KiB cp.async.bulk copies per K chunk into
+// a ring of stages and the copies complete on the stage's mbarrier (complete_tx).  No producer warps, no
+// registers or scoreboards tied up by loads, as many chunks in flight as the ring is deep.
+//   warps 0-3  epilogue (thread = pair): fetch the tile's row ids / norms, tcgen05.ld, bound test
+//   warp  4    lane 0: TMA producer          warp 5    lane 0: MMA issuer
+constexpr int LT_STAGES = 3;
+constexpr int LT_NT = 192;
+constexpr int LT_RING = LT_STAGES * TC_STAGE_BYTES;
+
+struct LtShared {
+  alignas(16) float cn[2][TC_N];
+  uint32_t vid[2][TC_N];
+  uint64_t full[LT_STAGES], empty[LT_STAGES], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(LT_NT, 2)
+    ivf_listmajor_tma_kernel(const float* __restrict__ a_scratch, const float* __restrict__ a_norms, TcMirrorView mv,
+                             const LmTile* __restrict__ items, const int64_t* __restrict__ totals,
+                             const int64_t* __restrict__ pair_j, int nprobe, ListDirectory dir, int k, int nseg_max,
+                             FilterArgs f, unsigned long long* tau_g, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ LtShared sh;
+  if ((int64_t)blockIdx.x >= totals[1]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const LmTile t = items[blockIdx.x];
+  const int row_end = t.row0 + t.nrows;
+  const int ntiles = (t.nrows + TC_N - 1) / TC_N;
+  const int nk = mv.k16 / TC_BK;
+  const uint32_t LBO = TC_M * 16, SBO = 128;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                 "n"(2 * TC_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < LT_STAGES; s++) {
+      mbar_init(&sh.full[s], 1);   // the producer's arrive.expect_tx; the copies complete the phase
+      mbar_init(&sh.empty[s], 1);  // tcgen05.commit
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&sh.acc_full[b], 1);
+      mbar_init(&sh.acc_empty[b], TC_M);
+    }
+    mbar_fence_init();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = sh.tmem_base;
+  const int64_t tile_floats = (int64_t)TC_N * mv.k16 * 2;
+  const int64_t ltile0 = mv.tile0[t.list] + t.row0 / TC_N;  // first mirror tile of this item
+
+  if (warp < 4) {
+    // ======================= epilogue =======================
+    unsigned long long* hk = reinterpret_cast<unsigned long long*>(smem + LT_RING) + tid;
+    const bool valid = tid < t.npairs;
+    int64_t j = 0;
+    int q = 0;
+    LmkState st{0ull, 0};
+    if (valid) {
+      j = pair_j[t.pair0 + tid];
+      q = (int)(j / nprobe);
+      st.tau = __ldcg(tau_g + q);
+    }
+    float bound = lmk_bound<METRIC>(st.tau);
+    const float xn = a_norms[(int64_t)t.grp * TC_M + tid];
+    const int64_t* __restrict__ lids = dir.ids[t.list];
+    for (int i = 0; i < ntiles; i++) {
+      const int b = i & 1;
+      {  // this tile's per-row scalars, fetched while its MMAs run
+        const int row = t.row0 + i * TC_N + tid;
+        uint32_t myvid = kLmkNoVid;
+        float cn = 0.f;
+        if (row < row_end) {
+          const int64_t raw = lids[row];  // tombstone: gamma_index_ivfflat.h:72
+          if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw)) myvid = (uint32_t)raw;
+          cn = mv.norms[(ltile0 + i) * TC_N + tid];
+        }
+        sh.cn[b][tid] = cn;
+        sh.vid[b][tid] = myvid;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      }
+      mbar_wait(&sh.acc_full[b], (uint32_t)((i >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = 0; c0 < TC_N; c0 += 32) {
+        uint32_t v[32];
+        tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
+        uint32_t hit = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 32; j4 += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(&sh.cn[b][c0 + j4]);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const float sc = tc_score<METRIC>(__uint_as_float(v[j4 + u]), xn, cc[u]);
+            v[j4 + u] = __float_as_uint(sc);
+            hit |= (METRIC == kMetricL2 ? sc <= bound : sc >= bound) ? (1u << (j4 + u)) : 0u;
+          }
+        }
+        if (hit) {
+#pragma unroll
+          for (int jj = 0; jj < 32; jj++) {
+            if (hit & (1u << jj))
+              st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
+          }
+          bound = lmk_bound<METRIC>(st.tau);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&sh.acc_empty[b]);
+      if (valid) {
+        const unsigned long long tg = __ldcg(tau_g + q);
+        if (tg < st.tau) {
+          st.tau = tg;
+          bound = lmk_bound<METRIC>(st.tau);
+        } else if (st.tau < tg) {
+          atomicMin(tau_g + q, st.tau);
+        }
+      }
+    }
+    if (valid) {
+      unsigned long long* o = out + ((int64_t)j * nseg_max + t.seg) * k;
+      for (int i = 0; i < k; i++) o[i] = i < st.n ? hk[i * TC_NT] : kKeySentinel;
+    }
+  } else if (warp == 4) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      const char* asrc = reinterpret_cast<const char*>(a_scratch) + (int64_t)t.grp * nk * (TC_STAGE_BYTES / 2);
+      const char* bsrc = reinterpret_cast<const char*>(mv.base + ltile0 * tile_floats);
+      int n = 0;
+      for (int i = 0; i < ntiles; i++) {
+        for (int kc = 0; kc < nk; kc++, n++) {
+          const int s = n % LT_STAGES;
+          mbar_wait(&sh.empty[s], (uint32_t)(((n / LT_STAGES) & 1) ^ 1));
+          unsigned char* stage = smem + (size_t)s * TC_STAGE_BYTES;
+          mbar_arrive_expect_tx(&sh.full[s], TC_STAGE_BYTES);
+          bulk_g2s(stage, asrc + (int64_t)kc * (TC_STAGE_BYTES / 2), TC_STAGE_BYTES / 2, &sh.full[s]);
+          bulk_g2s(stage + TC_STAGE_BYTES / 2, bsrc + ((int64_t)i * nk + kc) * (TC_STAGE_BYTES / 2), TC_STAGE_BYTES / 2,
+                   &sh.full[s]);
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc =
+        (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    for (int i = 0; i < ntiles; i++) {
+      const int b = i & 1;
+      mbar_wait(&sh.acc_empty[b], (uint32_t)(((i >> 1) & 1) ^ 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc = tmem_d + (uint32_t)(b * TC_N);
+      for (int kc = 0; kc < nk; kc++) {
+        const int n = i * nk + kc;
+        const int s = n % LT_STAGES;
+        mbar_wait(&sh.full[s], (uint32_t)((n / LT_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + (size_t)s * TC_STAGE_BYTES);
+        const uint32_t a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ks++) {
+          const uint32_t koff = (uint32_t)ks * 2 * LBO;
+          const uint64_t dah = make_smem_desc(a_hi + koff, LBO, SBO), dal = make_smem_desc(a_lo + koff, LBO, SBO);
+          const uint64_t dbh = make_smem_desc(b_hi + koff, LBO, SBO), dbl = make_smem_desc(b_lo + koff, LBO, SBO);
+          tc_mma_tf32(acc, dah, dbh, idesc, (kc | ks) != 0);
+          tc_mma_tf32(acc, dah, dbl, idesc, 1);
+          tc_mma_tf32(acc, dal, dbh, idesc, 1);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&sh.empty[s]))
+                     : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(&sh.acc_full[b]))
+                   : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * TC_N) : "memory");
+  }
+}
+
+// one operand row -> its 16-byte units of every K chunk, TF32 head and fp32 remainder, canonical
+// K-major layout; returns |row|^2 accumulated in index order (the order the staging loops use)
+__device__ __forceinline__ float tc_split_row(const float* __restrict__ src, int d, int k16, int r, float* tile) {
+  float nrm = 0.f;
+  for (int kc = 0; kc < k16 / TC_BK; kc++) {
+    float* hi = tile + (int64_t)kc * (TC_STAGE_BYTES / 8);  // 16 KiB per chunk = 4096 floats: hi then lo
+    float* lo = hi + TC_TILE_BYTES / 4;
+#pragma unroll
+    for (int k4 = 0; k4 < 4; k4++) {
+      const int gk = kc * TC_BK + k4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src && gk < d) v = __ldg(reinterpret_cast<const float4*>(src + gk));
+      nrm = fmaf(v.x, v.x, nrm), nrm = fmaf(v.y, v.y, nrm), nrm = fmaf(v.z, v.z, nrm), nrm = fmaf(v.w, v.w, nrm);
+      float4 h, l;
+      h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), l.x = v.x - h.x;
+      h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u), l.y = v.y - h.y;
+      h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), l.z = v.z - h.z;
+      h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u), l.w = v.w - h.w;
+      const int off = k4 * (TC_M * 4) + r * 4;  // unit (r, k4): k4 * LBO + r * 16 bytes
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  }
+  return nrm;
+}
+
+__global__ void __launch_bounds__(TC_N)
+    tc_mirror_build_kernel(ListDirectory dir, int d, int k16, const int64_t* __restrict__ tile0, float* __restrict__ mirror,
+                           float* __restrict__ norms) {
+  const int64_t gt = blockIdx.x;
+  int lo = 0, hi = dir.nlist;  // last list whose first tile is <= gt
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tile0[mid] <= gt) lo = mid; else hi = mid;
+  }
+  const int l = lo, r = threadIdx.x;
+  const int row = (int)(gt - tile0[l]) * TC_N + r;
+  const float* src = row < dir.len[l] ? dir.vecs[l] + (int64_t)row * d : nullptr;
+  norms[gt * TC_N + r] = tc_split_row(src, d, k16, r, mirror + gt * ((int64_t)TC_N * k16 * 2));
+}
+
+__global__ void __launch_bounds__(TC_M)
+    lm_stage_queries_kernel(const float* __restrict__ xq, int64_t ldq, int d, int k16, const LmTile* __restrict__ items,
+                            const int64_t* __restrict__ totals, const int64_t* __restrict__ pair_j, int nprobe,
+                            float* __restrict__ a_scratch, float* __restrict__ a_norms) {
+  if ((int64_t)blockIdx.x >= totals[1]) return;
+  const LmTile t = items[blockIdx.x];
+  if (t.seg != 0) return;  // one staging per pair group: the first item of the group owns the slot
+  const int r = threadIdx.x;
+  const float* src = r < t.npairs ? xq + (pair_j[t.pair0 + r] / nprobe) * ldq : nullptr;
+  a_norms[(int64_t)t.grp * TC_M + r] = tc_split_row(src, d, k16, r, a_scratch + (int64_t)t.grp * ((int64_t)TC_M * k16 * 2));
+}
+
 // ---- grouping for the fused kernel: histogram (lm_count_kernel) -> scan -> slots -> items ----
 __device__ __forceinline__ int lmk_nseg(int len, int nseg_max) {
   int n = (len + kLmkSegRows - 1) / kLmkSegRows;
@@ -712,38 +957,42 @@ __device__ __forceinline__ int lmk_nseg(int len, int nseg_max) {
 
 __global__ void __launch_bounds__(1024)
     lmk_scan_kernel(const int32_t* __restrict__ cnt, ListDirectory dir, int nseg_max, int32_t* __restrict__ start,
-                    int32_t* __restrict__ item_start, int64_t* __restrict__ totals) {
-  __shared__ long long s_pairs[1024], s_items[1024];
-  __shared__ long long carry[2];
+                    int32_t* __restrict__ item_start, int32_t* __restrict__ grp_start, int64_t* __restrict__ totals) {
+  __shared__ long long s_pairs[1024], s_items[1024], s_grps[1024];
+  __shared__ long long carry[3];
   const int tid = threadIdx.x;
-  if (tid == 0) carry[0] = carry[1] = 0;
+  if (tid == 0) carry[0] = carry[1] = carry[2] = 0;
   __syncthreads();
   for (int base = 0; base < dir.nlist; base += 1024) {
     const int l = base + tid;
-    long long c = 0, it = 0;
+    long long c = 0, it = 0, g = 0;
     if (l < dir.nlist) {
       c = cnt[l];
       const int len = dir.len[l];
-      if (c > 0 && len > 0) it = ((c + TC_M - 1) / TC_M) * lmk_nseg(len, nseg_max);
+      if (c > 0 && len > 0) {
+        g = (c + TC_M - 1) / TC_M;
+        it = g * lmk_nseg(len, nseg_max);
+      }
     }
-    s_pairs[tid] = c, s_items[tid] = it;
+    s_pairs[tid] = c, s_items[tid] = it, s_grps[tid] = g;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
-      long long a = 0, b = 0;
-      if (tid >= off) a = s_pairs[tid - off], b = s_items[tid - off];
+      long long a = 0, b = 0, e = 0;
+      if (tid >= off) a = s_pairs[tid - off], b = s_items[tid - off], e = s_grps[tid - off];
       __syncthreads();
-      s_pairs[tid] += a, s_items[tid] += b;
+      s_pairs[tid] += a, s_items[tid] += b, s_grps[tid] += e;
       __syncthreads();
     }
     if (l < dir.nlist) {
       start[l] = (int32_t)(carry[0] + s_pairs[tid] - c);
       item_start[l] = (int32_t)(carry[1] + s_items[tid] - it);
+      grp_start[l] = (int32_t)(carry[2] + s_grps[tid] - g);
     }
     __syncthreads();
-    if (tid == 1023) carry[0] += s_pairs[1023], carry[1] += s_items[1023];
+    if (tid == 1023) carry[0] += s_pairs[1023], carry[1] += s_items[1023], carry[2] += s_grps[1023];
     __syncthreads();
   }
-  if (tid == 0) totals[0] = 0, totals[1] = carry[1], totals[2] = carry[0];
+  if (tid == 0) totals[0] = carry[2], totals[1] = carry[1], totals[2] = carry[0];  // groups, items, pairs
 }
 
 __global__ void lmk_assign_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, ListDirectory dir,
@@ -757,8 +1006,8 @@ __global__ void lmk_assign_kernel(const int32_t* __restrict__ probe_ids, int64_t
 }
 
 __global__ void lmk_items_kernel(const int32_t* __restrict__ cnt, const int32_t* __restrict__ start,
-                                 const int32_t* __restrict__ item_start, ListDirectory dir, int nseg_max,
-                                 LmTile* __restrict__ items) {
+                                 const int32_t* __restrict__ item_start, const int32_t* __restrict__ grp_start,
+                                 ListDirectory dir, int nseg_max, LmTile* __restrict__ items) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= dir.nlist) return;
   const int c = cnt[l], len = dir.len[l];
@@ -771,6 +1020,7 @@ __global__ void lmk_items_kernel(const int32_t* __restrict__ cnt, const int32_t*
       LmTile tl;
       tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(TC_M, c - p0);
       tl.row0 = sg * seglen, tl.nrows = max(0, min(seglen, len - tl.row0)), tl.seg = sg;
+      tl.grp = grp_start[l] + p0 / TC_M;
       items[it++] = tl;
     }
 }
@@ -921,7 +1171,7 @@ __global__ void lm_tiles_kernel(const int32_t* __restrict__ cnt, const int32_t* 
   for (int p0 = 0; p0 < c; p0 += 128)
     for (int r0 = 0; r0 < len; r0 += 128) {
       LmTile tl;
-      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(128, c - p0), tl.row0 = r0, tl.nrows = min(128, len - r0), tl.seg = 0;
+      tl.list = l, tl.pair0 = start[l] + p0, tl.npairs = min(128, c - p0), tl.row0 = r0, tl.nrows = min(128, len - r0), tl.seg = 0, tl.grp = 0;
       tiles[t++] = tl;
     }
 }
@@ -1011,8 +1261,8 @@ cudaError_t launch_lm_assign_tiles(const int32_t* probe_ids, int64_t npairs, int
 }
 
 cudaError_t launch_lmk_group(const int32_t* probe_ids, int64_t npairs, ListDirectory dir, int nseg_max, int32_t* cnt,
-                             int32_t* start, int32_t* cursor, int32_t* item_start, int64_t* totals, int64_t* pair_j,
-                             LmTile* items, cudaStream_t st) {
+                             int32_t* start, int32_t* cursor, int32_t* item_start, int32_t* grp_start, int64_t* totals,
+                             int64_t* pair_j, LmTile* items, cudaStream_t st) {
   if (npairs <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * dir.nlist, st);
   if (e != cudaSuccess) return e;
@@ -1021,11 +1271,52 @@ cudaError_t launch_lmk_group(const int32_t* probe_ids, int64_t npairs, ListDirec
   const unsigned nb = (unsigned)((npairs + 255) / 256);
   lm_count_kernel<<<nb, 256, 0, st>>>(probe_ids, npairs, dir, cnt);
   note_launch();
-  lmk_scan_kernel<<<1, 1024, 0, st>>>(cnt, dir, nseg_max, start, item_start, totals);
+  lmk_scan_kernel<<<1, 1024, 0, st>>>(cnt, dir, nseg_max, start, item_start, grp_start, totals);
   note_launch();
   lmk_assign_kernel<<<nb, 256, 0, st>>>(probe_ids, npairs, dir, start, cursor, pair_j);
   note_launch();
-  lmk_items_kernel<<<(dir.nlist + 255) / 256, 256, 0, st>>>(cnt, start, item_start, dir, nseg_max, items);
+  lmk_items_kernel<<<(dir.nlist + 255) / 256, 256, 0, st>>>(cnt, start, item_start, grp_start, dir, nseg_max, items);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_mirror_build(ListDirectory dir, int d, int k16, const int64_t* tile0, int64_t total_tiles,
+                                   float* mirror, float* norms, cudaStream_t st) {
+  if (total_tiles <= 0) return cudaSuccess;
+  if (total_tiles > INT32_MAX || (d & 3) || (k16 % TC_BK)) return cudaErrorInvalidValue;
+  tc_mirror_build_kernel<<<(unsigned)total_tiles, TC_N, 0, st>>>(dir, d, k16, tile0, mirror, norms);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lm_stage_queries(const float* xq, int64_t ldq, int d, int k16, const LmTile* items, int max_items,
+                                    const int64_t* totals, const int64_t* pair_j, int nprobe, float* a_scratch,
+                                    float* a_norms, cudaStream_t st) {
+  if (max_items <= 0) return cudaSuccess;
+  lm_stage_queries_kernel<<<max_items, TC_M, 0, st>>>(xq, ldq, d, k16, items, totals, pair_j, nprobe, a_scratch, a_norms);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ivf_listmajor_tma(const float* a_scratch, const float* a_norms, TcMirrorView mv, const LmTile* items,
+                                     int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
+                                     ListDirectory dir, int k, int nseg_max, int metric, FilterArgs f,
+                                     unsigned long long* tau_g, unsigned long long* out, cudaStream_t st) {
+  if (k <= 0 || k > kLmkMaxK || mv.k16 <= TC_BK || (mv.k16 % TC_BK)) return cudaErrorInvalidValue;
+  if (max_items <= 0) return cudaSuccess;
+  const size_t smem = (size_t)LT_RING + (size_t)k * TC_NT * 8;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(ivf_listmajor_tma_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_tma_kernel<kMetricL2><<<max_items, LT_NT, smem, st>>>(a_scratch, a_norms, mv, items, totals, pair_j, nprobe,
+                                                                       dir, k, nseg_max, f, tau_g, out);
+  } else {
+    e = cudaFuncSetAttribute(ivf_listmajor_tma_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    ivf_listmajor_tma_kernel<kMetricIP><<<max_items, LT_NT, smem, st>>>(a_scratch, a_norms, mv, items, totals, pair_j, nprobe,
+                                                                       dir, k, nseg_max, f, tau_g, out);
+  }
   note_launch();
   return cudaGetLastError();
 }
