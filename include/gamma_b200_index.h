@@ -101,6 +101,10 @@ int gb_index_tombstone(gb_index *index, int list, int pos);
  * the file indexes must already be in the store (gb_index_add); *load_num = vectors covered, 0 if
  * there is no file.  FLAT indexes: both are no-ops. */
 int gb_index_dump(gb_index *index, const char *dir, const char *abs_name);
+/* re-pack the inverted lists into one tight allocation (the growable lists of
+ * realtime_mem_data.cc never give memory back; neither do ours until this runs).  Also done
+ * automatically after a bulk add when more than half of the list memory is dead. */
+int gb_index_compact(gb_index *index);
 int gb_index_load(gb_index *index, const char *dir, const char *abs_name, int64_t *load_num);
 /* quantizer->search (gamma_index_ivfflat.cc:568) */
 int gb_index_coarse_search(gb_index *index, int nq, const float *x, int nprobe, float *out_dis, int64_t *out_ids);

@@ -582,3 +582,29 @@ def test_ivfflat_listmajor_float_data_within_tolerance(metric, d):
     assert idx.last_scan_kernel == "ivf_listmajor_tma_kernel"
     assert np.array_equal(ig2[:, 0], n + np.arange(40))
     idx.close()
+
+
+def test_ivf_lists_compaction_keeps_results(ivf_state):
+    """Lists grown in many small steps leave dead regions behind; compact() re-packs them: same
+    lists, same answers, less memory, and the index keeps accepting vectors afterwards."""
+    s = ivf_state
+    idx = gi().GammaIndex("IVFFLAT", s["d"], {"ncentroids": s["nlist"], "nprobe": 8, "metric_type": "L2"})
+    idx.set_centroids(s["cent"])
+    for a in range(0, 12000, 500):
+        idx.add_vectors(s["db"][a:a + 500])
+        idx.add_pending()
+    before = idx.export_lists()
+    ref = idx.search(s["xq"], 10, params={"nprobe": 8})
+    mem0 = idx.mem_bytes(0)
+    idx.compact()
+    after = idx.export_lists()
+    assert all(np.array_equal(a, b) for a, b in zip(before, after))
+    assert idx.mem_bytes(0) < mem0
+    got = idx.search(s["xq"], 10, params={"nprobe": 8})
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    idx.add_vectors(s["db"][12000:13000])
+    idx.add_pending()
+    do, io = orc.flat_search(s["db"][:13000], s["db"][12500:12501], 1, L2)
+    dg, ig = idx.search(s["db"][12500:12501], 1, params={"nprobe": s["nlist"]})
+    assert ig[0, 0] == io[0, 0] == 12500 and dg[0, 0] == do[0, 0]
+    idx.close()

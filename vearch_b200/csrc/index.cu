@@ -248,6 +248,48 @@ int IvfLists::commit(const std::vector<int>& add, cudaStream_t st) {
   GB_CUDA(cudaMemcpyAsync(d_len_, h_len_.data(), sizeof(int) * nlist_, cudaMemcpyHostToDevice, st));
   return 0;
 }
+int64_t IvfLists::packed_bytes() const {
+  int64_t b = 0;
+  for (int l = 0; l < nlist_; l++) {
+    if (h_len_[l] == 0) continue;
+    const int64_t cap = round_up(h_len_[l], 32);
+    b += round_up(cap * code_bytes_ + 16, 256) + round_up(cap * 8, 256);
+  }
+  return b;
+}
+int IvfLists::compact(cudaStream_t st) {
+  const int64_t need = packed_bytes();
+  if (need == 0 || slabs_.empty()) return 0;
+  void* slab = nullptr;
+  if (cudaMalloc(&slab, (size_t)need) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // not enough room to re-pack: keep the current layout
+  }
+  char* cur = static_cast<char*>(slab);
+  for (int l = 0; l < nlist_; l++) {
+    if (h_len_[l] == 0) {
+      h_data_[l] = nullptr, h_ids_[l] = nullptr, h_cap_[l] = 0;
+      continue;
+    }
+    const int64_t cap = round_up(h_len_[l], 32);
+    void* nd = cur;
+    cur += round_up(cap * code_bytes_ + 16, 256);
+    int64_t* ni = reinterpret_cast<int64_t*>(cur);
+    cur += round_up(cap * 8, 256);
+    GB_CUDA(cudaMemcpyAsync(nd, h_data_[l], (size_t)h_len_[l] * code_bytes_, cudaMemcpyDeviceToDevice, st));
+    GB_CUDA(cudaMemcpyAsync(ni, h_ids_[l], (size_t)h_len_[l] * 8, cudaMemcpyDeviceToDevice, st));
+    h_data_[l] = nd, h_ids_[l] = ni, h_cap_[l] = (int)cap;
+  }
+  GB_CUDA(cudaMemcpyAsync(d_data_, h_data_.data(), sizeof(void*) * nlist_, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(d_ids_, h_ids_.data(), sizeof(int64_t*) * nlist_, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaDeviceSynchronize());  // copies done, and no kernel of an earlier search still reads the old slabs
+  for (void* p : slabs_) cudaFree(p);
+  slabs_.assign(1, slab);
+  slab_cur_ = nullptr;
+  slab_left_ = 0;
+  bytes_ = need;
+  return 0;
+}
 int IvfLists::tombstone(int list, int pos, cudaStream_t st) {
   if (list < 0 || list >= nlist_ || pos < 0 || pos >= h_len_[list]) return -1;
   int64_t v;
@@ -795,7 +837,8 @@ int IVFFlatIndex::training_threshold() const {
   return (int)t;
 }
 int64_t IVFFlatIndex::index_mem_bytes() const {
-  return (int64_t)nlist_ * dpad_ * 4 + (lists_ ? lists_->mem_bytes() : 0);
+  const int64_t mirror = mirror_.cap_tiles * (tc_mirror_tile_floats((int)round_up(dpad_, 16)) * 4 + 512);
+  return (int64_t)nlist_ * dpad_ * 4 + (lists_ ? lists_->mem_bytes() : 0) + mirror;
 }
 int IVFFlatIndex::set_centroids(const float* host, int nlist) {
   if (nlist != nlist_) {
@@ -913,7 +956,21 @@ int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
     if (index_batch(x, n, vid0, del_bitmap)) return -1;
     indexed_count_ += n;
   }
+  // a bulk build leaves most of the slab space in regions the lists have outgrown: re-pack once the
+  // waste is worth a copy (more than half of the live bytes and more than 1 GiB)
+  if (lists_ && lists_->mem_bytes() - lists_->packed_bytes() > std::max<int64_t>((int64_t)1 << 30, lists_->packed_bytes() / 2)) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    if (lists_->compact(build_stream_)) return -1;
+  }
   return 0;
+}
+
+int IVFFlatIndex::compact_lists() {
+  std::lock_guard<std::mutex> bg(build_mu_);
+  if (!lists_) return 0;
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  return lists_->compact(build_stream_);
 }
 
 int Index::update_vector(int64_t vid, const float* x) {

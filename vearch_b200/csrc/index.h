@@ -110,6 +110,11 @@ class IvfLists {
   void* list_data(int l) const { return static_cast<char*>(h_data_[l]) + (size_t)h_len_[l] * code_bytes_; }
   int64_t* list_ids(int l) const { return h_ids_[l] + h_len_[l]; }
   int64_t mem_bytes() const { return bytes_; }
+  // bytes the lists would occupy packed tightly; compact() re-packs them into one fresh slab and
+  // frees every old one (copy-on-grow never reuses the regions it leaves behind).  The caller must
+  // exclude concurrent searches; in-flight kernels are drained before the old slabs go.
+  int64_t packed_bytes() const;
+  int compact(cudaStream_t st);
 
  private:
   void* slab_alloc(size_t bytes);
@@ -294,6 +299,9 @@ class IVFFlatIndex : public Index {
                                       const float* coarse_dis, int nprobe, float* out_dis, int64_t* out_ids);
   // gamma's own index files (index_io.cu): <dir>/<abs_name>/{ivfflat,ivfpq}.index.  load: the vector
   // store must already hold the vectors the file indexes; *load_num = IndexModel::Load's load_num
+  // re-pack the inverted lists into one tight slab (IvfLists::compact); also done automatically after
+  // a bulk add_pending when more than half of the slab space is dead
+  int compact_lists();
   int dump_gamma(const std::string& dir, const std::string& abs_name);
   int load_gamma(const std::string& dir, const std::string& abs_name, int64_t* load_num);
 

@@ -282,6 +282,11 @@ int gb_index_get_precomputed_table(gb_index* index, float* table) {
   PQ_OR_FAIL(pq, index);
   return pq->get_precomputed_table(table);
 }
+int gb_index_compact(gb_index* index) {
+  IDX_OR_FAIL(index);
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index->impl);
+  return ivf ? ivf->compact_lists() : 0;
+}
 int gb_index_dump(gb_index* index, const char* dir, const char* abs_name) {
   IDX_OR_FAIL(index);
   if (!dir || !abs_name) return -1;

@@ -232,6 +232,9 @@ class GammaIndex:
                 ids[off[l]:off[l + 1]] = i
         return off, codes, ids
 
+    def compact(self):
+        _check(_lib.lib().gb_index_compact(self._h), "compact")
+
     def dump(self, directory, abs_name):
         """IndexModel::Dump in gamma's own format: <directory>/<abs_name>/{ivfflat,ivfpq}.index."""
         _check(_lib.lib().gb_index_dump(self._h, str(directory).encode(), abs_name.encode()), "dump")
