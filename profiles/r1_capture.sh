@@ -7,6 +7,7 @@ for w in flat_100k ivfflat_1m ivfpq_10m ivfflat_768; do
 done
 GB_LISTMAJOR=0 timeout 400 python bench.py --workload ivfflat_1m --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r1_bench_ivfflat_1m_querymajor.json
 GB_LISTMAJOR=2 timeout 400 python bench.py --workload ivfflat_1m --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r1_bench_ivfflat_1m_densescores.json
+GB_TC_MIRROR=0 timeout 400 python bench.py --workload ivfflat_1m --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r1_bench_ivfflat_1m_regstaged.json
 for w in ivfflat_1m ivfpq_10m; do
   timeout 600 python bench.py --workload $w --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > gpurun_out/r1_bench_reference_$w.json
 done

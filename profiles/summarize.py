@@ -67,5 +67,31 @@ def full(path):
                 print(f"{k:80s} {vals[i]:>18s} {units[i]}")
 
 
+def traffic(out_path):
+    """profiles/r1_traffic.json: DRAM bytes per launch of each dominant kernel, read back from the
+    committed full-capture summaries (bench.py copies the figure into roofline.traffic)."""
+    import json
+    import os
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+
+    def dram(name):
+        t = open(os.path.join(here, name)).read()
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(key + r"\s+([0-9.]+) (\w+)", t)
+            tot += float(m.group(1)) * scale[m.group(2)]
+        return tot
+
+    out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures "
+                       "summarised in this directory (profiles/r1_capture.sh)",
+           "ivfpq_scan_kernel": dram("r1_ncu_ivfpq_scan.txt"),
+           "ivf_listmajor_tma_kernel": dram("r1_ncu_ivfflat_listmajor.txt"),
+           "ivfflat_scan_warp_kernel": dram("r1_ncu_ivfflat_scan_querymajor.txt")}
+    json.dump(out, open(out_path, "w"), indent=1)
+    print(out)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
