@@ -608,3 +608,46 @@ def test_ivf_lists_compaction_keeps_results(ivf_state):
     dg, ig = idx.search(s["db"][12500:12501], 1, params={"nprobe": s["nlist"]})
     assert ig[0, 0] == io[0, 0] == 12500 and dg[0, 0] == do[0, 0]
     idx.close()
+
+
+def test_listmajor_mirror_survives_concurrent_adds_and_searches():
+    """Big-batch searches (list-major, TMA kernel over the mirror) from two threads while a third
+    keeps adding vectors: every search must see a consistent index (each probe vector finds itself),
+    and the mirror is rebuilt behind the readers' backs without tearing."""
+    import threading
+    d, nlist, n0 = 64, 8, 8000
+    db = synth.sift_like(n0 + 4000, d, seed=51)
+    cent, _, _ = orc.kmeans(db[:3000], nlist, niter=4)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": nlist, "metric_type": "L2"})
+    idx.set_centroids(cent)
+    idx.add_vectors(db[:n0])
+    idx.add_pending()
+    errs, stop = [], threading.Event()
+
+    def searcher(seed):
+        rng = np.random.default_rng(seed)
+        try:
+            while not stop.is_set():
+                pick = rng.integers(0, n0, 300)
+                dg, ig = idx.search(db[pick], 1, params={"nprobe": nlist})
+                assert idx.last_scan_kernel.startswith("ivf_listmajor")
+                ok = (dg[:, 0] == 0) & (np.all(db[ig[:, 0]] == db[pick], axis=1))
+                assert ok.all()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=searcher, args=(s,)) for s in (1, 2)]
+    for t in ts:
+        t.start()
+    try:
+        for a in range(n0, n0 + 4000, 250):
+            idx.add_vectors(db[a:a + 250])
+            idx.add_pending()
+    finally:
+        stop.set()
+        for t in ts:
+            t.join()
+    assert not errs, errs[:1]
+    dg, ig = idx.search(db[n0 + 3000:n0 + 3300], 1, params={"nprobe": nlist})
+    assert np.all(dg[:, 0] == 0) and np.all(np.all(db[ig[:, 0]] == db[n0 + 3000:n0 + 3300], axis=1))
+    idx.close()

@@ -4,13 +4,16 @@
 //    gamma_index_ivfpq.cc:595) and point x centroid (k-means assign, faiss Clustering via
 //    gamma_index_ivfflat.cc:407 / gamma_index_ivfpq.cc:372).  faiss itself evaluates this
 //    contraction as sgemm + norms (IndexFlat, >= 20 queries).
-//  * K3 list-major  ivf_listmajor_tc_kernel: when many queries of a batch probe the same list the
-//    IVF-Flat scan (gamma_index_ivfflat.cc:579-787) IS a dense contraction: the (query, probe) pairs
-//    are grouped by list on the host, one CTA multiplies a 128-query group by a 128-row list tile
-//    and writes the 128 x 128 scores into per-(query, probe) score segments; a segment-select
-//    kernel then applies tombstones / bitmaps / score window and keeps the top-k exactly as
-//    scan_codes does (gamma_index_ivfflat.h:63-91).  The list is read once per 128 queries instead
-//    of once per query.
+//  * K3 list-major: when many queries of a batch probe the same list the IVF-Flat scan
+//    (gamma_index_ivfflat.cc:579-787) IS a dense contraction.  The (query, probe) pairs are grouped by
+//    list on the device (lm_count / lmk_scan / lmk_assign / lmk_items); a work item multiplies a group
+//    of <= 128 pairs by the 128-row tiles of a row segment of the list, so the list is read once per
+//    128 queries instead of once per query, and tombstones / bitmaps / score window / top-k are
+//    applied as scan_codes does (gamma_index_ivfflat.h:63-91).  Four kernels, one algorithm:
+//      ivf_listmajor_tma_kernel   operands arrive by cp.async.bulk from the pre-tiled mirror (default)
+//      ivf_listmajor_pipe_kernel  warp-specialised, operands staged through registers (no mirror)
+//      ivf_listmajor_topk_kernel  the same without warp specialisation (single-chunk rows)
+//      ivf_listmajor_tc_kernel + seg_select_kernel   dense scores + segment select (k > 64)
 //
 // Precision: every operand is split x = hi + lo, hi = the TF32-representable head (low 13 mantissa
 // bits cleared), and three MMAs accumulate hi*hi + hi*lo + lo*hi in fp32 (error-compensated
@@ -19,11 +22,12 @@
 // exact fp32 kernels.  L2 uses |x|^2 + |y|^2 - 2 x.y with both norms accumulated in-kernel from the
 // staged operands (faiss clamps the expanded form at 0; so do we).
 //
-// Operand staging: global loads -> st.shared in the canonical no-swizzle K-major UMMA layout
-// (8-row x 16-byte core matrices; LBO = stride between the two K core matrices of one MMA,
-// SBO = stride between 8-row groups), fence.proxy.async, one elected thread issues the MMAs and
-// commits to an mbarrier.  Thread t stages row t of both operands, so it also owns |x_t|^2 and
-// |y_t|^2.  One 128 x 128 output tile per CTA.
+// Operand layout: canonical no-swizzle K-major UMMA tiles (8-row x 16-byte core matrices; LBO = stride
+// between the two K core matrices of one MMA, SBO = stride between 8-row groups).  Register-staged
+// kernels: global loads -> hi/lo split -> st.shared, fence.proxy.async, one elected thread issues the
+// MMAs and commits to an mbarrier; thread t stages row t of both operands, so it also owns |x_t|^2
+// and |y_t|^2.  TMA kernel: the same tiles already exist in global memory (tc_mirror_build_kernel,
+// lm_stage_queries_kernel) and arrive as 16 KiB bulk copies.
 #include <float.h>
 #include <stdlib.h>
 
