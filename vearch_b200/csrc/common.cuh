@@ -54,6 +54,16 @@ __host__ __device__ __forceinline__ unsigned long long make_key(uint32_t ord, ui
   return ((unsigned long long)ord << 32) | vid;
 }
 
+// float image of the bound: a score can only matter if it is on the good side of it.  The two
+// sentinels (no bound yet / slot without a candidate stream) map to +-inf / NaN so the compare does the right thing.
+template <int METRIC>
+__device__ __forceinline__ float key_bound(unsigned long long tau) {
+  const uint32_t hi = (uint32_t)(tau >> 32);
+  if (METRIC == kMetricL2) return hi >= 0xFF800000u ? __int_as_float(0x7F800000) : ord2f(hi);
+  const uint32_t x = ~hi;
+  return x <= 0x007FFFFFu ? __int_as_float(0xFF800000) : ord2f(x);
+}
+
 // dense LSB-first bitmaps (util/bitmap_manager.h): bit id -> word id>>5, mask 1<<(id&31)
 __device__ __forceinline__ bool bit_test(const uint32_t* __restrict__ bm, uint32_t id) {
   return (__ldg(bm + (id >> 5)) >> (id & 31)) & 1u;

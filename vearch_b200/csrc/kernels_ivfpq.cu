@@ -78,9 +78,10 @@ constexpr int PQ_NT = 256;
 constexpr int PQ_NST = 2;
 constexpr int PQ_MAX_PG = 32;  // probes per CTA
 
-// entries per thread per tile for the vector-load code layouts (MW = M / 4 code words per entry):
-// 16 KiB tiles, two stages in flight; per-tile bookkeeping (barrier, tau reload, fill estimate, refill)
-// is paid once per PT entries
+// entries per thread per tile for the vector-load code layouts (MW = M / 4 code words per entry): per-tile
+// bookkeeping (barrier, tau reload, fill estimate, refill) is paid once per PT entries, while LUT + queue +
+// two code stages must stay within ~52 KiB so that four CTAs share an SM (M = 16: 2 x 256 entries, 8 KiB;
+// 3 x 256 and 4 x 256 entries per tile measured slower: 20.2 / 21.1 ms against 19.7 ms)
 __host__ __device__ constexpr int pq_pt(int MW) { return MW == 2 ? 4 : (MW == 4 ? 2 : (MW == 8 ? 2 : 1)); }
 
 __host__ __device__ inline int pq_tile_entries(int M) {
@@ -136,9 +137,11 @@ __global__ void __launch_bounds__(PQ_NT)
                       unsigned long long* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tile_bytes = tile_e * M;
-  unsigned char* stages = smem_raw;
-  float* lut = reinterpret_cast<float*>(smem_raw + (size_t)PQ_NST * tile_bytes);
+  // the LUT sits at the start of the dynamic window: its shared address is a link-time constant, so
+  // every gather is  LDS [byte_offset + imm]  with no base add
+  float* lut = reinterpret_cast<float*>(smem_raw);
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(lut + M * KSUB);
+  unsigned char* stages = reinterpret_cast<unsigned char*>(buf + SORTN);
   __shared__ __align__(8) uint64_t full_bar[PQ_NST];
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
@@ -229,21 +232,23 @@ __global__ void __launch_bounds__(PQ_NT)
     const int s = gt % PQ_NST;
     mbar_wait(&full_bar[s], (gt / PQ_NST) & 1);
     const unsigned long long tau = s_tau;
-    const uint32_t tau_hi = (uint32_t)(tau >> 32);
+    // score window and the queue's bound folded into one float interval: two compares per entry, the
+    // order-preserving key is only built for entries inside it
+    const float tb = key_bound<METRIC>(tau);
+    const float lo_b = METRIC == kMetricL2 ? f.min_score : fmaxf(tb, f.min_score);
+    const float hi_b = METRIC == kMetricL2 ? fminf(tb, f.max_score) : f.max_score;
     const unsigned char* st = stages + (size_t)s * tile_bytes;
     int pushed = 0;
 
     auto consider = [&](int e, float dis) {
-      bool pred = e < n_e && dis <= f.max_score && dis >= f.min_score;
+      bool pred = e < n_e && dis <= hi_b && dis >= lo_b;
       unsigned long long key = kKeySentinel;
-      uint32_t ord = score2ord<METRIC>(dis);
-      pred = pred && ord <= tau_hi;
       if (pred) {
         int64_t raw = lids[(int64_t)ti * tile_e + e];
         pred = raw >= 0;  // tombstone (gamma_index_ivfpq.h:930)
         uint32_t vid = (uint32_t)raw;
         if (pred) pred = ctx_is_valid(f.del_bits, f.filter_bits, vid);
-        key = make_key(ord, vid);
+        key = make_key(score2ord<METRIC>(dis), vid);
         pred = pred && key < tau;
       }
       cq.push_warp(pred, key);

@@ -331,16 +331,6 @@ __global__ void __launch_bounds__(TC_NT)
 // tau_g[q] carries the best bound any CTA has published for query q: a key is only dropped when it
 // is >= the k-th best of k valid keys of the same query, so the union of the per-pair sets always
 // contains the query's true top-k, whatever the CTA schedule.
-// float image of the bound: a score can only matter if it is on the good side of it.  The two
-// sentinels (no bound yet / thread without a pair) map to +-inf / NaN so the compare does the right thing.
-template <int METRIC>
-__device__ __forceinline__ float lmk_bound(unsigned long long tau) {
-  const uint32_t hi = (uint32_t)(tau >> 32);
-  if (METRIC == kMetricL2) return hi >= 0xFF800000u ? __int_as_float(0x7F800000) : ord2f(hi);
-  const uint32_t x = ~hi;
-  return x <= 0x007FFFFFu ? __int_as_float(0xFF800000) : ord2f(x);
-}
-
 struct LmkState {
   unsigned long long tau;  // admission bound (exclusive)
   int n;                   // keys held, <= k
@@ -415,7 +405,7 @@ __global__ void __launch_bounds__(TC_NT)
   const float* lvecs = dir.vecs[t.list];
   const int64_t* __restrict__ lids = dir.ids[t.list];
   const int row_end = t.row0 + t.nrows;
-  float bound = lmk_bound<METRIC>(st.tau);
+  float bound = key_bound<METRIC>(st.tau);
   for (int r0 = t.row0; r0 < row_end; r0 += TC_N) {
     const float* brow = nullptr;
     uint32_t myvid = kLmkNoVid;  // validity of row r0 + tid, resolved while the tile is being multiplied
@@ -437,7 +427,7 @@ __global__ void __launch_bounds__(TC_NT)
         const float s = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[c0 + jj]);
         if (METRIC == kMetricL2 ? s <= bound : s >= bound) {
           st = lmk_consider<METRIC>(hk, k, s_vid[c0 + jj], s, f.min_score, f.max_score, st);
-          bound = lmk_bound<METRIC>(st.tau);
+          bound = key_bound<METRIC>(st.tau);
         }
       }
     }
@@ -446,7 +436,7 @@ __global__ void __launch_bounds__(TC_NT)
       const unsigned long long tg = __ldcg(tau_g + q);
       if (tg < st.tau) {
         st.tau = tg;
-        bound = lmk_bound<METRIC>(st.tau);
+        bound = key_bound<METRIC>(st.tau);
       } else if (st.tau < tg) {
         atomicMin(tau_g + q, st.tau);
       }
@@ -536,7 +526,7 @@ __global__ void __launch_bounds__(LW_NT, 2)
       q = (int)(j / nprobe);
       st.tau = __ldcg(tau_g + q);
     }
-    float bound = lmk_bound<METRIC>(st.tau);
+    float bound = key_bound<METRIC>(st.tau);
     float xn = 0.f;
     for (int i = 0; i < ntiles; i++) {
       const int b = i & 1;
@@ -567,7 +557,7 @@ __global__ void __launch_bounds__(LW_NT, 2)
             if (hit & (1u << jj))
               st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
           }
-          bound = lmk_bound<METRIC>(st.tau);
+          bound = key_bound<METRIC>(st.tau);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -576,7 +566,7 @@ __global__ void __launch_bounds__(LW_NT, 2)
         const unsigned long long tg = __ldcg(tau_g + q);
         if (tg < st.tau) {
           st.tau = tg;
-          bound = lmk_bound<METRIC>(st.tau);
+          bound = key_bound<METRIC>(st.tau);
         } else if (st.tau < tg) {
           atomicMin(tau_g + q, st.tau);
         }
@@ -803,7 +793,7 @@ __global__ void __launch_bounds__(LT_NT, 2)
       q = (int)(j / nprobe);
       st.tau = __ldcg(tau_g + q);
     }
-    float bound = lmk_bound<METRIC>(st.tau);
+    float bound = key_bound<METRIC>(st.tau);
     const float xn = a_norms[(int64_t)t.grp * TC_M + tid];
     const int64_t* __restrict__ lids = dir.ids[t.list];
     for (int i = 0; i < ntiles; i++) {
@@ -845,7 +835,7 @@ __global__ void __launch_bounds__(LT_NT, 2)
             if (hit & (1u << jj))
               st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
           }
-          bound = lmk_bound<METRIC>(st.tau);
+          bound = key_bound<METRIC>(st.tau);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -854,7 +844,7 @@ __global__ void __launch_bounds__(LT_NT, 2)
         const unsigned long long tg = __ldcg(tau_g + q);
         if (tg < st.tau) {
           st.tau = tg;
-          bound = lmk_bound<METRIC>(st.tau);
+          bound = key_bound<METRIC>(st.tau);
         } else if (st.tau < tg) {
           atomicMin(tau_g + q, st.tau);
         }
