@@ -38,15 +38,21 @@ def build_pool():
     msg("VectorQuery", [("name", 1, F.TYPE_STRING, OPT, None), ("value", 2, F.TYPE_BYTES, OPT, None),
                         ("min_score", 3, F.TYPE_DOUBLE, OPT, None), ("max_score", 4, F.TYPE_DOUBLE, OPT, None),
                         ("format", 5, F.TYPE_STRING, OPT, None), ("index_type", 6, F.TYPE_STRING, OPT, None)])
-    msg("RangeFilter", [("field", 1, F.TYPE_STRING, OPT, None), ("lower_value", 2, F.TYPE_BYTES, OPT, None)])
+    msg("RangeFilter", [("field", 1, F.TYPE_STRING, OPT, None), ("lower_value", 2, F.TYPE_BYTES, OPT, None),
+                        ("upper_value", 3, F.TYPE_BYTES, OPT, None), ("include_lower", 4, F.TYPE_BOOL, OPT, None),
+                        ("include_upper", 5, F.TYPE_BOOL, OPT, None), ("is_union", 6, F.TYPE_INT32, OPT, None)])
+    msg("TermFilter", [("field", 1, F.TYPE_STRING, OPT, None), ("value", 2, F.TYPE_BYTES, OPT, None),
+                       ("is_union", 3, F.TYPE_INT32, OPT, None)])
     msg("SearchRequest", [("head", 1, F.TYPE_MESSAGE, OPT, ".vearchpb.RequestHead"), ("req_num", 2, F.TYPE_INT32, OPT, None),
                           ("topN", 3, F.TYPE_INT32, OPT, None), ("is_brute_search", 4, F.TYPE_INT32, OPT, None),
                           ("vec_fields", 5, F.TYPE_MESSAGE, REP, ".vearchpb.VectorQuery"),
                           ("fields", 6, F.TYPE_STRING, REP, None),
                           ("range_filters", 7, F.TYPE_MESSAGE, REP, ".vearchpb.RangeFilter"),
+                          ("term_filters", 8, F.TYPE_MESSAGE, REP, ".vearchpb.TermFilter"),
                           ("index_params", 9, F.TYPE_STRING, OPT, None), ("multi_vector_rank", 10, F.TYPE_INT32, OPT, None),
                           ("l2_sqrt", 11, F.TYPE_BOOL, OPT, None), ("ranker", 15, F.TYPE_STRING, OPT, None),
-                          ("trace", 16, F.TYPE_BOOL, OPT, None), ("offset", 20, F.TYPE_INT32, OPT, None),
+                          ("trace", 16, F.TYPE_BOOL, OPT, None), ("operator", 17, F.TYPE_INT32, OPT, None),
+                          ("offset", 20, F.TYPE_INT32, OPT, None),
                           ("partition_names", 22, F.TYPE_STRING, REP, None)])
     msg("Field", [("name", 1, F.TYPE_STRING, OPT, None), ("type", 2, F.TYPE_INT32, OPT, None),
                   ("value", 3, F.TYPE_BYTES, OPT, None)])

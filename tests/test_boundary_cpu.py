@@ -96,6 +96,35 @@ def test_python_encoder_matches_official_parser():
     assert rc == 0 and got["request_id"] == "r1" and got["partition_id"] == 3 and got["vec_fields"][0]["value_len"] == 96
 
 
+def test_scalar_filters_cross_the_wire_like_the_official_runtime():
+    """RangeFilter / TermFilter / operator (router_grpc.proto:109-122, 185): the hand-written encoder
+    produces what the official protobuf runtime parses, and the C++ reader recovers every field."""
+    import struct
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_golden
+    cls = gen_golden.classes()
+    q = np.arange(8, dtype=np.float32).reshape(1, 8)
+    lo, hi = struct.pack("<i", -5), struct.pack("<i", 70000)
+    mine = wire.encode_search_request("emb", q, 5, range_filters=[("price", lo, hi, True, False), ("stock", lo, b"", False, False, 2)],
+                                      term_filters=[("tag", b"a\x01b", 1), ("color", b"red")], operator=1)
+    m = cls["SearchRequest"]()
+    m.ParseFromString(mine)
+    assert [(r.field, r.lower_value, r.upper_value, r.include_lower, r.include_upper, r.is_union) for r in m.range_filters] == \
+        [("price", lo, hi, True, False, 0), ("stock", lo, b"", False, False, 2)]
+    assert [(t.field, t.value, t.is_union) for t in m.term_filters] == [("tag", b"a\x01b", 1), ("color", b"red", 0)]
+    assert m.operator == 1
+    for raw in (mine, m.SerializeToString()):
+        rc, out = _call_json(_lib.lib().gb_debug_parse_search_request, raw)
+        got = json.loads(out)
+        assert rc == 0 and got["filter_operator"] == 1 and got["n_range_filters"] == 2 and got["n_term_filters"] == 2
+        assert got["filters"] == [
+            dict(field="price", lower=lo.hex(), upper=hi.hex(), include_lower=True, include_upper=False, is_term=False, is_union=0),
+            dict(field="stock", lower=lo.hex(), upper="", include_lower=False, include_upper=False, is_term=False, is_union=2),
+            dict(field="tag", lower=b"a\x01b".hex(), upper="", include_lower=False, include_upper=False, is_term=True, is_union=1),
+            dict(field="color", lower=b"red".hex(), upper="", include_lower=False, include_upper=False, is_term=True, is_union=0)]
+
+
 def test_cpp_response_bytes_equal_official_serializer():
     exp = json.load(open(os.path.join(GOLD, "search_response.json")))
     official = open(os.path.join(GOLD, "search_response.bin"), "rb").read()

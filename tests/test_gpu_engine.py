@@ -299,3 +299,62 @@ def test_concurrent_search_while_adding(tmp_path, data):
     res = keys_of(e.search(db[3999:4000], 1, index_params={"nprobe": 16}))
     assert res == [["doc3999"]]
     e.close()
+
+
+def test_scalar_filters_restrict_the_candidate_set(tmp_path, data):
+    """range / term filters (search/engine.cc:349-366, table/scalar_index_manager.cc:294-345, 588-651):
+    the engine turns them into the dense docid bitmap every scan kernel applies before selection, so a
+    filtered search is the exact search over the surviving documents."""
+    import struct
+    db, xq = data
+    n = 3000
+    e = eng_mod().GammaEngine(str(tmp_path), space_name="ts")
+    e.create_table("ts", D, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 1000},
+                   fields=(("_id", wire.DT_STRING, False), ("price", wire.DT_INT, True), ("tag", wire.DT_STRING, True),
+                           ("cats", wire.DT_STRINGARRAY, True), ("plain", wire.DT_INT, False)))
+    price = (np.arange(n) * 37) % 1000
+    tags = np.array([f"t{i % 7}" for i in range(n)])
+    for i in range(n):
+        cats = f"c{i % 5}\x01c{(i // 5) % 11}".encode()
+        assert e.add_doc(f"doc{i}", db[i], extra_fields=[("price", struct.pack("<i", int(price[i])), wire.DT_INT),
+                                                          ("tag", tags[i].encode(), wire.DT_STRING),
+                                                          ("cats", cats, wire.DT_STRINGARRAY),
+                                                          ("plain", struct.pack("<i", i), wire.DT_INT)]) == 0
+    e.wait_indexed(n)
+    e.delete_doc("doc7")
+    alive = np.ones(n, bool)
+    alive[7] = False
+
+    def check(mask, **kw):
+        res = e.search(xq, 5, index_params={"nprobe": 16}, **kw)
+        fb = np.packbits(mask & alive, bitorder="little")
+        do, io = orc.flat_search(db[:n], xq, 5, L2, filter_bitmap=fb)
+        assert keys_of(res) == [[f"doc{i}" for i in row if i >= 0] for row in io]
+        assert scores_of(res) == [[float(s) for s, i in zip(drow, irow) if i >= 0] for drow, irow in zip(do, io)]
+
+    i32 = lambda v: struct.pack("<i", v)
+    check((price >= 100) & (price < 300), range_filters=[("price", i32(100), i32(300), True, False)])
+    check(price > 900, range_filters=[("price", i32(900), b"", False, False)])
+    check(price <= 36, range_filters=[("price", b"", i32(36), False, True)])
+    check(price == 370, range_filters=[("price", i32(370), i32(370), True, True)])
+    check(price != 370, range_filters=[("price", i32(370), i32(370), True, True, 2)])
+    check((tags == "t1") | (tags == "t4"), term_filters=[("tag", b"t1\x01t4")])
+    check(~((tags == "t1") | (tags == "t4")), term_filters=[("tag", b"t1\x01t4", 2)])
+    cats_hit = np.array([(i % 5 == 2) or ((i // 5) % 11 == 9) for i in range(n)])
+    check(cats_hit, term_filters=[("cats", b"c2\x01c9")])
+    both = (price < 500) & (tags == "t3")
+    check(both, range_filters=[("price", b"", i32(500), False, False)], term_filters=[("tag", b"t3")])
+    check((price < 50) | (tags == "t3"), range_filters=[("price", b"", i32(50), False, False)], term_filters=[("tag", b"t3")],
+          operator=1)
+    # nothing survives / the field has no scalar index: req_num empty results, not an error
+    for kw in (dict(range_filters=[("price", i32(5000), b"", True, False)]),
+               dict(range_filters=[("plain", i32(5), b"", True, False)]),
+               dict(term_filters=[("nofield", b"x")])):
+        res = e.search(xq, 5, **kw)
+        assert len(res) == NQ and all(r["items"] == [] and "no result" in r["msg"] for r in res)
+    # brute-force path (FLAT kernel) honours the same bitmap
+    res = e.search(xq, 5, is_brute_search=1, range_filters=[("price", i32(100), i32(300), True, False)])
+    fb = np.packbits((price >= 100) & (price < 300) & alive, bitorder="little")
+    _, io = orc.flat_search(db[:n], xq, 5, L2, filter_bitmap=fb)
+    assert keys_of(res) == [[f"doc{i}" for i in row] for row in io]
+    e.close()

@@ -83,14 +83,37 @@ bool SearchRequestPB::parse(const uint8_t* data, size_t len) {
       case 6:
         if (f.wire == 2) fields.emplace_back(reinterpret_cast<const char*>(f.data), f.len);
         break;
-      case 7: n_range_filters++; break;
-      case 8: n_term_filters++; break;
+      case 7:
+      case 8: {
+        if (f.wire != 2) break;
+        Filter fl;
+        fl.is_term = f.num == 8;
+        (fl.is_term ? n_term_filters : n_range_filters)++;
+        PbReader v(f.data, f.len);
+        PbField vf;
+        while (v.next(&vf)) {
+          if (vf.num == 1 && vf.wire == 2) fl.field.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+          if (vf.num == 2 && vf.wire == 2) fl.lower.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+          if (fl.is_term) {
+            if (vf.num == 3 && vf.wire == 0) fl.is_union = (int)vf.val;
+          } else {
+            if (vf.num == 3 && vf.wire == 2) fl.upper.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+            if (vf.num == 4 && vf.wire == 0) fl.include_lower = vf.val != 0;
+            if (vf.num == 5 && vf.wire == 0) fl.include_upper = vf.val != 0;
+            if (vf.num == 6 && vf.wire == 0) fl.is_union = (int)vf.val;
+          }
+        }
+        if (v.error()) return false;
+        filters.push_back(std::move(fl));
+        break;
+      }
       case 9:
         if (f.wire == 2) index_params.assign(reinterpret_cast<const char*>(f.data), f.len);
         break;
       case 10: multi_vector_rank = (int)f.val; break;
       case 11: l2_sqrt = f.val != 0; break;
       case 16: trace = f.val != 0; break;
+      case 17: filter_operator = (int)f.val; break;
       case 20: offset = (int)f.val; break;
       default: break;  // unknown / unused fields are skipped
     }
@@ -142,14 +165,14 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
   bool has_id = false;
   for (size_t i = 0; i < t.vec_len(1); i++) {
     FbTable f = t.vec_table(1, i);
-    FieldDef fd{f.str(0), (int)f.scalar<int8_t>(1, 0)};
+    FieldDef fd{f.str(0), (int)f.scalar<int8_t>(1, 0), f.scalar<uint8_t>(2, 0) != 0};
     if (fd.name == "_id") has_id = true;
     field_idx_[fd.name] = (int)fields_.size();
     fields_.push_back(fd);
   }
   if (!has_id) {  // the key field always exists (table/table.cc)
     field_idx_["_id"] = (int)fields_.size();
-    fields_.push_back({"_id", DT_STRING});
+    fields_.push_back({"_id", DT_STRING, false});
   }
   values_.assign(fields_.size(), {});
   size_t nvec = t.vec_len(2);
@@ -371,14 +394,112 @@ int Engine::GetDocByDocid(int docid, bool next, std::string* fb_out) {
   return 0;
 }
 
+// ---- scalar filters ------------------------------------------------------------------------------
+// Filter() semantics per field type (table/scalar_index_manager.cc:294-345):
+//   numeric: lower == upper -> Equal (NotEqual when is_union == Not); only one bound -> <, <=, >, >=;
+//            both -> Range with the include flags.  Values are the field type's raw little-endian bytes.
+//   string / string array: lower_value split at \001 -> In (NotIn when is_union == Not); a string-array
+//            document matches when any of its \001-separated elements does.
+// Search(): the per-filter sets are intersected (operator And) or united (Or).  A filter on a field
+// without a scalar index, or an empty result, means "no result" (scalar_index_manager.cc:598-610).
+namespace {
+template <typename T>
+int cmp_num(const std::string& a, const std::string& b) {
+  T x, y;
+  memcpy(&x, a.data(), sizeof(T));
+  memcpy(&y, b.data(), sizeof(T));
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+// -2: not comparable (wrong width)
+int cmp_typed(int dt, const std::string& a, const std::string& b) {
+  size_t w = (dt == DT_INT || dt == DT_FLOAT) ? 4 : (dt == DT_BOOL ? 1 : 8);
+  if (a.size() != w || b.size() != w) return -2;
+  switch (dt) {
+    case DT_INT: return cmp_num<int32_t>(a, b);
+    case DT_FLOAT: return cmp_num<float>(a, b);
+    case DT_DOUBLE: return cmp_num<double>(a, b);
+    case DT_BOOL: return cmp_num<uint8_t>(a, b);
+    default: return cmp_num<int64_t>(a, b);  // DT_LONG, DT_DATE
+  }
+}
+std::vector<std::string> split001(const std::string& s) {
+  std::vector<std::string> out;
+  size_t a = 0;
+  while (true) {
+    size_t b = s.find('\001', a);
+    out.push_back(s.substr(a, b == std::string::npos ? std::string::npos : b - a));
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  return out;
+}
+}  // namespace
+
+int64_t Engine::eval_filters(const SearchRequestPB& req, std::vector<uint8_t>* bitmap) const {
+  const int n = max_docid_;
+  bitmap->assign((size_t)(n >> 3) + 1, 0);
+  std::vector<uint8_t> cur((size_t)(n >> 3) + 1);
+  bool first = true;
+  for (const auto& fl : req.filters) {
+    auto it = field_idx_.find(fl.field);
+    if (it == field_idx_.end() || !fields_[it->second].indexed) return 0;
+    const int fi = it->second, dt = fields_[fi].data_type;
+    const bool is_str = dt == DT_STRING || dt == DT_STRINGARRAY;
+    if (fl.lower.empty() && (is_str || fl.upper.empty())) continue;  // Filter() returns an untouched result
+    std::fill(cur.begin(), cur.end(), 0);
+    const bool neg = fl.is_union == 2;
+    std::vector<std::string> items;
+    if (is_str) items = split001(fl.lower);
+    for (int d = 0; d < n; d++) {
+      const std::string& v = values_[fi][d];
+      bool hit;
+      if (is_str) {
+        bool in = false;
+        if (dt == DT_STRINGARRAY) {
+          for (const auto& e : split001(v))
+            if (std::find(items.begin(), items.end(), e) != items.end()) in = true;
+        } else {
+          in = std::find(items.begin(), items.end(), v) != items.end();
+        }
+        hit = neg ? !in : in;
+      } else if (fl.lower == fl.upper) {
+        const int c = cmp_typed(dt, v, fl.lower);
+        hit = c != -2 && (neg ? c != 0 : c == 0);
+      } else {
+        hit = true;
+        if (!fl.lower.empty()) {
+          const int c = cmp_typed(dt, v, fl.lower);
+          hit = c != -2 && (c > 0 || (c == 0 && fl.include_lower));
+        }
+        if (hit && !fl.upper.empty()) {
+          const int c = cmp_typed(dt, v, fl.upper);
+          hit = c != -2 && (c < 0 || (c == 0 && fl.include_upper));
+        }
+      }
+      if (hit) cur[d >> 3] |= (uint8_t)(1u << (d & 7));
+    }
+    if (first) {
+      bitmap->swap(cur);
+      cur.resize(bitmap->size());
+      first = false;
+    } else if (req.filter_operator == 0) {
+      for (size_t i = 0; i < cur.size(); i++) (*bitmap)[i] &= cur[i];
+    } else if (req.filter_operator == 1) {
+      for (size_t i = 0; i < cur.size(); i++) (*bitmap)[i] |= cur[i];
+    }
+  }
+  if (first) return 0;
+  int64_t card = 0;
+  for (uint8_t b : *bitmap) card += __builtin_popcount(b);
+  return card;
+}
+
 // Engine::Search (search/engine.cc:242-402) + VectorManager::Search (vector_manager.cc:739-1079)
 // + Response::Serialize (response.cc:46-185)
 Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
   if (req.req_num <= 0) return Status::Make(kInvalidArgument, space_name_ + " req_num should not less than 0");
   if (req.topn <= 0) return Status::Make(kInvalidArgument, "limit[topN] is zero");
-  if (req.n_range_filters || req.n_term_filters)
-    return Status::Make(kNotSupported, "scalar filters are not supported by the B200 engine yet");
   if (req.vec_fields.size() != 1)
     return Status::Make(req.vec_fields.empty() ? kInvalidArgument : kNotSupported,
                         req.vec_fields.empty() ? "no vector query" : "multi-vector queries are not supported yet");
@@ -410,7 +531,7 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   memcpy(x.data(), vq.value.data(), x.size() * 4);
   std::vector<float> dis((size_t)n * topN);
   std::vector<int64_t> ids((size_t)n * topN);
-  std::vector<uint8_t> bm;
+  std::vector<uint8_t> bm, fbm;
   int total_docs;
   {
     std::unique_lock<std::shared_mutex> wl(mu_, std::defer_lock);
@@ -429,6 +550,23 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
       ctx.bitmap_bits = max_docid_;
     }
     total_docs = doc_num();
+    if (!req.filters.empty()) {  // ScalarIndexQuery (search/engine.cc:349-366, 525-580)
+      if (eval_filters(req, &fbm) == 0) {
+        PbWriter resp;
+        for (int i = 0; i < req.req_num; i++) {
+          PbWriter sr, st;
+          st.put_int32(1, 0);
+          st.put_int32(3, 0);
+          sr.put_message(5, st.out);
+          sr.put_string(6, space_name_ + " no result: numeric filter return 0 result");
+          resp.put_message(2, sr.out);
+        }
+        *pb_out = resp.out;
+        return Status::OK();
+      }
+      ctx.filter_bitmap = fbm.data();
+      ctx.bitmap_bits = max_docid_;
+    }
   }
   int rc = index_->search(ctx, n, x.data(), topN, dis.data(), ids.data());
   if (rc == -2 || IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");

@@ -56,6 +56,15 @@ struct SearchRequestPB {  // c_api/api_data/request.{h,cc}
   };
   std::vector<VecQuery> vec_fields;
   std::vector<std::string> fields;
+  // RangeFilter / TermFilter (router_grpc.proto:109-122): a term filter is a range filter that only
+  // carries lower_value (search/engine.cc:551-559)
+  struct Filter {
+    std::string field, lower, upper;
+    bool include_lower = false, include_upper = false, is_term = false;
+    int is_union = 0;  // FilterOperator: 0 And, 1 Or, 2 Not (table/scalar_index_utils.h:31)
+  };
+  std::vector<Filter> filters;
+  int filter_operator = 0;  // SearchRequest.operator: how the filters combine
   int n_range_filters = 0, n_term_filters = 0;
   std::string index_params;
   int multi_vector_rank = 0;
@@ -105,7 +114,11 @@ class Engine {
   struct FieldDef {
     std::string name;
     int data_type;
+    bool indexed = false;  // FieldInfo.is_index: only indexed fields can be filtered on
   };
+  // ScalarIndexManager::Search (table/scalar_index_manager.cc:294-345, 588-651) as a scan of the
+  // in-memory columns: dense LSB-first bitmap of the docids that pass; returns the cardinality
+  int64_t eval_filters(const SearchRequestPB& req, std::vector<uint8_t>* bitmap) const;
   std::vector<FieldDef> fields_;
   std::unordered_map<std::string, int> field_idx_;
   std::vector<std::vector<std::string>> values_;  // [field][docid]

@@ -184,6 +184,12 @@ void DeleteKillStatus(const char* request_id, int partition_id) {
 #include "wire.h"
 
 static std::string hex_escape(const std::string& s) { return gb::json_escape(s); }
+static std::string to_hex(const std::string& s) {
+  static const char* d = "0123456789abcdef";
+  std::string o;
+  for (unsigned char c : s) o += d[c >> 4], o += d[c & 15];
+  return o;
+}
 
 extern "C" {
 
@@ -204,6 +210,16 @@ int gb_debug_parse_search_request(const char* buf, int len, char** json_out, int
   j += ",\"offset\":" + std::to_string(r.offset);
   j += ",\"n_range_filters\":" + std::to_string(r.n_range_filters);
   j += ",\"n_term_filters\":" + std::to_string(r.n_term_filters);
+  j += ",\"filter_operator\":" + std::to_string(r.filter_operator);
+  j += ",\"filters\":[";
+  for (size_t i = 0; i < r.filters.size(); i++) {
+    auto& fl = r.filters[i];
+    j += std::string(i ? "," : "") + "{\"field\":\"" + hex_escape(fl.field) + "\",\"lower\":\"" + to_hex(fl.lower) +
+         "\",\"upper\":\"" + to_hex(fl.upper) + "\",\"include_lower\":" + (fl.include_lower ? "true" : "false") +
+         ",\"include_upper\":" + (fl.include_upper ? "true" : "false") + ",\"is_term\":" + (fl.is_term ? "true" : "false") +
+         ",\"is_union\":" + std::to_string(fl.is_union) + "}";
+  }
+  j += "]";
   j += ",\"fields\":[";
   for (size_t i = 0; i < r.fields.size(); i++) j += (i ? ",\"" : "\"") + hex_escape(r.fields[i]) + "\"";
   j += "],\"vec_fields\":[";

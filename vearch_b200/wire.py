@@ -249,8 +249,11 @@ def _ld(num, payload):
 
 
 def encode_search_request(vec_name, queries, topn, index_params="", is_brute_search=0, fields=("_id",), request_id="",
-                          partition_id=None, min_score=None, max_score=None, offset=0, trace=False, req_num=None):
-    """vearchpb.SearchRequest (internal/proto/router_grpc.proto:168-191). queries: float32 ndarray [nq, d]."""
+                          partition_id=None, min_score=None, max_score=None, offset=0, trace=False, req_num=None,
+                          range_filters=(), term_filters=(), operator=0):
+    """vearchpb.SearchRequest (internal/proto/router_grpc.proto:168-191). queries: float32 ndarray [nq, d].
+    range_filters: (field, lower_bytes, upper_bytes, include_lower, include_upper[, is_union]);
+    term_filters: (field, value_bytes[, is_union]); operator: 0 And / 1 Or between the filters."""
     import numpy as np
     q = np.ascontiguousarray(queries, dtype=np.float32)
     out = bytearray()
@@ -277,10 +280,31 @@ def encode_search_request(vec_name, queries, topn, index_params="", is_brute_sea
     out += _ld(5, vq)
     for f in fields:
         out += _ld(6, f.encode())
+    for rf in range_filters:
+        field, lo, hi, inc_lo, inc_hi = rf[:5]
+        m = _ld(1, field.encode())
+        if lo:
+            m += _ld(2, lo)
+        if hi:
+            m += _ld(3, hi)
+        if inc_lo:
+            m += _key(4, 0) + _varint(1)
+        if inc_hi:
+            m += _key(5, 0) + _varint(1)
+        if len(rf) > 5 and rf[5]:
+            m += _key(6, 0) + _varint(rf[5])
+        out += _ld(7, m)
+    for tf in term_filters:
+        m = _ld(1, tf[0].encode()) + (_ld(2, tf[1]) if tf[1] else b"")
+        if len(tf) > 2 and tf[2]:
+            m += _key(3, 0) + _varint(tf[2])
+        out += _ld(8, m)
     if index_params:
         out += _ld(9, index_params.encode())
     if trace:
         out += _key(16, 0) + _varint(1)
+    if operator:
+        out += _key(17, 0) + _varint(operator)
     if offset:
         out += _key(20, 0) + _varint(offset)
     return bytes(out)
