@@ -358,3 +358,28 @@ def test_scalar_filters_restrict_the_candidate_set(tmp_path, data):
     _, io = orc.flat_search(db[:n], xq, 5, L2, filter_bitmap=fb)
     assert keys_of(res) == [[f"doc{i}" for i in row] for row in io]
     e.close()
+
+
+def test_process_exit_without_close_is_clean(tmp_path):
+    """A partition server that is killed never calls Close: the library's own threads (indexing loop,
+    request coalescer) must be parked before the CUDA runtime unloads, or the process dies in a
+    signal instead of exiting."""
+    import subprocess
+    import sys
+    code = f"""
+import numpy as np
+from vearch_b200 import engine, synth, wire
+e = engine.GammaEngine({str(tmp_path)!r}, space_name="ts")
+e.create_table("ts", 32, "IVFFLAT", {{"ncentroids": 16, "nprobe": 4, "metric_type": "L2", "training_threshold": 1000}},
+               refresh_interval=20)
+db = synth.sift_like(1500, 32, seed=5)
+for i, v in enumerate(db):
+    assert e.add_doc(f"doc{{i}}", v) == 0
+e.wait_indexed(1500)
+assert len(e.search(db[:1], 3)[0]["items"]) == 3   # nq = 1: goes through the coalescer thread
+print("leaving without close", flush=True)
+"""
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert "leaving without close" in p.stdout, p.stderr[-2000:]
+    assert p.returncode == 0, (p.returncode, p.stderr[-2000:])

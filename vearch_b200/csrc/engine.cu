@@ -142,12 +142,40 @@ bool Engine::IsKilled(const std::string& request_id, int partition_id) {
 Engine::Engine(const std::string& path, const std::string& space_name, int device)
     : path_(path), space_name_(space_name), device_(device) {}
 
-Engine::~Engine() {
-  // Close: stop the indexing thread (search/engine.cc Engine::~Engine / Close)
+namespace {
+struct LiveEngines {
+  std::mutex mu;
+  std::vector<Engine*> all;
+};
+LiveEngines& live_engines() {
+  static LiveEngines* s = new LiveEngines;  // leaked on purpose
+  return *s;
+}
+void quiesce_all_engines() {
+  std::vector<Engine*> v;
+  {
+    std::lock_guard<std::mutex> g(live_engines().mu);
+    v = live_engines().all;
+  }
+  for (Engine* e : v) e->quiesce();
+}
+}  // namespace
+
+void Engine::quiesce() {
   int st = indexing_state_.load();
   if (st != 0) indexing_state_.store(3);
   idx_cv_.notify_all();
   if (indexing_thread_.joinable()) indexing_thread_.join();
+}
+
+Engine::~Engine() {
+  // Close: stop the indexing thread (search/engine.cc Engine::~Engine / Close)
+  {
+    std::lock_guard<std::mutex> g(live_engines().mu);
+    auto& a = live_engines().all;
+    a.erase(std::remove(a.begin(), a.end(), this), a.end());
+  }
+  quiesce();
   cudaSetDevice(device_);
   index_.reset();
 }
@@ -218,6 +246,12 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
                                     : kNotSupported,
                                 last_error());
   index_.reset(idx);
+  {  // registered after the index (and so after CUDA start-up): at exit the engine's thread stops first
+    std::lock_guard<std::mutex> g(live_engines().mu);
+    static bool hooked = (atexit(quiesce_all_engines), true);
+    (void)hooked;
+    live_engines().all.push_back(this);
+  }
   if (training_threshold_ <= 0) training_threshold_ = index_->training_threshold();
   created_table_ = true;
   // <path>/<table>.schema, as the reference writes it (engine.cc:676-684)

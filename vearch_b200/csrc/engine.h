@@ -93,6 +93,7 @@ class Engine {
   int Dump();
   int Load();
   const std::string& space_name() const { return space_name_; }
+  void quiesce();  // stop the indexing thread (also from an atexit hook for engines never Closed)
 
   // cooperative cancellation (c_api/api_data/request_context.h:51-88)
   static void SetKill(const std::string& request_id, int partition_id, int reason);

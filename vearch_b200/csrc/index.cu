@@ -315,6 +315,25 @@ int IvfLists::download_list(int l, std::vector<uint8_t>* codes, std::vector<int6
 }
 
 // ------------------------------------------------------------------------------------------
+namespace {
+struct LiveIndexes {
+  std::mutex mu;
+  std::vector<Index*> all;
+};
+LiveIndexes& live_indexes() {
+  static LiveIndexes* s = new LiveIndexes;  // leaked on purpose: must outlive every static destructor
+  return *s;
+}
+void quiesce_all_indexes() {
+  std::vector<Index*> v;
+  {
+    std::lock_guard<std::mutex> g(live_indexes().mu);
+    v = live_indexes().all;
+  }
+  for (Index* i : v) i->quiesce();
+}
+}  // namespace
+
 Index::Index(const std::string& type, int d, const ModelParams& mp, int device, int seg_shift)
     : type_(type), d_(d), dpad_((int)round_up(d, 4)), device_(device), mp_(mp) {
   cudaSetDevice(device_);
@@ -323,16 +342,31 @@ Index::Index(const std::string& type, int d, const ModelParams& mp, int device, 
     uint64_t thr = UINT64_MAX;  // keep scratch memory cached between searches
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  {  // the CUDA runtime is initialised by now, so this hook runs before its teardown
+    std::lock_guard<std::mutex> g(live_indexes().mu);
+    static bool hooked = (atexit(quiesce_all_indexes), true);
+    (void)hooked;
+    live_indexes().all.push_back(this);
+  }
   store_.reset(new RawStore(d, seg_shift));
   cudaStreamCreateWithFlags(&build_stream_, cudaStreamNonBlocking);
 }
-Index::~Index() {
+void Index::quiesce() {
   {
     std::lock_guard<std::mutex> lk(co_mu_);
     co_stop_ = true;
   }
   co_cv_.notify_all();
   if (co_thread_.joinable()) co_thread_.join();
+}
+
+Index::~Index() {
+  {
+    std::lock_guard<std::mutex> g(live_indexes().mu);
+    auto& a = live_indexes().all;
+    a.erase(std::remove(a.begin(), a.end(), this), a.end());
+  }
+  quiesce();
   for (auto& b : big_) {
     cudaFree(b.p);
     cudaEventDestroy(b.done);

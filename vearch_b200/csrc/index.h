@@ -192,6 +192,9 @@ class Index {
   int search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
                     int64_t* out_ids_dev, cudaStream_t st);
   virtual int64_t index_mem_bytes() const { return 0; }
+  // stop the background worker (request coalescer); also run from an atexit hook for objects the host
+  // never closed, so no thread of ours is inside the CUDA runtime while it is being torn down
+  void quiesce();
   // device time spent in the dominant scan kernel(s) since the last call (ms), for the bench
   // roofline: CUDA events recorded on the launching stream around the scan launches, read here.
   float last_scan_ms();
