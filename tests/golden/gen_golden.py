@@ -54,6 +54,14 @@ def build_pool():
                           ("trace", 16, F.TYPE_BOOL, OPT, None), ("operator", 17, F.TYPE_INT32, OPT, None),
                           ("offset", 20, F.TYPE_INT32, OPT, None),
                           ("partition_names", 22, F.TYPE_STRING, REP, None)])
+    msg("QueryRequest", [("head", 1, F.TYPE_MESSAGE, OPT, ".vearchpb.RequestHead"),
+                         ("document_ids", 2, F.TYPE_STRING, REP, None), ("partition_id", 3, F.TYPE_INT32, OPT, None),
+                         ("next", 4, F.TYPE_BOOL, OPT, None),
+                         ("range_filters", 5, F.TYPE_MESSAGE, REP, ".vearchpb.RangeFilter"),
+                         ("term_filters", 6, F.TYPE_MESSAGE, REP, ".vearchpb.TermFilter"),
+                         ("fields", 7, F.TYPE_STRING, REP, None), ("is_vector_value", 8, F.TYPE_BOOL, OPT, None),
+                         ("limit", 9, F.TYPE_INT32, OPT, None), ("operator", 15, F.TYPE_INT32, OPT, None),
+                         ("offset", 17, F.TYPE_INT32, OPT, None)])
     msg("Field", [("name", 1, F.TYPE_STRING, OPT, None), ("type", 2, F.TYPE_INT32, OPT, None),
                   ("value", 3, F.TYPE_BYTES, OPT, None)])
     msg("ResultItem", [("score", 1, F.TYPE_DOUBLE, OPT, None), ("fields", 2, F.TYPE_MESSAGE, REP, ".vearchpb.Field"),
@@ -74,7 +82,7 @@ def build_pool():
 def classes():
     pool = build_pool()
     get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("vearchpb." + n))
-    return {n: get(n) for n in ("SearchRequest", "SearchResponse", "VectorQuery", "RequestHead")}
+    return {n: get(n) for n in ("SearchRequest", "SearchResponse", "VectorQuery", "RequestHead", "QueryRequest")}
 
 
 def main():

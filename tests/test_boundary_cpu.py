@@ -125,6 +125,24 @@ def test_scalar_filters_cross_the_wire_like_the_official_runtime():
             dict(field="color", lower=b"red".hex(), upper="", include_lower=False, include_upper=False, is_term=True, is_union=0)]
 
 
+def test_query_request_encoder_matches_official_runtime():
+    import struct
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_golden
+    cls = gen_golden.classes()
+    lo = struct.pack("<q", 7)
+    mine = wire.encode_query_request(document_ids=["a", "b"], partition_id=2, fields=["_id", "tag"], limit=20, operator=1,
+                                     offset=3, range_filters=[("n", lo, b"", True, False)], term_filters=[("tag", b"x", 2)])
+    m = cls["QueryRequest"]()
+    m.ParseFromString(mine)
+    assert list(m.document_ids) == ["a", "b"] and m.partition_id == 2 and list(m.fields) == ["_id", "tag"]
+    assert (m.limit, m.operator, m.offset) == (20, 1, 3)
+    assert [(r.field, r.lower_value, r.include_lower) for r in m.range_filters] == [("n", lo, True)]
+    assert [(t.field, t.value, t.is_union) for t in m.term_filters] == [("tag", b"x", 2)]
+    assert m.SerializeToString() == mine  # same field order as the official serializer
+
+
 def test_cpp_response_bytes_equal_official_serializer():
     exp = json.load(open(os.path.join(GOLD, "search_response.json")))
     official = open(os.path.join(GOLD, "search_response.bin"), "rb").read()

@@ -124,7 +124,7 @@ def test_error_conventions(tmp_path, data):
     with pytest.raises(E.GammaStatusError) as ei:
         e.search_raw(b"\x0a\xff\xff")  # malformed protobuf
     assert ei.value.code == 4
-    assert e.query_status() == 3  # Query: kNotSupported
+    assert e.query()["items"] == []  # Query without ids or filters: one empty result (engine.cc:443-521)
     # FLAT, few docs, not "indexed": allowed because max_docid <= 100 (brute_force_search_threshold)
     res = e.search(xq[:1], 5)
     assert keys_of(res) == [["a"]] or keys_of(res) == [["a"]]
@@ -383,3 +383,32 @@ print("leaving without close", flush=True)
     p = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert "leaving without close" in p.stdout, p.stderr[-2000:]
     assert p.returncode == 0, (p.returncode, p.stderr[-2000:])
+
+
+def test_query_by_ids_and_by_filters(tmp_path, data):
+    """Query (search/engine.cc:404-523): by key, by docid (partition_id > 0), by scalar filters with
+    limit / offset; deleted documents never come back."""
+    import struct
+    db, _ = data
+    e = eng_mod().GammaEngine(str(tmp_path), space_name="ts")
+    e.create_table("ts", D, "FLAT", {"metric_type": "L2"},
+                   fields=(("_id", wire.DT_STRING, False), ("n", wire.DT_LONG, True), ("tag", wire.DT_STRING, True)))
+    for i in range(200):
+        assert e.add_doc(f"doc{i}", db[i], extra_fields=[("n", struct.pack("<q", i * 3), wire.DT_LONG),
+                                                          ("tag", f"t{i % 4}".encode(), wire.DT_STRING)]) == 0
+    e.delete_doc("doc9")
+    r = e.query(document_ids=["doc5", "nope", "doc9", "doc7"], fields=["_id", "n"])
+    assert [it["fields"]["_id"] for it in r["items"]] == [b"doc5", b"doc7"] and r["total"] == 2
+    assert struct.unpack("<q", r["items"][1]["fields"]["n"])[0] == 21 and "tag" not in r["items"][0]["fields"]
+    r = e.query(document_ids=["3", "9", "4000", "x"], partition_id=1)  # docids; every field comes back
+    assert [it["fields"]["_id"] for it in r["items"]] == [b"doc3"] and set(r["items"][0]["fields"]) == {"_id", "n", "tag"}
+    q8 = lambda v: struct.pack("<q", v)
+    r = e.query(range_filters=[("n", q8(12), q8(60), True, True)], term_filters=[("tag", b"t1\x01t3")], limit=100,
+                fields=["_id"])
+    want = [i for i in range(200) if 12 <= i * 3 <= 60 and i % 4 in (1, 3) and i != 9]
+    assert [it["fields"]["_id"] for it in r["items"]] == [f"doc{i}".encode() for i in want]
+    r = e.query(term_filters=[("tag", b"t2")], limit=3, offset=2, fields=["_id"])
+    assert [it["fields"]["_id"] for it in r["items"]] == [b"doc10", b"doc14", b"doc18"]
+    r = e.query(term_filters=[("tag", b"zzz")], limit=5)
+    assert r["items"] == [] and "no result" in r["msg"]
+    e.close()

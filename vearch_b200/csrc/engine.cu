@@ -36,6 +36,54 @@ std::string Status::ToString() const {  // util/status.cc:43-100
 }
 
 // ---- vearchpb.SearchRequest (router_grpc.proto:168-191; request.cc:17-91) --------------------
+static bool parse_filter(const PbField& f, bool is_term, SearchRequestPB::Filter* fl) {
+  fl->is_term = is_term;
+  PbReader v(f.data, f.len);
+  PbField vf;
+  while (v.next(&vf)) {
+    if (vf.num == 1 && vf.wire == 2) fl->field.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+    if (vf.num == 2 && vf.wire == 2) fl->lower.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+    if (is_term) {
+      if (vf.num == 3 && vf.wire == 0) fl->is_union = (int)vf.val;
+    } else {
+      if (vf.num == 3 && vf.wire == 2) fl->upper.assign(reinterpret_cast<const char*>(vf.data), vf.len);
+      if (vf.num == 4 && vf.wire == 0) fl->include_lower = vf.val != 0;
+      if (vf.num == 5 && vf.wire == 0) fl->include_upper = vf.val != 0;
+      if (vf.num == 6 && vf.wire == 0) fl->is_union = (int)vf.val;
+    }
+  }
+  return !v.error();
+}
+
+bool QueryRequestPB::parse(const uint8_t* data, size_t len) {
+  PbReader r(data, len);
+  PbField f;
+  while (r.next(&f)) {
+    switch (f.num) {
+      case 2:
+        if (f.wire == 2) document_ids.emplace_back(reinterpret_cast<const char*>(f.data), f.len);
+        break;
+      case 3: partition_id = (int)f.val; break;
+      case 5:
+      case 6: {
+        if (f.wire != 2) break;
+        SearchRequestPB::Filter fl;
+        if (!parse_filter(f, f.num == 6, &fl)) return false;
+        filters.push_back(std::move(fl));
+        break;
+      }
+      case 7:
+        if (f.wire == 2) fields.emplace_back(reinterpret_cast<const char*>(f.data), f.len);
+        break;
+      case 9: limit = (int)f.val; break;
+      case 15: filter_operator = (int)f.val; break;
+      case 17: offset = (int)f.val; break;
+      default: break;
+    }
+  }
+  return !r.error();
+}
+
 bool SearchRequestPB::parse(const uint8_t* data, size_t len) {
   PbReader r(data, len);
   PbField f;
@@ -87,23 +135,8 @@ bool SearchRequestPB::parse(const uint8_t* data, size_t len) {
       case 8: {
         if (f.wire != 2) break;
         Filter fl;
-        fl.is_term = f.num == 8;
+        if (!parse_filter(f, f.num == 8, &fl)) return false;
         (fl.is_term ? n_term_filters : n_range_filters)++;
-        PbReader v(f.data, f.len);
-        PbField vf;
-        while (v.next(&vf)) {
-          if (vf.num == 1 && vf.wire == 2) fl.field.assign(reinterpret_cast<const char*>(vf.data), vf.len);
-          if (vf.num == 2 && vf.wire == 2) fl.lower.assign(reinterpret_cast<const char*>(vf.data), vf.len);
-          if (fl.is_term) {
-            if (vf.num == 3 && vf.wire == 0) fl.is_union = (int)vf.val;
-          } else {
-            if (vf.num == 3 && vf.wire == 2) fl.upper.assign(reinterpret_cast<const char*>(vf.data), vf.len);
-            if (vf.num == 4 && vf.wire == 0) fl.include_lower = vf.val != 0;
-            if (vf.num == 5 && vf.wire == 0) fl.include_upper = vf.val != 0;
-            if (vf.num == 6 && vf.wire == 0) fl.is_union = (int)vf.val;
-          }
-        }
-        if (v.error()) return false;
         filters.push_back(std::move(fl));
         break;
       }
@@ -469,12 +502,12 @@ std::vector<std::string> split001(const std::string& s) {
 }
 }  // namespace
 
-int64_t Engine::eval_filters(const SearchRequestPB& req, std::vector<uint8_t>* bitmap) const {
+int64_t Engine::eval_filters(const std::vector<SearchRequestPB::Filter>& filters, int op, std::vector<uint8_t>* bitmap) const {
   const int n = max_docid_;
   bitmap->assign((size_t)(n >> 3) + 1, 0);
   std::vector<uint8_t> cur((size_t)(n >> 3) + 1);
   bool first = true;
-  for (const auto& fl : req.filters) {
+  for (const auto& fl : filters) {
     auto it = field_idx_.find(fl.field);
     if (it == field_idx_.end() || !fields_[it->second].indexed) return 0;
     const int fi = it->second, dt = fields_[fi].data_type;
@@ -516,9 +549,9 @@ int64_t Engine::eval_filters(const SearchRequestPB& req, std::vector<uint8_t>* b
       bitmap->swap(cur);
       cur.resize(bitmap->size());
       first = false;
-    } else if (req.filter_operator == 0) {
+    } else if (op == 0) {
       for (size_t i = 0; i < cur.size(); i++) (*bitmap)[i] &= cur[i];
-    } else if (req.filter_operator == 1) {
+    } else if (op == 1) {
       for (size_t i = 0; i < cur.size(); i++) (*bitmap)[i] |= cur[i];
     }
   }
@@ -585,7 +618,7 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
     }
     total_docs = doc_num();
     if (!req.filters.empty()) {  // ScalarIndexQuery (search/engine.cc:349-366, 525-580)
-      if (eval_filters(req, &fbm) == 0) {
+      if (eval_filters(req.filters, req.filter_operator, &fbm) == 0) {
         PbWriter resp;
         for (int i = 0; i < req.req_num; i++) {
           PbWriter sr, st;
@@ -661,6 +694,100 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
     sr.out += items.out;
     resp.put_message(2, sr.out);
   }
+  *pb_out = resp.out;
+  return Status::OK();
+}
+
+void Engine::put_doc_fields(int docid, const std::vector<int>& attr, bool want_vec, PbWriter* item) {
+  for (int fi : attr) {
+    PbWriter fld;
+    fld.put_string(1, fields_[fi].name);
+    const std::string& val = values_[fi][docid];
+    fld.put_bytes(3, val.data(), val.size());
+    item->put_message(2, fld.out);
+  }
+  if (want_vec) {
+    std::vector<float> vbuf(dim_);
+    if (index_->store().get_host(docid, vbuf.data()) == 0) {
+      PbWriter fld;
+      fld.put_string(1, vec_name_);
+      fld.put_bytes(3, vbuf.data(), (size_t)dim_ * 4);
+      item->put_message(2, fld.out);
+    }
+  }
+}
+
+// Engine::Query (search/engine.cc:404-523): documents by key (by docid when partition_id > 0), or the
+// first `limit` live documents that pass the scalar filters, as one SearchResult with score-less items
+Status Engine::Query(const QueryRequestPB& req, std::string* pb_out) {
+  if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
+  std::unique_lock<std::shared_mutex> wl(mu_);
+  if (pending_n_ > 0 && flush_pending_locked()) return Status::Make(kIndexError, last_error());
+  std::vector<int> docids;
+  auto deleted = [&](int d) { return ((del_bitmap_[d >> 3] >> (d & 7)) & 1) != 0; };
+  if (!req.document_ids.empty()) {
+    for (const auto& id : req.document_ids) {
+      int docid = -1;
+      if (req.partition_id > 0) {
+        char* end = nullptr;
+        long v = strtol(id.c_str(), &end, 10);
+        if (id.empty() || *end != '\0' || v < 0 || v >= max_docid_) continue;
+        docid = (int)v;
+      } else {
+        auto it = key2docid_.find(id);
+        if (it == key2docid_.end()) continue;
+        docid = it->second;
+      }
+      if (!deleted(docid)) docids.push_back(docid);
+    }
+  } else {
+    const int topn = req.limit;
+    std::vector<uint8_t> fbm;
+    if (!req.filters.empty()) {
+      if (eval_filters(req.filters, req.filter_operator, &fbm) == 0) {
+        PbWriter resp, sr, st;
+        st.put_int32(1, 0);
+        st.put_int32(3, 0);
+        sr.put_message(5, st.out);
+        sr.put_string(6, space_name_ + " no result: numeric filter return 0 result");
+        resp.put_message(2, sr.out);
+        *pb_out = resp.out;
+        return Status::OK();
+      }
+      int skipped = 0;
+      for (int d = 0; d < max_docid_ && (int)docids.size() < topn; d++) {
+        if (!((fbm[d >> 3] >> (d & 7)) & 1)) continue;
+        if (skipped++ < req.offset) continue;  // ScalarIndexManager::Query drops `offset` hits first
+        if (!deleted(d)) docids.push_back(d);
+      }
+    }
+  }
+  std::vector<int> attr;
+  bool want_vec = false;
+  if (!req.fields.empty()) {
+    for (auto& nme : req.fields) {
+      if (nme == vec_name_)
+        want_vec = true;
+      else if (field_idx_.count(nme))
+        attr.push_back(field_idx_[nme]);
+    }
+  } else {
+    for (size_t fi = 0; fi < fields_.size(); fi++) attr.push_back((int)fi);
+  }
+  std::sort(attr.begin(), attr.end(), [&](int a, int b) { return fields_[a].name < fields_[b].name; });
+  PbWriter resp, sr, st, items;
+  for (int d : docids) {
+    PbWriter item;  // score 0.0: proto3 leaves it off the wire
+    put_doc_fields(d, attr, want_vec, &item);
+    items.put_message(7, item.out);
+  }
+  sr.put_double(2, docids.empty() ? -DBL_MAX : 0.0);
+  st.put_int32(1, (int)docids.size());
+  st.put_int32(3, (int)docids.size());
+  sr.put_message(5, st.out);
+  sr.put_string(6, Status::OK().ToString());
+  sr.out += items.out;
+  resp.put_message(2, sr.out);
   *pb_out = resp.out;
   return Status::OK();
 }

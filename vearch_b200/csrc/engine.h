@@ -16,6 +16,7 @@
 #include "index.h"
 
 namespace gb {
+struct PbWriter;
 
 struct Status {  // util/status.h
   int code = 0;  // vearch::status::Code (idl/fbs/status.fbs)
@@ -74,6 +75,16 @@ struct SearchRequestPB {  // c_api/api_data/request.{h,cc}
   bool parse(const uint8_t* data, size_t len);
 };
 
+struct QueryRequestPB {  // vearchpb.QueryRequest (router_grpc.proto:147-166), c_api/api_data/query_request.cc
+  std::vector<std::string> document_ids;
+  int partition_id = 0;
+  std::vector<SearchRequestPB::Filter> filters;
+  int filter_operator = 0;
+  std::vector<std::string> fields;
+  int limit = 0, offset = 0;
+  bool parse(const uint8_t* data, size_t len);
+};
+
 class Engine {
  public:
   Engine(const std::string& path, const std::string& space_name, int device);
@@ -85,6 +96,7 @@ class Engine {
   int GetDocByKey(const std::string& key, std::string* fb_out);
   int GetDocByDocid(int docid, bool next, std::string* fb_out);
   Status Search(const SearchRequestPB& req, std::string* pb_out);
+  Status Query(const QueryRequestPB& req, std::string* pb_out);  // search/engine.cc:404-523
   int BuildIndex();
   std::string EngineStatus();
   std::string MemoryInfo();
@@ -119,7 +131,8 @@ class Engine {
   };
   // ScalarIndexManager::Search (table/scalar_index_manager.cc:294-345, 588-651) as a scan of the
   // in-memory columns: dense LSB-first bitmap of the docids that pass; returns the cardinality
-  int64_t eval_filters(const SearchRequestPB& req, std::vector<uint8_t>* bitmap) const;
+  int64_t eval_filters(const std::vector<SearchRequestPB::Filter>& filters, int op, std::vector<uint8_t>* bitmap) const;
+  void put_doc_fields(int docid, const std::vector<int>& attr, bool want_vec, PbWriter* item);
   std::vector<FieldDef> fields_;
   std::unordered_map<std::string, int> field_idx_;
   std::vector<std::vector<std::string>> values_;  // [field][docid]

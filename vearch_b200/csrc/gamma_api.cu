@@ -133,9 +133,21 @@ struct CStatus Search(void* engine, const char* request_str, int req_len, char**
   return c;
 }
 
-struct CStatus Query(void*, const char*, int, char**, int*) {
+struct CStatus Query(void* engine, const char* request_str, int req_len, char** response_str, int* res_len) {
   struct CStatus c;
-  to_cstatus(gb::Status::Make(gb::kNotSupported, "Query (scalar-only document query) is outside the vector hot path"), &c);
+  if (!engine) {
+    to_cstatus(gb::Status::Make(gb::kInvalidArgument, "null engine"), &c);
+    return c;
+  }
+  gb::QueryRequestPB req;
+  if (!req.parse(reinterpret_cast<const uint8_t*>(request_str), (size_t)req_len)) {
+    to_cstatus(gb::Status::Make(gb::kInvalidArgument, "parse query request failed"), &c);
+    return c;
+  }
+  std::string resp;
+  gb::Status st = static_cast<Engine*>(engine)->Query(req, &resp);
+  to_cstatus(st, &c);
+  if (st.ok()) out_buffer(resp, response_str, res_len);
   return c;
 }
 

@@ -189,7 +189,9 @@ class GammaEngine:
         _api().GetConfig(self._h, C.byref(p), C.byref(n))
         return json.loads(_take(p, n))
 
-    def query_status(self):
+    def query(self, **kw):
+        """Query (search/engine.cc:404-523): documents by key / docid or by scalar filters; one result."""
+        req = wire.encode_query_request(**kw)
         p, n = C.c_void_p(), C.c_int()
-        st = _api().Query(self._h, b"", 0, C.byref(p), C.byref(n))
-        return st.code
+        _status(_api().Query(self._h, req, len(req), C.byref(p), C.byref(n)))
+        return wire.decode_search_response(_take(p, n))[0]

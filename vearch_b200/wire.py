@@ -281,24 +281,9 @@ def encode_search_request(vec_name, queries, topn, index_params="", is_brute_sea
     for f in fields:
         out += _ld(6, f.encode())
     for rf in range_filters:
-        field, lo, hi, inc_lo, inc_hi = rf[:5]
-        m = _ld(1, field.encode())
-        if lo:
-            m += _ld(2, lo)
-        if hi:
-            m += _ld(3, hi)
-        if inc_lo:
-            m += _key(4, 0) + _varint(1)
-        if inc_hi:
-            m += _key(5, 0) + _varint(1)
-        if len(rf) > 5 and rf[5]:
-            m += _key(6, 0) + _varint(rf[5])
-        out += _ld(7, m)
+        out += _ld(7, _enc_range_filter(rf))
     for tf in term_filters:
-        m = _ld(1, tf[0].encode()) + (_ld(2, tf[1]) if tf[1] else b"")
-        if len(tf) > 2 and tf[2]:
-            m += _key(3, 0) + _varint(tf[2])
-        out += _ld(8, m)
+        out += _ld(8, _enc_term_filter(tf))
     if index_params:
         out += _ld(9, index_params.encode())
     if trace:
@@ -307,6 +292,53 @@ def encode_search_request(vec_name, queries, topn, index_params="", is_brute_sea
         out += _key(17, 0) + _varint(operator)
     if offset:
         out += _key(20, 0) + _varint(offset)
+    return bytes(out)
+
+
+def _enc_range_filter(rf):
+    field, lo, hi, inc_lo, inc_hi = rf[:5]
+    m = _ld(1, field.encode())
+    if lo:
+        m += _ld(2, lo)
+    if hi:
+        m += _ld(3, hi)
+    if inc_lo:
+        m += _key(4, 0) + _varint(1)
+    if inc_hi:
+        m += _key(5, 0) + _varint(1)
+    if len(rf) > 5 and rf[5]:
+        m += _key(6, 0) + _varint(rf[5])
+    return m
+
+
+def _enc_term_filter(tf):
+    m = _ld(1, tf[0].encode()) + (_ld(2, tf[1]) if tf[1] else b"")
+    if len(tf) > 2 and tf[2]:
+        m += _key(3, 0) + _varint(tf[2])
+    return m
+
+
+def encode_query_request(document_ids=(), partition_id=0, range_filters=(), term_filters=(), fields=(), limit=0,
+                         operator=0, offset=0):
+    """vearchpb.QueryRequest (internal/proto/router_grpc.proto:147-166): documents by key (by docid when
+    partition_id > 0) or by scalar filters."""
+    out = bytearray()
+    for d in document_ids:
+        out += _ld(2, d.encode() if isinstance(d, str) else d)
+    if partition_id:
+        out += _key(3, 0) + _varint(partition_id)
+    for rf in range_filters:
+        out += _ld(5, _enc_range_filter(rf))
+    for tf in term_filters:
+        out += _ld(6, _enc_term_filter(tf))
+    for f in fields:
+        out += _ld(7, f.encode())
+    if limit:
+        out += _key(9, 0) + _varint(limit)
+    if operator:
+        out += _key(15, 0) + _varint(operator)
+    if offset:
+        out += _key(17, 0) + _varint(offset)
     return bytes(out)
 
 
