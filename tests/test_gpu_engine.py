@@ -412,3 +412,68 @@ def test_query_by_ids_and_by_filters(tmp_path, data):
     r = e.query(term_filters=[("tag", b"zzz")], limit=5)
     assert r["items"] == [] and "no result" in r["msg"]
     e.close()
+
+
+def test_multi_vector_table_join_and_weighted_rank(tmp_path, data):
+    """Two vector fields, each with its own index: a request with two vec_fields searches both, keeps the
+    documents BOTH returned and scores them with the WeightedRanker (vector_manager.cc:747, 900-964)."""
+    db, xq = data
+    n, d2, topn = 2500, 16, 60
+    img = synth.sift_like(n, d2, seed=91)
+    imq = synth.sift_like(NQ, d2, seed=92)
+    e = eng_mod().GammaEngine(str(tmp_path), space_name="ts")
+    e.create_table("ts", D, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 1000},
+                   extra_vectors=[("img", d2, "FLAT", {"metric_type": "L2"})])
+    assert e.add_doc("bad", db[0]) == -3  # CheckDoc: every vector field must be present (engine.cc:802-813)
+    for i in range(n):
+        assert e.add_doc(f"doc{i}", db[i], extra_fields=[("img", img[i].tobytes(), wire.DT_VECTOR)]) == 0
+    st = e.wait_indexed(n)
+    assert st["min_indexed_num"] == n
+    rc, doc = e.get_doc_by_id("doc3")
+    assert rc == 0 and np.array_equal(np.frombuffer(doc["img"][0], np.float32), img[3])
+    assert np.array_equal(np.frombuffer(doc["emb"][0], np.float32), db[3])
+    # one field at a time: either field can be the query
+    d1, i1 = orc.flat_search(db[:n], xq, topn, L2)
+    d2s, i2 = orc.flat_search(img, imq, topn, L2)
+    w = np.array([0.3, 0.7], np.float32)
+
+    def expect(rank):
+        out = []
+        for q in range(NQ):
+            m1 = dict(zip(i1[q].tolist(), d1[q].tolist()))
+            m2 = dict(zip(i2[q].tolist(), d2s[q].tolist()))
+            both = sorted(set(m1) & set(m2))
+            sc = [float(np.float32(float(np.float32(m1[k]) * w[0]) + float(np.float32(m2[k]) * w[1]))) for k in both]
+            pairs = list(zip(both, sc))
+            if rank:
+                pairs.sort(key=lambda t: t[1])  # stable: docid order among equal scores
+            out.append(pairs)
+        return out
+
+    for rank in (0, 1):
+        res = e.search(xq, topn, is_brute_search=1, extra_vec_queries=[("img", imq)],
+                       ranker='{"type": "WeightedRanker", "params": [0.3, 0.7]}', multi_vector_rank=rank)
+        exp = expect(rank)
+        assert keys_of(res) == [[f"doc{k}" for k, _ in row] for row in exp]
+        got_sc = scores_of(res)
+        for q in range(NQ):
+            assert np.allclose(got_sc[q], [s for _, s in exp[q]], rtol=1e-6)
+    assert sum(len(r) for r in exp) > NQ  # the join is not trivially empty
+    # default weights 1 / vec_num; bad ranker -> InvalidArgument (common_query_data.h:257-300)
+    res = e.search(xq[:2], topn, is_brute_search=1, extra_vec_queries=[("img", imq[:2])], multi_vector_rank=1)
+    assert len(res) == 2 and all(len(r["items"]) > 0 for r in res)
+    with pytest.raises(eng_mod().GammaStatusError) as ei:
+        e.search(xq[:2], topn, is_brute_search=1, extra_vec_queries=[("img", imq[:2])], ranker='{"type": "WeightedRanker", "params": [1.0]}')
+    assert ei.value.code == 4 and "length don't equal" in ei.value.msg
+    # dump / load keeps both fields
+    before = keys_of(e.search(xq, topn, is_brute_search=1, extra_vec_queries=[("img", imq)], multi_vector_rank=1))
+    assert e.dump() == 0
+    e.close()
+    e2 = eng_mod().GammaEngine(str(tmp_path), space_name="ts")
+    e2.create_table("ts", D, "IVFFLAT", {"ncentroids": 16, "nprobe": 16, "metric_type": "L2", "training_threshold": 1000},
+                    extra_vectors=[("img", d2, "FLAT", {"metric_type": "L2"})])
+    assert e2.load() == 0
+    e2.wait_indexed(n)
+    after = keys_of(e2.search(xq, topn, is_brute_search=1, extra_vec_queries=[("img", imq)], multi_vector_rank=1))
+    assert after == before
+    e2.close()

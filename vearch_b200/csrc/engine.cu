@@ -144,6 +144,9 @@ bool SearchRequestPB::parse(const uint8_t* data, size_t len) {
         if (f.wire == 2) index_params.assign(reinterpret_cast<const char*>(f.data), f.len);
         break;
       case 10: multi_vector_rank = (int)f.val; break;
+      case 15:
+        if (f.wire == 2) ranker.assign(reinterpret_cast<const char*>(f.data), f.len);
+        break;
       case 11: l2_sqrt = f.val != 0; break;
       case 16: trace = f.val != 0; break;
       case 17: filter_operator = (int)f.val; break;
@@ -238,7 +241,6 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
   values_.assign(fields_.size(), {});
   size_t nvec = t.vec_len(2);
   if (nvec == 0) return Status::Make(kInvalidArgument, space_name_ + " table has no vector field");
-  if (nvec > 1) return Status::Make(kNotSupported, "multi-vector tables are not supported by the B200 engine yet");
   FbTable v = t.vec_table(2, 0);
   vec_name_ = v.str(0);
   dim_ = v.scalar<int32_t>(3, 0);
@@ -279,6 +281,30 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
                                     : kNotSupported,
                                 last_error());
   index_.reset(idx);
+  extra_.clear();
+  for (size_t vi = 1; vi < nvec; vi++) {  // the other vector fields: same rules, their own index each
+    FbTable ev = t.vec_table(2, vi);
+    VecField vf;
+    vf.name = ev.str(0);
+    vf.dim = ev.scalar<int32_t>(3, 0);
+    if (vf.dim <= 0 || vf.name.empty() || vf.name == vec_name_) return Status::Make(kInvalidArgument, "invalid vector field");
+    for (size_t i = 0; i < t.vec_len(8); i++) {
+      FbTable ix = t.vec_table(8, i);
+      if (ix.str(2) == vf.name && !ix.str(1).empty()) {
+        vf.index_type = ix.str(1);
+        vf.index_params = ix.str(4);
+        break;
+      }
+    }
+    if (vf.index_type.empty()) return Status::Make(kInvalidArgument, vf.name + " index type is empty");
+    ModelParams emp;
+    if (!parse_model_params(vf.index_params, &emp, &err)) return Status::Make(kInvalidArgument, err);
+    if (training_threshold_ > 0) emp.training_threshold = training_threshold_;
+    Index* eidx = create_index(vf.index_type, vf.dim, emp, device_, 20);
+    if (!eidx) return Status::Make(kInvalidArgument, last_error());
+    vf.index.reset(eidx);
+    extra_.push_back(std::move(vf));
+  }
   {  // registered after the index (and so after CUDA start-up): at exit the engine's thread stops first
     std::lock_guard<std::mutex> g(live_engines().mu);
     static bool hooked = (atexit(quiesce_all_engines), true);
@@ -296,8 +322,25 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
   return Status::OK();
 }
 
+Index* Engine::index_of(const std::string& vec_name, int* dim) {
+  if (vec_name == vec_name_) {
+    *dim = dim_;
+    return index_.get();
+  }
+  for (auto& e : extra_)
+    if (e.name == vec_name) {
+      *dim = e.dim;
+      return e.index.get();
+    }
+  return nullptr;
+}
+
 int Engine::flush_pending_locked() {
   if (pending_n_ == 0) return 0;
+  for (auto& e : extra_) {
+    if (e.index->add_vectors(e.pending.data(), pending_n_)) return -1;
+    e.pending.clear();
+  }
   int rc = index_->add_vectors(pending_.data(), pending_n_);
   if (rc) return rc;
   pending_.clear();
@@ -315,6 +358,7 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
   const uint8_t* vec = nullptr;
   size_t vec_len = 0;
   bool has_vec = false;
+  std::vector<std::pair<const uint8_t*, size_t>> evec(extra_.size(), {nullptr, 0});
   for (size_t i = 0; i < d.vec_len(0); i++) {
     FbTable f = d.vec_table(0, i);
     DocField df;
@@ -330,6 +374,8 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
         vec_len = n;
         has_vec = true;
       }
+      for (size_t ei = 0; ei < extra_.size(); ei++)
+        if (df.name == extra_[ei].name) evec[ei] = {p, n};
     } else {
       if (!field_idx_.count(df.name)) continue;  // "Unknown field" (doc.cc:66-69)
       df.value.assign(reinterpret_cast<const char*>(p), n);
@@ -348,12 +394,22 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
       if (flush_pending_locked()) return -1;
       if (index_->update_vector(docid, x.data())) return -1;
     }
+    for (size_t ei = 0; ei < extra_.size(); ei++) {
+      if (!evec[ei].first) continue;
+      if (evec[ei].second != (size_t)extra_[ei].dim * 4) return -1;
+      std::vector<float> x(extra_[ei].dim);
+      memcpy(x.data(), evec[ei].first, evec[ei].second);
+      if (flush_pending_locked()) return -1;
+      if (extra_[ei].index->update_vector(docid, x.data())) return -1;
+    }
     return 0;
   } else if (docid >= max_docid_) {
     return -2;
   }
   // CheckDoc (engine.cc:802-813): every vector field present with d*4 bytes
   if (!has_vec || vec_len != (size_t)dim_ * 4) return -3;
+  for (size_t ei = 0; ei < extra_.size(); ei++)
+    if (!evec[ei].first || evec[ei].second != (size_t)extra_[ei].dim * 4) return -3;
   if (key.empty()) return -3;
   for (size_t fi = 0; fi < fields_.size(); fi++) values_[fi].emplace_back();
   for (auto& f : table_fields) values_[field_idx_[f.name]][max_docid_] = f.value;
@@ -362,6 +418,11 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
   key2docid_[key] = max_docid_;
   pending_.resize((size_t)(pending_n_ + 1) * dim_);
   memcpy(pending_.data() + (size_t)pending_n_ * dim_, vec, vec_len);
+  for (size_t ei = 0; ei < extra_.size(); ei++) {
+    auto& e = extra_[ei];
+    e.pending.resize((size_t)(pending_n_ + 1) * e.dim);
+    memcpy(e.pending.data() + (size_t)pending_n_ * e.dim, evec[ei].first, evec[ei].second);
+  }
   pending_n_++;
   ++max_docid_;
   if ((size_t)(max_docid_ >> 3) + 1 > del_bitmap_.size()) del_bitmap_.resize((size_t)(max_docid_ >> 3) + 4096, 0);
@@ -413,6 +474,17 @@ void Engine::serialize_doc(int docid, bool with_docid, std::string* out) {
       got = true;
     }
     if (got) add_field(vec_name_, std::string(reinterpret_cast<const char*>(x.data()), (size_t)dim_ * 4), DT_VECTOR);
+    for (auto& e : extra_) {
+      std::vector<float> ex(e.dim);
+      bool egot = false;
+      if (docid < stored) {
+        egot = e.index->store().get_host(docid, ex.data()) == 0;
+      } else if (docid - stored < pending_n_) {
+        memcpy(ex.data(), e.pending.data() + (size_t)(docid - stored) * e.dim, (size_t)e.dim * 4);
+        egot = true;
+      }
+      if (egot) add_field(e.name, std::string(reinterpret_cast<const char*>(ex.data()), (size_t)e.dim * 4), DT_VECTOR);
+    }
   }
   FbBuilder::Off fv = b.create_offset_vector(offs);
   b.start_table(1);
@@ -567,18 +639,18 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
   if (req.req_num <= 0) return Status::Make(kInvalidArgument, space_name_ + " req_num should not less than 0");
   if (req.topn <= 0) return Status::Make(kInvalidArgument, "limit[topN] is zero");
-  if (req.vec_fields.size() != 1)
-    return Status::Make(req.vec_fields.empty() ? kInvalidArgument : kNotSupported,
-                        req.vec_fields.empty() ? "no vector query" : "multi-vector queries are not supported yet");
+  if (req.vec_fields.empty()) return Status::Make(kInvalidArgument, "no vector query");
+  if (req.vec_fields.size() > 1) return SearchMulti(req, pb_out);
   const auto& vq = req.vec_fields[0];
-  if (vq.name != vec_name_)
-    return Status::Make(kInvalidArgument, "Query name " + vq.name + " not exist in created vector table");
+  int qdim = 0;
+  Index* qindex = index_of(vq.name, &qdim);
+  if (!qindex) return Status::Make(kInvalidArgument, "Query name " + vq.name + " not exist in created vector table");
   int brute = req.brute_force_search;
   if (brute == 2 && index_status_.load() != 2) brute = 1;
   if (brute == 0 && index_status_.load() != 2 && max_docid_ > 100 && !enable_realtime_)
     return Status::Make(kIndexError, space_name_ + " index not trained, brute_force_search is 0, max_docid_ = " +
                                          std::to_string(max_docid_) + ", threshold = 100");
-  int n = (int)(vq.value.size() / ((size_t)dim_ * 4));
+  int n = (int)(vq.value.size() / ((size_t)qdim * 4));
   if (n <= 0) return Status::Make(kInvalidArgument, "Search n shouldn't less than 0!");
   if (IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
   SearchContext ctx;
@@ -594,7 +666,7 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
     ctx.max_score = FLT_MAX;
   }
   const int topN = req.topn + req.offset;
-  std::vector<float> x((size_t)n * dim_);
+  std::vector<float> x((size_t)n * qdim);
   memcpy(x.data(), vq.value.data(), x.size() * 4);
   std::vector<float> dis((size_t)n * topN);
   std::vector<int64_t> ids((size_t)n * topN);
@@ -635,29 +707,37 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
       ctx.bitmap_bits = max_docid_;
     }
   }
-  int rc = index_->search(ctx, n, x.data(), topN, dis.data(), ids.data());
+  int rc = qindex->search(ctx, n, x.data(), topN, dis.data(), ids.data());
   if (rc == -2 || IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
-  if (rc != 0) return Status::Make(kInvalidArgument, "faild search of query " + vec_name_ + ": " + last_error());
+  if (rc != 0) return Status::Make(kInvalidArgument, "faild search of query " + vq.name + ": " + last_error());
 
-  // ---- Response::Serialize -------------------------------------------------------------------
-  std::shared_lock<std::shared_mutex> rl(mu_);
-  // fields to return: requested ones, or every table field (response.cc:70-86)
-  std::vector<int> attr;
-  bool want_vec = false;
-  if (!req.fields.empty()) {
-    for (auto& nme : req.fields) {
-      if (nme == vec_name_)
-        want_vec = true;
+  serialize_results(req, n, topN, dis.data(), ids.data(), total_docs, pb_out);
+  return Status::OK();
+}
+
+Engine::FieldSel Engine::select_fields(const std::vector<std::string>& names) {
+  FieldSel sel;
+  if (!names.empty()) {
+    int dim;
+    for (auto& nme : names) {
+      if (index_of(nme, &dim))
+        sel.vecs.push_back(nme);
       else if (field_idx_.count(nme))
-        attr.push_back(field_idx_[nme]);
+        sel.attr.push_back(field_idx_[nme]);
     }
   } else {
-    for (size_t fi = 0; fi < fields_.size(); fi++) attr.push_back((int)fi);
+    for (size_t fi = 0; fi < fields_.size(); fi++) sel.attr.push_back((int)fi);
   }
-  std::sort(attr.begin(), attr.end(), [&](int a, int b) { return fields_[a].name < fields_[b].name; });  // std::map order
+  std::sort(sel.attr.begin(), sel.attr.end(), [&](int a, int b) { return fields_[a].name < fields_[b].name; });
+  return sel;
+}
+
+void Engine::serialize_results(const SearchRequestPB& req, int n, int topN, const float* dis, const int64_t* ids,
+                               int total_docs, std::string* pb_out) {
+  std::shared_lock<std::shared_mutex> rl(mu_);
+  const FieldSel sel = select_fields(req.fields);
   PbWriter resp;
   Status okst;
-  std::vector<float> vbuf(dim_);
   for (int i = 0; i < req.req_num && i < n; i++) {
     PbWriter sr;
     // field order on the wire follows the field numbers, like the C++ serializer
@@ -670,19 +750,7 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
       max_score = std::max(max_score, score);
       PbWriter item;
       item.put_double(1, score);
-      for (int fi : attr) {
-        PbWriter fld;
-        fld.put_string(1, fields_[fi].name);
-        const std::string& val = values_[fi][docid];
-        fld.put_bytes(3, val.data(), val.size());
-        item.put_message(2, fld.out);
-      }
-      if (want_vec && index_->store().get_host(docid, vbuf.data()) == 0) {
-        PbWriter fld;
-        fld.put_string(1, vec_name_);
-        fld.put_bytes(3, vbuf.data(), (size_t)dim_ * 4);
-        item.put_message(2, fld.out);
-      }
+      put_doc_fields((int)docid, sel, &item);
       items.put_message(7, item.out);
     }
     sr.put_double(2, max_score);
@@ -695,23 +763,146 @@ Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
     resp.put_message(2, sr.out);
   }
   *pb_out = resp.out;
+}
+
+// WeightedRanker::Parse (common/common_query_data.h:257-300)
+static bool parse_ranker(const std::string& raw, size_t nvec, std::vector<double>* w, std::string* err) {
+  w->assign(nvec, 1.0 / (double)nvec);
+  if (raw.empty()) return true;
+  *err = "weighted ranker params err: " + raw;
+  JsonValue jv;
+  if (!JsonParser::parse(raw, &jv) || !jv.get("type") || !jv.get("params")) return false;
+  const JsonValue* arr = jv.get("params");
+  if (arr->type != JsonValue::Array) return false;
+  if (arr->arr.size() != nvec) {
+    *err = "weighted ranker params: " + raw + ", length don't equal to " + std::to_string(nvec);
+    return false;
+  }
+  for (size_t i = 0; i < nvec; i++) {
+    if (arr->arr[i].type != JsonValue::Number) return false;
+    (*w)[i] = arr->arr[i].num;
+  }
+  return true;
+}
+
+Status Engine::SearchMulti(const SearchRequestPB& req, std::string* pb_out) {
+  const size_t nvec = req.vec_fields.size();
+  std::vector<Index*> idx(nvec);
+  std::vector<int> dims(nvec);
+  int n = -1;
+  for (size_t j = 0; j < nvec; j++) {
+    const auto& vq = req.vec_fields[j];
+    idx[j] = index_of(vq.name, &dims[j]);
+    if (!idx[j]) return Status::Make(kInvalidArgument, "Query name " + vq.name + " not exist in created vector table");
+    const int nj = (int)(vq.value.size() / ((size_t)dims[j] * 4));
+    if (nj <= 0 || (n >= 0 && nj != n)) return Status::Make(kInvalidArgument, "Search n shouldn't less than 0!");
+    n = nj;
+  }
+  std::vector<double> weights;
+  std::string err;
+  if (!parse_ranker(req.ranker, nvec, &weights, &err)) return Status::Make(kInvalidArgument, err);
+  int brute = req.brute_force_search;
+  if (brute == 2 && index_status_.load() != 2) brute = 1;
+  if (brute == 0 && index_status_.load() != 2 && max_docid_ > 100 && !enable_realtime_)
+    return Status::Make(kIndexError, space_name_ + " index not trained, brute_force_search is 0, max_docid_ = " +
+                                         std::to_string(max_docid_) + ", threshold = 100");
+  if (IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
+  SearchContext base;
+  if (!parse_retrieval_params(req.index_params, &base.params, &err)) return Status::Make(kInvalidArgument, err);
+  base.params.brute_force = brute != 0;
+  base.search_unindexed_tail = enable_realtime_;
+  const int topN = req.topn + req.offset;
+  std::vector<uint8_t> bm, fbm;
+  int total_docs;
+  {
+    std::unique_lock<std::shared_mutex> wl(mu_);
+    if (pending_n_ > 0 && flush_pending_locked()) return Status::Make(kIndexError, last_error());
+    if (delete_num_ > 0) {
+      bm.assign(del_bitmap_.begin(), del_bitmap_.begin() + (max_docid_ >> 3) + 1);
+      base.del_bitmap = bm.data();
+      base.bitmap_bits = max_docid_;
+    }
+    total_docs = doc_num();
+    if (!req.filters.empty()) {
+      if (eval_filters(req.filters, req.filter_operator, &fbm) == 0) {
+        PbWriter resp;
+        for (int i = 0; i < req.req_num; i++) {
+          PbWriter sr, st;
+          st.put_int32(1, 0);
+          st.put_int32(3, 0);
+          sr.put_message(5, st.out);
+          sr.put_string(6, space_name_ + " no result: numeric filter return 0 result");
+          resp.put_message(2, sr.out);
+        }
+        *pb_out = resp.out;
+        return Status::OK();
+      }
+      base.filter_bitmap = fbm.data();
+      base.bitmap_bits = max_docid_;
+    }
+  }
+  // every field on its own, topN each (vector_manager.cc:790-852)
+  std::vector<std::vector<float>> dis(nvec, std::vector<float>((size_t)n * topN));
+  std::vector<std::vector<int64_t>> ids(nvec, std::vector<int64_t>((size_t)n * topN));
+  for (size_t j = 0; j < nvec; j++) {
+    const auto& vq = req.vec_fields[j];
+    SearchContext ctx = base;
+    ctx.min_score = vq.has_min ? (float)std::max(vq.min_score, -(double)FLT_MAX) : (vq.has_max ? 0.f : -FLT_MAX);
+    ctx.max_score = vq.has_max ? (float)std::min(vq.max_score, (double)FLT_MAX) : (vq.has_min ? 0.f : FLT_MAX);
+    if (!vq.has_min && !vq.has_max) ctx.min_score = -FLT_MAX, ctx.max_score = FLT_MAX;
+    std::vector<float> x((size_t)n * dims[j]);
+    memcpy(x.data(), vq.value.data(), x.size() * 4);
+    int rc = idx[j]->search(ctx, n, x.data(), topN, dis[j].data(), ids[j].data());
+    if (rc == -2 || IsKilled(req.request_id, req.partition_id)) return Status::Make(kMemoryExceeded, "");
+    if (rc != 0) return Status::Make(kInvalidArgument, "faild search of query " + vq.name + ": " + last_error());
+  }
+  // docid join (vector_manager.cc:900-964): a document survives when EVERY field returned it; its score is
+  // the weighted sum of the per-field scores; docid order unless multi_vector_rank asks for score order
+  std::vector<float> out_dis((size_t)n * topN, 0.f);
+  std::vector<int64_t> out_ids((size_t)n * topN, -1);
+  const bool l2 = index_->metric() == kMetricL2;
+  for (int i = 0; i < n; i++) {
+    std::map<int64_t, std::pair<int, double>> acc;  // docid -> (fields seen, score)
+    for (size_t j = 0; j < nvec; j++)
+      for (int r = 0; r < topN; r++) {
+        const int64_t d = ids[j][(size_t)i * topN + r];
+        if (d < 0) continue;
+        auto& e = acc[d];
+        e.first++;
+        e.second += (double)((float)dis[j][(size_t)i * topN + r] * (float)weights[j]);  // float product, as the reference
+      }
+    std::vector<std::pair<int64_t, double>> common;
+    for (auto& kv : acc)
+      if (kv.second.first == (int)nvec) common.push_back({kv.first, kv.second.second});
+    if (req.multi_vector_rank == 1)
+      std::sort(common.begin(), common.end(), [l2](const std::pair<int64_t, double>& a, const std::pair<int64_t, double>& b) {
+        return l2 ? a.second < b.second : a.second > b.second;
+      });
+    for (size_t r = 0; r < common.size() && r < (size_t)topN; r++) {
+      out_ids[(size_t)i * topN + r] = common[r].first;
+      out_dis[(size_t)i * topN + r] = (float)common[r].second;
+    }
+  }
+  serialize_results(req, n, topN, out_dis.data(), out_ids.data(), total_docs, pb_out);
   return Status::OK();
 }
 
-void Engine::put_doc_fields(int docid, const std::vector<int>& attr, bool want_vec, PbWriter* item) {
-  for (int fi : attr) {
+void Engine::put_doc_fields(int docid, const FieldSel& sel, PbWriter* item) {
+  for (int fi : sel.attr) {
     PbWriter fld;
     fld.put_string(1, fields_[fi].name);
     const std::string& val = values_[fi][docid];
     fld.put_bytes(3, val.data(), val.size());
     item->put_message(2, fld.out);
   }
-  if (want_vec) {
-    std::vector<float> vbuf(dim_);
-    if (index_->store().get_host(docid, vbuf.data()) == 0) {
+  for (const auto& vn : sel.vecs) {
+    int dim = 0;
+    Index* ix = index_of(vn, &dim);
+    std::vector<float> vbuf(dim);
+    if (ix && ix->store().get_host(docid, vbuf.data()) == 0) {
       PbWriter fld;
-      fld.put_string(1, vec_name_);
-      fld.put_bytes(3, vbuf.data(), (size_t)dim_ * 4);
+      fld.put_string(1, vn);
+      fld.put_bytes(3, vbuf.data(), (size_t)dim * 4);
       item->put_message(2, fld.out);
     }
   }
@@ -762,23 +953,11 @@ Status Engine::Query(const QueryRequestPB& req, std::string* pb_out) {
       }
     }
   }
-  std::vector<int> attr;
-  bool want_vec = false;
-  if (!req.fields.empty()) {
-    for (auto& nme : req.fields) {
-      if (nme == vec_name_)
-        want_vec = true;
-      else if (field_idx_.count(nme))
-        attr.push_back(field_idx_[nme]);
-    }
-  } else {
-    for (size_t fi = 0; fi < fields_.size(); fi++) attr.push_back((int)fi);
-  }
-  std::sort(attr.begin(), attr.end(), [&](int a, int b) { return fields_[a].name < fields_[b].name; });
+  const FieldSel sel = select_fields(req.fields);
   PbWriter resp, sr, st, items;
   for (int d : docids) {
     PbWriter item;  // score 0.0: proto3 leaves it off the wire
-    put_doc_fields(d, attr, want_vec, &item);
+    put_doc_fields(d, sel, &item);
     items.put_message(7, item.out);
   }
   sr.put_double(2, docids.empty() ? -DBL_MAX : 0.0);
@@ -813,7 +992,9 @@ void Engine::indexing_loop() {
     std::unique_lock<std::shared_mutex> lk(mu_);
     flush_pending_locked();
   }
-  if (index_->train() != 0) {  // TrainIndex failed (e.g. fewer vectors than training_threshold)
+  bool train_failed = index_->train() != 0;  // e.g. fewer vectors than training_threshold
+  for (auto& e : extra_) train_failed = train_failed || e.index->train() != 0;
+  if (train_failed) {
     indexing_state_.store(0);
     idx_cv_.notify_all();
     return;
@@ -831,6 +1012,8 @@ void Engine::indexing_loop() {
       if (delete_num_ > 0) bm.assign(del_bitmap_.begin(), del_bitmap_.begin() + (max_docid_ >> 3) + 1);
     }
     if (!has_error && index_->add_pending(bm.empty() ? nullptr : bm.data()) != 0) has_error = true;
+    for (auto& e : extra_)
+      if (!has_error && e.index->add_pending(bm.empty() ? nullptr : bm.data()) != 0) has_error = true;
     if (!has_error) index_status_.store(2);
     // sleep refresh_interval ms, waking early on Close
     std::unique_lock<std::mutex> lk(idx_mu_);
@@ -844,6 +1027,7 @@ void Engine::indexing_loop() {
 std::string Engine::EngineStatus() {  // search/engine.cc:1164-1176
   std::shared_lock<std::shared_mutex> lk(mu_);
   int64_t min_indexed = created_table_ && index_ ? index_->indexed_count() : 0;
+  for (auto& e : extra_) min_indexed = std::min(min_indexed, e.index->indexed_count());  // min over the vector fields
   char buf[256];
   snprintf(buf, sizeof buf,
            "{\"backup_status\":0,\"doc_num\":%d,\"index_status\":%d,\"max_docid\":%d,\"min_indexed_num\":%lld}",
@@ -858,6 +1042,7 @@ std::string Engine::MemoryInfo() {  // search/engine.cc:1178-1200
     for (auto& v : col) table_mem += (long long)v.size() + (long long)sizeof(std::string);
   long long index_mem = index_ ? index_->index_mem_bytes() : 0;
   long long vec_mem = index_ ? index_->store().mem_bytes() : 0;
+  for (auto& e : extra_) index_mem += e.index->index_mem_bytes(), vec_mem += e.index->store().mem_bytes();
   char buf[256];
   snprintf(buf, sizeof buf,
            "{\"bitmap_mem\":%lld,\"field_range_mem\":0,\"index_mem\":%lld,\"table_mem\":%lld,\"vector_mem\":%lld}",
@@ -948,6 +1133,17 @@ int Engine::Dump() {
   // the index itself in gamma's own format (IndexModel::Dump via VectorManager::Dump,
   // vector_manager.cc:1155-1170): <dir>/<vector name>.000/{ivfflat,ivfpq}.index
   if (trained && ivf && ivf->dump_gamma(dir, vec_name_ + ".000")) return -1;
+  for (auto& e : extra_) {  // the other vector fields: raw rows next to the table, index in gamma's format
+    std::ofstream ef(dir + "/" + table_name_ + "." + e.name + ".gbvec", std::ios::binary | std::ios::trunc);
+    std::vector<float> erows((size_t)max_docid_ * e.dim);
+    if (!ef || (max_docid_ && e.index->store().get_rows_host(0, max_docid_, erows.data()))) return -1;
+    wr<int32_t>(ef, max_docid_);
+    wr<int32_t>(ef, e.dim);
+    ef.write(reinterpret_cast<const char*>(erows.data()), (std::streamsize)(erows.size() * 4));
+    if (ef.fail()) return -1;
+    IVFFlatIndex* eivf = dynamic_cast<IVFFlatIndex*>(e.index.get());
+    if (eivf && eivf->trained() && eivf->dump_gamma(dir, e.name + ".000")) return -1;
+  }
   std::ofstream done(dir + "/dump.done");
   done << "ok";
   return f.fail() ? -1 : 0;
@@ -994,6 +1190,17 @@ int Engine::Load() {
   max_docid_ = maxd;
   delete_num_ = deln;
   if (maxd && index_->add_vectors(rows.data(), maxd)) return -1;
+  for (auto& e : extra_) {
+    std::ifstream ef(dir + "/" + table_name_ + "." + e.name + ".gbvec", std::ios::binary);
+    int32_t en = 0, ed = 0;
+    if (!ef || !rdv(ef, &en) || !rdv(ef, &ed) || en != maxd || ed != e.dim) return -1;
+    std::vector<float> erows((size_t)maxd * e.dim);
+    if (maxd && !ef.read(reinterpret_cast<char*>(erows.data()), (std::streamsize)(erows.size() * 4))) return -1;
+    if (maxd && e.index->add_vectors(erows.data(), maxd)) return -1;
+    IVFFlatIndex* eivf = dynamic_cast<IVFFlatIndex*>(e.index.get());
+    int64_t eload = 0;
+    if (eivf) eivf->load_gamma(dir, e.name + ".000", &eload);  // trained state + lists; absent: trained again later
+  }
   IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index_.get());
   IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index_.get());
   if (trained && ivf) {

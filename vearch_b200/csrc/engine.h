@@ -69,6 +69,7 @@ struct SearchRequestPB {  // c_api/api_data/request.{h,cc}
   int n_range_filters = 0, n_term_filters = 0;
   std::string index_params;
   int multi_vector_rank = 0;
+  std::string ranker;  // WeightedRanker JSON {"type": ..., "params": [w0, w1, ...]} (common_query_data.h:251-300)
   bool l2_sqrt = false;
   bool trace = false;
   int offset = 0;
@@ -132,7 +133,17 @@ class Engine {
   // ScalarIndexManager::Search (table/scalar_index_manager.cc:294-345, 588-651) as a scan of the
   // in-memory columns: dense LSB-first bitmap of the docids that pass; returns the cardinality
   int64_t eval_filters(const std::vector<SearchRequestPB::Filter>& filters, int op, std::vector<uint8_t>* bitmap) const;
-  void put_doc_fields(int docid, const std::vector<int>& attr, bool want_vec, PbWriter* item);
+  struct FieldSel {
+    std::vector<int> attr;           // table fields, in name order (std::map order of the reference)
+    std::vector<std::string> vecs;   // vector fields asked for by name
+  };
+  FieldSel select_fields(const std::vector<std::string>& names);  // requested ones, or every table field
+  void put_doc_fields(int docid, const FieldSel& sel, PbWriter* item);
+  // Response::Serialize (response.cc:89-162) for n queries x topN (score, docid) slots, -1 = empty
+  void serialize_results(const SearchRequestPB& req, int n, int topN, const float* dis, const int64_t* ids, int total_docs,
+                         std::string* pb_out);
+  // VectorManager::Search with several vector fields (vector_manager.cc:747, 900-964)
+  Status SearchMulti(const SearchRequestPB& req, std::string* pb_out);
   std::vector<FieldDef> fields_;
   std::unordered_map<std::string, int> field_idx_;
   std::vector<std::vector<std::string>> values_;  // [field][docid]
@@ -145,6 +156,16 @@ class Engine {
   std::unique_ptr<Index> index_;
   std::vector<float> pending_;  // rows accepted by AddOrUpdate, not yet uploaded to HBM
   int pending_n_ = 0;
+  // further vector fields of a multi-vector table (vector_manager.cc:343-453: one raw vector + one index
+  // per field).  The first field keeps the members above; every document carries all of them.
+  struct VecField {
+    std::string name, index_type, index_params;
+    int dim = 0;
+    std::unique_ptr<Index> index;
+    std::vector<float> pending;
+  };
+  std::vector<VecField> extra_;
+  Index* index_of(const std::string& vec_name, int* dim);  // nullptr: no such vector field
 
   std::vector<uint8_t> del_bitmap_;
   int max_docid_ = 0, delete_num_ = 0;

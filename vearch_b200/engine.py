@@ -107,11 +107,13 @@ class GammaEngine:
             self._h = None
 
     def create_table(self, name, dim, index_type, index_params, vec_name="emb", fields=(("_id", wire.DT_STRING, False),),
-                     refresh_interval=100, **kw):
+                     refresh_interval=100, extra_vectors=(), **kw):
+        """extra_vectors: further vector fields [(name, dim, index_type, index_params)] of a multi-vector table."""
         self.vec_name, self.dim = vec_name, dim
-        tb = wire.build_table(name, list(fields), [(vec_name, dim, "MemoryOnly", "")],
-                              [("idx", index_type, vec_name, json.dumps(index_params))],
-                              refresh_interval=refresh_interval, **kw)
+        vectors = [(vec_name, dim, "MemoryOnly", "")] + [(n, d, "MemoryOnly", "") for n, d, _, _ in extra_vectors]
+        indexes = [("idx", index_type, vec_name, json.dumps(index_params))] + \
+                  [(f"idx_{n}", t, n, json.dumps(p)) for n, _, t, p in extra_vectors]
+        tb = wire.build_table(name, list(fields), vectors, indexes, refresh_interval=refresh_interval, **kw)
         _status(_api().CreateTable(self._h, tb, len(tb)))
 
     def add_doc(self, key, vector, extra_fields=()):

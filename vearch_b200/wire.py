@@ -250,10 +250,13 @@ def _ld(num, payload):
 
 def encode_search_request(vec_name, queries, topn, index_params="", is_brute_search=0, fields=("_id",), request_id="",
                           partition_id=None, min_score=None, max_score=None, offset=0, trace=False, req_num=None,
-                          range_filters=(), term_filters=(), operator=0):
+                          range_filters=(), term_filters=(), operator=0, extra_vec_queries=(), ranker="",
+                          multi_vector_rank=0):
     """vearchpb.SearchRequest (internal/proto/router_grpc.proto:168-191). queries: float32 ndarray [nq, d].
     range_filters: (field, lower_bytes, upper_bytes, include_lower, include_upper[, is_union]);
-    term_filters: (field, value_bytes[, is_union]); operator: 0 And / 1 Or between the filters."""
+    term_filters: (field, value_bytes[, is_union]); operator: 0 And / 1 Or between the filters.
+    extra_vec_queries: further (vector field, queries) pairs of a multi-vector search; ranker: WeightedRanker JSON;
+    multi_vector_rank=1: order the joined documents by the combined score."""
     import numpy as np
     q = np.ascontiguousarray(queries, dtype=np.float32)
     out = bytearray()
@@ -278,6 +281,8 @@ def encode_search_request(vec_name, queries, topn, index_params="", is_brute_sea
     if max_score is not None and max_score != 0:
         vq += _key(4, 1) + struct.pack("<d", max_score)
     out += _ld(5, vq)
+    for ename, eq in extra_vec_queries:
+        out += _ld(5, _ld(1, ename.encode()) + _ld(2, np.ascontiguousarray(eq, dtype=np.float32).tobytes()))
     for f in fields:
         out += _ld(6, f.encode())
     for rf in range_filters:
@@ -286,6 +291,10 @@ def encode_search_request(vec_name, queries, topn, index_params="", is_brute_sea
         out += _ld(8, _enc_term_filter(tf))
     if index_params:
         out += _ld(9, index_params.encode())
+    if multi_vector_rank:
+        out += _key(10, 0) + _varint(multi_vector_rank)
+    if ranker:
+        out += _ld(15, ranker.encode())
     if trace:
         out += _key(16, 0) + _varint(1)
     if operator:
