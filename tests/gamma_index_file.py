@@ -24,10 +24,28 @@ def _index_header(d, ntotal, metric):
     return struct.pack("<iqqq?i", d, ntotal, 1 << 20, 1 << 20, True, metric)
 
 
-def _ivf_header(d, ntotal, metric, nlist, nprobe, centroids):
+def _hnsw_graph(n, m=4):
+    """faiss::HNSW as write_hnsw stores it (index/index_io.cc:196-212): five vectors, five ints.  A
+    syntactically valid single-level graph; readers that only want the centroids skip it."""
+    nb = 2 * m
+    neigh = np.full(n * nb, -1, np.int32)
+    for i in range(n):
+        neigh[i * nb] = (i + 1) % n
+    out = struct.pack("<Q", 1) + struct.pack("<d", 1.0)                       # assign_probas
+    out += struct.pack("<Q", 2) + struct.pack("<ii", 0, nb)                    # cum_nneighbor_per_level
+    out += struct.pack("<Q", n) + np.ones(n, np.int32).tobytes()               # levels
+    out += struct.pack("<Q", n + 1) + (np.arange(n + 1, dtype=np.uint64) * nb).tobytes()  # offsets
+    out += struct.pack("<Q", neigh.size) + neigh.tobytes()                     # neighbors
+    out += struct.pack("<iiiii", 0, 0, 40, 16, 1)   # entry_point, max_level, efConstruction, efSearch, upper_beam
+    return out
+
+
+def _ivf_header(d, ntotal, metric, nlist, nprobe, centroids, hnsw_quantizer=False):
     cent = np.ascontiguousarray(centroids, np.float32)
     assert cent.shape == (nlist, d)
     out = _index_header(d, ntotal, metric) + struct.pack("<QQ", nlist, nprobe)
+    if hnsw_quantizer:  # faiss::write_index(IndexHNSWFlat): "IHNf", header, graph, then the flat storage
+        out += fourcc("IHNf") + _index_header(d, nlist, metric) + _hnsw_graph(nlist)
     out += fourcc("IxF2" if metric == METRIC_L2 else "IxFI") + _index_header(d, nlist, metric)
     out += struct.pack("<Q", cent.size) + cent.tobytes()  # WRITEXBVECTOR: count in 4-byte units
     out += struct.pack("<bQ", 0, 0)                        # DirectMap::NoMap, empty array
@@ -48,11 +66,11 @@ def _inverted_lists(list_off, codes, ids, code_bytes):
     return out
 
 
-def write_ivfflat(d, metric, nprobe, centroids, list_off, vecs, ids, indexed_count):
+def write_ivfflat(d, metric, nprobe, centroids, list_off, vecs, ids, indexed_count, hnsw_quantizer=False):
     """vecs: [n, d] fp32 in list order; ids: int64 with the tombstone top bit."""
     nlist = len(list_off) - 1
     vecs = np.ascontiguousarray(vecs, np.float32).reshape(-1, d)
-    out = fourcc("IvFl") + _ivf_header(d, indexed_count, metric, nlist, nprobe, centroids)
+    out = fourcc("IvFl") + _ivf_header(d, indexed_count, metric, nlist, nprobe, centroids, hnsw_quantizer)
     out += _inverted_lists(list_off, vecs.view(np.uint8), ids, d * 4)
     out += struct.pack("<i", indexed_count)
     return out

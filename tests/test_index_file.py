@@ -100,6 +100,17 @@ def test_ivfflat_dump_is_byte_exact_and_loads_back(tmp_path, metric, d):
     assert np.array_equal(o2, off) and np.array_equal(c2, codes) and np.array_equal(i2, ids)
     got2 = idx2.search_preassigned(xq, k, keys, cd)
     assert np.array_equal(got2[0], ref[0]) and np.array_equal(got2[1], ref[1])
+    # a file whose coarse quantizer is an IndexHNSWFlat: the centroids are taken, the graph is skipped
+    hdir = tmp_path / "hnsw" / "emb.000"
+    hdir.mkdir(parents=True)
+    (hdir / "ivfflat.index").write_bytes(gif.write_ivfflat(d, faiss_metric(metric), nprobe, cent, off, vecs, ids, n,
+                                                          hnsw_quantizer=True))
+    idx4 = gi().GammaIndex("IVFFLAT", d, params)
+    idx4.add_vectors(db2)
+    assert idx4.load(tmp_path / "hnsw", "emb.000") == n and np.array_equal(idx4.get_centroids(), cent)
+    got4 = idx4.search_preassigned(xq, k, keys, cd)
+    assert np.array_equal(got4[0], ref[0]) and np.array_equal(got4[1], ref[1])
+    idx4.close()
     # the loaded index keeps working: realtime adds and an update that must find vid -> (list, pos)
     more = synth.sift_like(500, d, seed=73)
     idx2.add_vectors(more)

@@ -17,7 +17,8 @@
 //   lists      : u32 "ilar", u64 nlist, u64 code_bytes, u32 "full", u64 nlist, u64 sizes[nlist],
 //                per non-empty list: codes[size * code_bytes], i64 ids[size] (top bit = tombstone)
 //   IvFl only  : i32 indexed_count
-// HNSW coarse quantisers ("IHNf") and OPQ are rejected with an error: SURVEY 8f N-4.
+// An IndexHNSWFlat coarse quantiser ("IHNf") is read for its centroids (the graph is skipped: the coarse
+// search here is exact); Dump always writes the IndexFlat form.  OPQ blocks are rejected: SURVEY 8f N-4.
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
@@ -169,8 +170,23 @@ int IVFFlatIndex::load_gamma(const std::string& dir, const std::string& abs_name
     return fail("index file does not match the table: d=" + std::to_string(ih.d) + " nlist=" + std::to_string(nlist));
   if ((ih.metric == 1 ? kMetricL2 : kMetricIP) != mp_.metric) return fail("index file metric differs from the table's");
   if (!rd(f, &h)) return fail("truncated quantizer in " + path);
+  if (h == fourcc("IHNf")) {
+    // IndexHNSWFlat coarse quantizer (quantizer_type 1, gamma_index_ivfflat.cc:252-263): index header,
+    // the HNSW graph (write_hnsw, index_io.cc:196-212: five vectors, five ints), then the IndexFlat that
+    // stores the centroids.  The graph only approximates "nearest centroids"; this engine finds them
+    // exactly with one dense tensor-core contraction, so the graph is skipped and the centroids are kept.
+    IndexHeader hh;
+    if (!rd_index_header(f, &hh)) return fail("truncated HNSW quantizer in " + path);
+    const size_t elem[5] = {8, 4, 4, 8, 4};  // assign_probas, cum_nneighbor_per_level, levels, offsets, neighbors
+    for (size_t e : elem) {
+      uint64_t cnt = 0;
+      if (!rd(f, &cnt) || cnt > ((uint64_t)1 << 40) || fseek(f, (long)(cnt * e), SEEK_CUR)) return fail("bad HNSW graph in " + path);
+    }
+    int32_t scalars[5];  // entry_point, max_level, efConstruction, efSearch, (deprecated) upper_beam
+    if (!rd_bytes(f, scalars, sizeof scalars) || !rd(f, &h)) return fail("truncated HNSW quantizer in " + path);
+  }
   if (h != fourcc("IxF2") && h != fourcc("IxFI") && h != fourcc("IxFl"))
-    return fail("unsupported coarse quantizer in " + path + " (only IndexFlat; HNSW: SURVEY 8f N-4)");
+    return fail("unsupported coarse quantizer in " + path + " (IndexFlat, or IndexHNSWFlat over IndexFlat)");
   if (!rd_index_header(f, &qh) || !rd(f, &n) || qh.d != d_ || qh.ntotal != nlist_ || n != (uint64_t)nlist_ * d_)
     return fail("bad quantizer in " + path);
   std::vector<float> cent((size_t)nlist_ * d_);
