@@ -136,10 +136,10 @@ def measured_peak(kind="hbm"):
     return 2250.0, "fallback (nominal dense bf16 2.25 PFLOP/s)"
 
 
-def ncu_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+def ncu_traffic(workload, kernel):
+    """dram bytes per launch of `kernel` on `workload` from the committed ncu --set full capture, or None."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(workload, {}).get(kernel)
     except Exception:
         return None
 
@@ -473,7 +473,7 @@ def main():
         aflops = detail["entries"] * 2.0 * wl["d"]
         achieved = aflops / (scan_avg / 1000) / 1e12 if scan_avg > 0 else None
         roofline = {"bound": "tensor", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(kname),
+                    "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload if not (args.n or args.nq or args.nprobe) else "", kname),
                     "peak_source": peak_src, "algorithmic_flops_per_launch": aflops, "mma_kind": "tf32 x3 (kind::tf32 peak is "
                     "half the bf16 figure)", "algorithmic_bytes_per_launch": abytes, "kernel_ms": scan_avg,
                     "kernel_share_of_step": scan_avg / ms_per_step if ms_per_step else None}
@@ -481,7 +481,7 @@ def main():
         peak, peak_src = measured_peak("hbm")
         achieved = abytes / (scan_avg / 1000) / 1e9 if scan_avg > 0 else None
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(kname), "peak_source": peak_src,
+                    "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(args.workload if not (args.n or args.nq or args.nprobe) else "", kname), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": abytes, "kernel_ms": scan_avg,
                     "kernel_share_of_step": scan_avg / ms_per_step if ms_per_step else None}
         if achieved and achieved > peak:

@@ -86,9 +86,10 @@ def traffic(out_path):
 
     out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures "
                        "summarised in this directory (profiles/r1_capture.sh)",
-           "ivfpq_scan_kernel": dram("r1_ncu_ivfpq_scan.txt"),
-           "ivf_listmajor_tma_kernel": dram("r1_ncu_ivfflat_listmajor.txt"),
-           "ivfflat_scan_warp_kernel": dram("r1_ncu_ivfflat_scan_querymajor.txt")}
+           # keyed by bench workload, then by the kernel the bench timed: a capture only speaks for its own workload
+           "ivfpq_10m": {"ivfpq_scan_kernel": dram("r1_ncu_ivfpq_scan.txt")},
+           "ivfflat_1m": {"ivf_listmajor_tma_kernel": dram("r1_ncu_ivfflat_listmajor.txt"),
+                          "ivfflat_scan_warp_kernel": dram("r1_ncu_ivfflat_scan_querymajor.txt")}}
     json.dump(out, open(out_path, "w"), indent=1)
     print(out)
 
