@@ -76,9 +76,9 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 // registers (global loads issued one chunk ahead) and write it into the other stage, so neither the
 // global-load latency nor the MMA latency sits on the critical path.
 struct TcShared {
+  alignas(16) float cn[TC_N];  // |y|^2 of the tile's rows (read as float4 by the fused epilogues)
   uint64_t mma_bar[TC_STAGES];
   uint32_t tmem_base;
-  float cn[TC_N];
 };
 
 // allocate TMEM (TC_N fp32 columns), initialise the stage barriers; returns the TMEM base address
@@ -374,6 +374,34 @@ __device__ __noinline__ LmkState lmk_consider(unsigned long long* hk, int k, uin
   return st;
 }
 
+// 32 accumulator columns of one pair (thread): turn them into scores in place and collect, branch-free, one
+// bit per column that beats the bound the block started with; only then visit the hits (the rare path
+// re-checks every hit against the live bound).  cn32 / vid32: the columns' |y|^2 (16-byte aligned) and row ids.
+template <int METRIC>
+__device__ __forceinline__ void lmk_scan_block(uint32_t (&v)[32], float xn, const float* cn32, const uint32_t* vid32,
+                                               unsigned long long* hk, int k, float min_score, float max_score,
+                                               LmkState& st, float& bound) {
+  uint32_t hit = 0;
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    const float4 c4 = *reinterpret_cast<const float4*>(cn32 + j4);
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const float sc = tc_score<METRIC>(__uint_as_float(v[j4 + u]), xn, cc[u]);
+      v[j4 + u] = __float_as_uint(sc);
+      hit |= (METRIC == kMetricL2 ? sc <= bound : sc >= bound) ? (1u << (j4 + u)) : 0u;
+    }
+  }
+  if (hit) {
+#pragma unroll
+    for (int jj = 0; jj < 32; jj++) {
+      if (hit & (1u << jj)) st = lmk_consider<METRIC>(hk, k, vid32[jj], __uint_as_float(v[jj]), min_score, max_score, st);
+    }
+    bound = key_bound<METRIC>(st.tau);
+  }
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(TC_NT)
     ivf_listmajor_topk_kernel(const float* __restrict__ xq, int64_t ldq, int d, const LmTile* __restrict__ items,
@@ -422,14 +450,7 @@ __global__ void __launch_bounds__(TC_NT)
     for (int c0 = 0; c0 < TC_N; c0 += 32) {
       uint32_t v[32];
       tc_load32(tmem_d, c0, v);
-#pragma unroll
-      for (int jj = 0; jj < 32; jj++) {
-        const float s = tc_score<METRIC>(__uint_as_float(v[jj]), xn, sh.cn[c0 + jj]);
-        if (METRIC == kMetricL2 ? s <= bound : s >= bound) {
-          st = lmk_consider<METRIC>(hk, k, s_vid[c0 + jj], s, f.min_score, f.max_score, st);
-          bound = key_bound<METRIC>(st.tau);
-        }
-      }
+      lmk_scan_block<METRIC>(v, xn, &sh.cn[c0], &s_vid[c0], hk, k, f.min_score, f.max_score, st, bound);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // next tile's MMAs overwrite the accumulator
     if (valid) {  // exchange bounds with the other CTAs working on this query
@@ -537,28 +558,7 @@ __global__ void __launch_bounds__(LW_NT, 2)
       for (int c0 = 0; c0 < TC_N; c0 += 32) {
         uint32_t v[32];
         tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
-        // branch-free pass over the 32 columns: scores in place, one bit per column that beats the
-        // bound this block started with (the rare path re-checks against the live bound)
-        uint32_t hit = 0;
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(&sh.cn[b][c0 + j4]);
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float sc = tc_score<METRIC>(__uint_as_float(v[j4 + u]), xn, cc[u]);
-            v[j4 + u] = __float_as_uint(sc);
-            hit |= (METRIC == kMetricL2 ? sc <= bound : sc >= bound) ? (1u << (j4 + u)) : 0u;
-          }
-        }
-        if (hit) {
-#pragma unroll
-          for (int jj = 0; jj < 32; jj++) {
-            if (hit & (1u << jj))
-              st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
-          }
-          bound = key_bound<METRIC>(st.tau);
-        }
+        lmk_scan_block<METRIC>(v, xn, &sh.cn[b][c0], &sh.vid[b][c0], hk, k, f.min_score, f.max_score, st, bound);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&sh.acc_empty[b]);  // accumulator b, cn[b], vid[b] may be overwritten
@@ -817,26 +817,7 @@ __global__ void __launch_bounds__(LT_NT, 2)
       for (int c0 = 0; c0 < TC_N; c0 += 32) {
         uint32_t v[32];
         tc_load32(tmem_d + (uint32_t)(b * TC_N), c0, v);
-        uint32_t hit = 0;
-#pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          const float4 c4 = *reinterpret_cast<const float4*>(&sh.cn[b][c0 + j4]);
-          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float sc = tc_score<METRIC>(__uint_as_float(v[j4 + u]), xn, cc[u]);
-            v[j4 + u] = __float_as_uint(sc);
-            hit |= (METRIC == kMetricL2 ? sc <= bound : sc >= bound) ? (1u << (j4 + u)) : 0u;
-          }
-        }
-        if (hit) {
-#pragma unroll
-          for (int jj = 0; jj < 32; jj++) {
-            if (hit & (1u << jj))
-              st = lmk_consider<METRIC>(hk, k, sh.vid[b][c0 + jj], __uint_as_float(v[jj]), f.min_score, f.max_score, st);
-          }
-          bound = key_bound<METRIC>(st.tau);
-        }
+        lmk_scan_block<METRIC>(v, xn, &sh.cn[b][c0], &sh.vid[b][c0], hk, k, f.min_score, f.max_score, st, bound);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&sh.acc_empty[b]);
