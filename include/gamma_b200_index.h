@@ -105,6 +105,9 @@ int gb_index_dump(gb_index *index, const char *dir, const char *abs_name);
  * realtime_mem_data.cc never give memory back; neither do ours until this runs).  Also done
  * automatically after a bulk add when more than half of the list memory is dead. */
 int gb_index_compact(gb_index *index);
+/* test hook: how often the tensor-core mirror of the lists was built in full; appends
+ * that fit the reserved tiles update it in place and do not count */
+int gb_index_mirror_builds(gb_index *index);
 int gb_index_load(gb_index *index, const char *dir, const char *abs_name, int64_t *load_num);
 /* quantizer->search (gamma_index_ivfflat.cc:568) */
 int gb_index_coarse_search(gb_index *index, int nq, const float *x, int nprobe, float *out_dis, int64_t *out_ids);

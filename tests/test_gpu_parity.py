@@ -651,3 +651,34 @@ def test_listmajor_mirror_survives_concurrent_adds_and_searches():
     dg, ig = idx.search(db[n0 + 3000:n0 + 3300], 1, params={"nprobe": nlist})
     assert np.all(dg[:, 0] == 0) and np.all(np.all(db[ig[:, 0]] == db[n0 + 3000:n0 + 3300], axis=1))
     idx.close()
+
+
+def test_listmajor_mirror_is_updated_in_place_by_small_appends():
+    """The pre-tiled mirror reserves 1/8 more rows per list: appends that fit go in place (no rebuild),
+    and what they added is found by the next list-major search; outgrowing the reserve rebuilds once."""
+    d, nlist, n0 = 64, 8, 16000
+    db = synth.sift_like(n0 + 12000, d, seed=61)
+    cent, _, _ = orc.kmeans(db[:3000], nlist, niter=4)
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": nlist, "metric_type": "L2"})
+    idx.set_centroids(cent)
+    idx.add_vectors(db[:n0])
+    idx.add_pending()
+
+    def finds_itself(a, b):
+        dg, ig = idx.search(db[a:b], 1, params={"nprobe": nlist})
+        assert idx.last_scan_kernel == "ivf_listmajor_tma_kernel"
+        return bool(np.all(dg[:, 0] == 0) and np.all(np.all(db[ig[:, 0]] == db[a:b], axis=1)))
+
+    assert finds_itself(0, 300) and idx.mirror_builds == 1
+    for a in range(n0, n0 + 600, 200):  # 600 rows over 8 lists: well inside the reserve
+        idx.add_vectors(db[a:a + 200])
+        idx.add_pending()
+        assert finds_itself(a, a + 200) and finds_itself(100, 400)
+    assert idx.mirror_builds == 1
+    idx.update_vector(5, db[n0 + 700])  # tombstone + re-append goes through the same path
+    dg, ig = idx.search(np.repeat(db[n0 + 700:n0 + 701], 300, axis=0), 1, params={"nprobe": nlist})
+    assert np.all(dg[:, 0] == 0) and idx.mirror_builds == 1
+    idx.add_vectors(db[n0 + 600:n0 + 11000])  # far beyond the reserve
+    idx.add_pending()
+    assert finds_itself(n0 + 10000, n0 + 10300) and idx.mirror_builds == 2
+    idx.close()

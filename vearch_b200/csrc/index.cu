@@ -973,6 +973,7 @@ int IVFFlatIndex::index_batch(const float* x, int64_t n, int64_t vid0, const uin
   if (lists_->reserve(add, st)) return -1;
   if (append_batch(x, n, vid0, d_list, d_pos, d_assign, s)) return -1;
   if (lists_->commit(add, st)) return -1;
+  if (type_ == "IVFFLAT" && mirror_append(x, n, d_list, d_pos, add, st)) return -1;
   GB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1074,6 +1075,25 @@ static bool tma_enabled() {  // GB_TC_MIRROR=0: never build the pre-tiled mirror
   return v != 0;
 }
 
+// called from index_batch with mu_ held exclusively: no search is inside ensure_mirror.  Kernels of an
+// earlier search_device may still be running, but they only look at rows below the lengths they were
+// launched with, and the rows written here lie above those.
+int IVFFlatIndex::mirror_append(const float* x, int64_t n, const int32_t* d_list, const int32_t* d_pos,
+                                const std::vector<int>& add, cudaStream_t st) {
+  if (!mirror_.base || mirror_.disabled || mirror_.lens.size() != (size_t)nlist_) return 0;
+  const std::vector<int>& lens = lists_->lens();  // already includes `add`
+  for (int l = 0; l < nlist_; l++) {
+    if (mirror_.lens[l] + add[l] != lens[l] || lens[l] > (int64_t)mirror_.list_tiles[l] * 128) {
+      mirror_.lens.clear();  // stale: outgrown (or out of step); rebuilt by the next list-major search
+      return 0;
+    }
+  }
+  GB_CUDA(launch_tc_mirror_append(x, dpad_, n, dpad_, (int)round_up(dpad_, 16), d_list, d_pos, mirror_.d_tile0, mirror_.base,
+                                  mirror_.norms, st));
+  mirror_.lens = lens;
+  return 0;
+}
+
 int IVFFlatIndex::ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStream_t st) {
   if (type_ != "IVFFLAT" || !lists_) return 1;
   lk.lock();
@@ -1084,30 +1104,39 @@ int IVFFlatIndex::ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStr
     std::unique_lock<std::shared_mutex> x(mirror_rw_);
     if (!mirror_.disabled && !(mirror_.base && mirror_.lens == lists_->lens())) {
       const std::vector<int>& lens = lists_->lens();
-      std::vector<int64_t> tile0(nlist_ + 1, 0);
-      for (int l = 0; l < nlist_; l++) tile0[l + 1] = tile0[l] + (lens[l] + 127) / 128;
-      const int64_t tiles = tile0[nlist_];
       const int k16 = (int)round_up(dpad_, 16);
       const size_t tile_bytes = (size_t)tc_mirror_tile_floats(k16) * 4;
       cudaDeviceSynchronize();  // kernels of other searches may still be reading the mirror
-      if (tiles > mirror_.cap_tiles) {
-        if (mirror_.base) cudaFree(mirror_.base);
-        if (mirror_.norms) cudaFree(mirror_.norms);
-        mirror_.base = mirror_.norms = nullptr;
-        mirror_.cap_tiles = 0;
-        const int64_t cap = tiles + tiles / 8 + 16;
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        const size_t need = (size_t)cap * (tile_bytes + 512);
-        if (need + ((size_t)4 << 30) > free_b || cudaMalloc(&mirror_.base, (size_t)cap * tile_bytes) != cudaSuccess ||
-            cudaMalloc(&mirror_.norms, (size_t)cap * 512) != cudaSuccess) {
+      if (mirror_.base) cudaFree(mirror_.base);
+      if (mirror_.norms) cudaFree(mirror_.norms);
+      mirror_.base = mirror_.norms = nullptr;
+      mirror_.cap_tiles = 0;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      std::vector<int64_t> tile0(nlist_ + 1, 0);
+      std::vector<int> list_tiles(nlist_, 0);
+      int64_t tiles = 0;
+      for (int slack = 8; slack >= 0 && !mirror_.base; slack -= 8) {  // 1/8 more rows per list, else none
+        for (int l = 0; l < nlist_; l++) {
+          const int64_t rows = slack ? (int64_t)lens[l] + lens[l] / slack : lens[l];
+          list_tiles[l] = (int)((rows + 127) / 128);
+          tile0[l + 1] = tile0[l] + list_tiles[l];
+        }
+        tiles = tile0[nlist_];
+        const size_t need = (size_t)std::max<int64_t>(tiles, 1) * (tile_bytes + 512);
+        if (need + ((size_t)4 << 30) > free_b) continue;
+        if (cudaMalloc(&mirror_.base, (size_t)std::max<int64_t>(tiles, 1) * tile_bytes) != cudaSuccess ||
+            cudaMalloc(&mirror_.norms, (size_t)std::max<int64_t>(tiles, 1) * 512) != cudaSuccess) {
           if (mirror_.base) cudaFree(mirror_.base);
           mirror_.base = nullptr;
           cudaGetLastError();
-          mirror_.disabled = true;  // HBM too full for a second, doubled copy of the lists
-        } else {
-          mirror_.cap_tiles = cap;
         }
+      }
+      if (!mirror_.base) {
+        mirror_.disabled = true;  // HBM too full for a second, doubled copy of the lists
+      } else {
+        mirror_.cap_tiles = tiles;
+        mirror_.list_tiles = list_tiles;
       }
       if (!mirror_.disabled) {
         if (!mirror_.d_tile0 && cudaMalloc(&mirror_.d_tile0, sizeof(int64_t) * (nlist_ + 1)) != cudaSuccess) return -1;
@@ -1117,6 +1146,7 @@ int IVFFlatIndex::ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStr
         GB_CUDA(cudaStreamSynchronize(st));  // tile0 is a stack vector; other streams may use the mirror next
         mirror_.tiles = tiles;
         mirror_.lens = lens;
+        mirror_.builds++;
       }
     }
   }

@@ -305,6 +305,7 @@ class IVFFlatIndex : public Index {
   // re-pack the inverted lists into one tight slab (IvfLists::compact); also done automatically after
   // a bulk add_pending when more than half of the slab space is dead
   int compact_lists();
+  int mirror_builds() const { return mirror_.builds; }  // test hook
   int dump_gamma(const std::string& dir, const std::string& abs_name);
   int load_gamma(const std::string& dir, const std::string& abs_name, int64_t* load_num);
 
@@ -346,9 +347,15 @@ class IVFFlatIndex : public Index {
     float* norms = nullptr;
     int64_t* d_tile0 = nullptr;
     int64_t tiles = 0, cap_tiles = 0;
-    std::vector<int> lens;
+    std::vector<int> lens;        // rows mirrored per list
+    std::vector<int> list_tiles;  // tiles reserved per list (a little slack, so appends go in place)
     bool disabled = false;
+    int builds = 0;  // full (re)builds so far
   } mirror_;
+  // appends keep the mirror current in place while the reserved tiles last; otherwise it goes stale and the
+  // next list-major search rebuilds it
+  int mirror_append(const float* x, int64_t n, const int32_t* d_list, const int32_t* d_pos, const std::vector<int>& add,
+                    cudaStream_t st);
   std::shared_mutex mirror_rw_;
   int ensure_mirror(std::shared_lock<std::shared_mutex>& lk, cudaStream_t st);  // 0 = usable and current
 };

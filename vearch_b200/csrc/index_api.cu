@@ -282,6 +282,11 @@ int gb_index_get_precomputed_table(gb_index* index, float* table) {
   PQ_OR_FAIL(pq, index);
   return pq->get_precomputed_table(table);
 }
+int gb_index_mirror_builds(gb_index* index) {
+  if (!index || !index->impl) return -1;
+  IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index->impl);
+  return ivf ? ivf->mirror_builds() : 0;
+}
 int gb_index_compact(gb_index* index) {
   IDX_OR_FAIL(index);
   IVFFlatIndex* ivf = dynamic_cast<IVFFlatIndex*>(index->impl);

@@ -110,6 +110,9 @@ struct TcMirrorView {
   int k16;               // row length rounded up to the K chunk (16)
 };
 inline int64_t tc_mirror_tile_floats(int k16) { return (int64_t)128 * k16 * 2; }
+// rows just appended to the lists (row i of x -> position pos[i] of list list[i], list < 0: skipped)
+cudaError_t launch_tc_mirror_append(const float* x, int64_t ldx, int64_t n, int d, int k16, const int32_t* list,
+                                    const int32_t* pos, const int64_t* tile0, float* mirror, float* norms, cudaStream_t st);
 cudaError_t launch_tc_mirror_build(ListDirectory dir, int d, int k16, const int64_t* tile0, int64_t total_tiles,
                                    float* mirror, float* norms, cudaStream_t st);
 // a_scratch: per pair group nk chunks of 16 KiB (hi, lo) of the group's 128 queries; a_norms: [group][128]

@@ -939,6 +939,19 @@ __global__ void __launch_bounds__(TC_N)
   norms[gt * TC_N + r] = tc_split_row(src, d, k16, r, mirror + gt * ((int64_t)TC_N * k16 * 2));
 }
 
+__global__ void tc_mirror_append_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d, int k16,
+                                        const int32_t* __restrict__ list, const int32_t* __restrict__ pos,
+                                        const int64_t* __restrict__ tile0, float* __restrict__ mirror,
+                                        float* __restrict__ norms) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = list[i];
+  if (l < 0) return;
+  const int p = pos[i];
+  const int64_t gt = tile0[l] + p / TC_N;
+  norms[gt * TC_N + p % TC_N] = tc_split_row(x + i * ldx, d, k16, p % TC_N, mirror + gt * ((int64_t)TC_N * k16 * 2));
+}
+
 __global__ void __launch_bounds__(TC_M)
     lm_stage_queries_kernel(const float* __restrict__ xq, int64_t ldq, int d, int k16, const LmTile* __restrict__ items,
                             const int64_t* __restrict__ totals, const int64_t* __restrict__ pair_j, int nprobe,
@@ -1287,6 +1300,14 @@ cudaError_t launch_tc_mirror_build(ListDirectory dir, int d, int k16, const int6
   if (total_tiles <= 0) return cudaSuccess;
   if (total_tiles > INT32_MAX || (d & 3) || (k16 % TC_BK)) return cudaErrorInvalidValue;
   tc_mirror_build_kernel<<<(unsigned)total_tiles, TC_N, 0, st>>>(dir, d, k16, tile0, mirror, norms);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tc_mirror_append(const float* x, int64_t ldx, int64_t n, int d, int k16, const int32_t* list,
+                                    const int32_t* pos, const int64_t* tile0, float* mirror, float* norms, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  tc_mirror_append_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(x, ldx, n, d, k16, list, pos, tile0, mirror, norms);
   note_launch();
   return cudaGetLastError();
 }

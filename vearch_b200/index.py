@@ -232,6 +232,10 @@ class GammaIndex:
                 ids[off[l]:off[l + 1]] = i
         return off, codes, ids
 
+    @property
+    def mirror_builds(self):
+        return int(_lib.lib().gb_index_mirror_builds(self._h))
+
     def compact(self):
         _check(_lib.lib().gb_index_compact(self._h), "compact")
 
