@@ -339,9 +339,10 @@ class IVFFlatIndex : public Index {
 
   // Tensor-core mirror of the lists (IVFFLAT only; kernels_tc.cu): every list once more, pre-split and
   // pre-tiled in the shared-memory operand layout so the list-major kernel is fed by cp.async.bulk.
-  // Rebuilt lazily by the first list-major search after the lists grew; users hold mirror_rw_ shared
-  // from the freshness check until their kernels are enqueued, the rebuilder takes it exclusively and
-  // drains the device first.  Skipped (register-staged kernel instead) when HBM is too full for it.
+  // Built by the first list-major search, kept current in place by appends that fit its reserve,
+  // rebuilt when a list outgrows it; users hold mirror_rw_ shared from the freshness check until their
+  // kernels are enqueued, the rebuilder takes it exclusively and drains the device first.  Skipped
+  // (register-staged kernel instead) when HBM is too full for it.
   struct TcMirror {
     float* base = nullptr;
     float* norms = nullptr;
