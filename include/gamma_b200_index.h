@@ -89,6 +89,12 @@ int gb_index_pq_m(gb_index *index);
 int gb_index_set_pq_centroids(gb_index *index, const float *pq); /* [M][256][dsub] */
 int gb_index_get_pq_centroids(gb_index *index, float *pq);
 int gb_index_get_precomputed_table(gb_index *index, float *table); /* [nlist][M][256] */
+/* OPQ rotation of an IVFPQ index created with "opq": {"nsubvector": M} (gamma_index_ivfpq.cc:168-178):
+ * A is d x d row-major, y = A x; apply runs the device path the index itself uses */
+int gb_index_has_opq(gb_index *index);
+int gb_index_set_opq(gb_index *index, const float *A);
+int gb_index_get_opq(gb_index *index, float *A);
+int gb_index_apply_opq(gb_index *index, int64_t n, const float *x, float *out);
 int gb_index_list_len(gb_index *index, int list);
 int gb_index_code_size(gb_index *index);
 /* copy one inverted list to the host: codes = len x code_size bytes, ids = len int64 */

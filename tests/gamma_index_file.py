@@ -76,13 +76,19 @@ def write_ivfflat(d, metric, nprobe, centroids, list_off, vecs, ids, indexed_cou
     return out
 
 
-def write_ivfpq(d, metric, nprobe, centroids, pq_centroids, list_off, codes, ids, ntotal):
+def write_ivfpq(d, metric, nprobe, centroids, pq_centroids, list_off, codes, ids, ntotal, opq=None):
+    """opq: d x d rotation (row-major, y = A x) written as the LinearTransform block of write_opq
+    (index/index_io.cc:230-246) between the product quantizer and the lists."""
     nlist = len(list_off) - 1
     pq = np.ascontiguousarray(pq_centroids, np.float32)
     M = pq.shape[0]
     assert pq.shape == (M, 256, d // M)
     out = fourcc("IwPQ") + _ivf_header(d, ntotal, metric, nlist, nprobe, centroids)
     out += struct.pack("<?QQQQQ", True, M, d, M, 8, pq.size) + pq.tobytes()
+    if opq is not None:
+        A = np.ascontiguousarray(opq, np.float32)
+        assert A.shape == (d, d)
+        out += fourcc("LTra") + struct.pack("<?Q", False, A.size) + A.tobytes() + struct.pack("<Qii?", 0, d, d, True)
     out += _inverted_lists(list_off, codes, ids, M)
     return out
 

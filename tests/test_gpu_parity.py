@@ -682,3 +682,55 @@ def test_listmajor_mirror_is_updated_in_place_by_small_appends():
     idx.add_pending()
     assert finds_itself(n0 + 10000, n0 + 10300) and idx.mirror_builds == 2
     idx.close()
+
+
+def test_ivfpq_opq_rotation_train_apply_search_and_file(tmp_path):
+    """"opq": {"nsubvector": M} (gamma_index_ivfpq.cc:168-178, 362-364, 470, 585-590): an orthonormal rotation is
+    learnt in front of the PQ, vectors and queries pass through it, the exact re-rank keeps using the raw
+    vectors, and the rotation travels in the index file as the reference's "LTra" block."""
+    import gamma_index_file as gif
+    d, n, nlist, M = 32, 20000, 32, 8
+    db = synth.sift_like(n, d, seed=83)
+    xq = synth.sift_like(100, d, seed=84)
+    base = {"ncentroids": nlist, "nprobe": 8, "nsubvector": M, "metric_type": "L2", "training_threshold": 8000}
+    plain = gi().GammaIndex("IVFPQ", d, base)
+    opq = gi().GammaIndex("IVFPQ", d, dict(base, opq={"nsubvector": M}))
+    with pytest.raises(gi().GammaError):
+        gi().GammaIndex("IVFPQ", d, dict(base, opq={"nsubvector": 5}))  # d % nsubvector != 0
+    assert opq.has_opq and not plain.has_opq
+    for idx in (plain, opq):
+        idx.add_vectors(db)
+        idx.train()
+        idx.add_pending()
+        assert idx.indexed_count == n
+    A = opq.get_opq()
+    assert np.allclose(A @ A.T, np.eye(d), atol=2e-5)  # orthonormal: distances are preserved
+    xr = opq.apply_opq(xq)
+    assert np.allclose(xr, xq @ A.T, rtol=1e-5, atol=1e-3)
+    _, gt = orc.flat_search(db, xq, 1, L2)
+    r_plain = recall_1nn(plain.search(xq, 10)[1], gt[:, 0], 10)
+    r_opq = recall_1nn(opq.search(xq, 10)[1], gt[:, 0], 10)
+    assert r_opq >= r_plain - 0.05 and r_opq >= 0.5  # the rotation must not hurt the ADC ranking
+    dr, ir = opq.search(xq, 10, params={"recall_num": 100})
+    assert np.array_equal(((xq[:, None, :] - db[ir]) ** 2).sum(-1), dr)  # re-rank: raw queries x raw vectors
+    assert recall_1nn(ir, gt[:, 0], 10) >= 0.9
+    # parity with the oracle on the device-built state: same rotated queries, same probes => same ADC results
+    off, codes, ids = opq.export_lists()
+    cent, pqc, T = opq.get_centroids(), opq.get_pq_centroids(), opq.get_precomputed_table()
+    cd, keys = opq.coarse_search(xq, 8)  # coarse search happens on the rotated queries
+    cdo, keyso = orc.coarse_search(cent, xr, 8, L2)
+    assert np.array_equal(keys, keyso)
+    dg, ig = opq.search_preassigned(xq, 50, keys, cd)
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids, cent, pqc, T, xr, 50, keys, cd, L2)
+    assert_same_results(dg, ig, do, io)
+    # index file: byte-identical to the independent writer, and it loads back with the rotation
+    opq.dump(tmp_path, "emb.000")
+    with open(tmp_path / "emb.000" / "ivfpq.index", "rb") as fh:
+        assert fh.read() == gif.write_ivfpq(d, gif.METRIC_L2, 8, cent, pqc, off, codes, ids, n, opq=A)
+    again = gi().GammaIndex("IVFPQ", d, dict(base, opq={"nsubvector": M}))
+    again.add_vectors(db)
+    assert again.load(tmp_path, "emb.000") == n and np.array_equal(again.get_opq(), A)
+    d2, i2 = again.search_preassigned(xq, 50, keys, cd)
+    assert np.array_equal(d2, dg) and np.array_equal(i2, ig)
+    for idx in (plain, opq, again):
+        idx.close()

@@ -64,6 +64,10 @@ def _declare(l):
     l.gb_index_set_pq_centroids.argtypes = [vp, vp]
     l.gb_index_get_pq_centroids.argtypes = [vp, vp]
     l.gb_index_get_precomputed_table.argtypes = [vp, vp]
+    l.gb_index_has_opq.argtypes = [vp]
+    l.gb_index_set_opq.argtypes = [vp, vp]
+    l.gb_index_get_opq.argtypes = [vp, vp]
+    l.gb_index_apply_opq.argtypes = [vp, i64, vp, vp]
     l.gb_index_list_len.argtypes = [vp, i32]
     l.gb_index_code_size.argtypes = [vp]
     l.gb_index_get_list.argtypes = [vp, i32, vp, vp]

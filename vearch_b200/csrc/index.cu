@@ -768,13 +768,15 @@ int kmeans_device(const float* x_in, int64_t ldx_in, int64_t n_in, int d, int k,
     x = xs;
     ldx = dpad;
   }
-  // initial centroids = first k entries of a seeded permutation
-  rand_perm_mt(perm, n, kp.seed + 1);
+  // initial centroids = first k entries of a seeded permutation (or the caller's, for a hot start)
   GB_ALLOC(d_perm, int32_t, n, s);
   GB_ALLOC(d_off, int32_t, k + 1, s);
-  GB_CUDA(cudaMemcpyAsync(d_perm, perm.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
-  GB_CUDA(launch_gather_rows(x, ldx, d_perm, k, d, centroids, ldc, st));
-  if (kp.spherical) GB_CUDA(launch_normalize_rows(centroids, ldc, k, d, st));
+  if (!kp.hot_start) {
+    rand_perm_mt(perm, n, kp.seed + 1);
+    GB_CUDA(cudaMemcpyAsync(d_perm, perm.data(), (size_t)k * 4, cudaMemcpyHostToDevice, st));
+    GB_CUDA(launch_gather_rows(x, ldx, d_perm, k, d, centroids, ldc, st));
+    if (kp.spherical) GB_CUDA(launch_normalize_rows(centroids, ldc, k, d, st));
+  }
   GB_CUDA(cudaStreamSynchronize(st));
 
   GB_ALLOC(best, unsigned long long, n, s);
@@ -914,6 +916,8 @@ int IVFFlatIndex::train() {
   const bool is_pq = (type_ == "IVFPQ");
   kp.niter = is_pq ? 10 : 25;                              // gamma_index_ivfpq.cc:188
   kp.spherical = is_pq && mp_.metric == kMetricIP;          // gamma_index_ivfpq.cc:189-191
+  xt = train_transform(xt, num, s);  // OPQ: learn the rotation, continue on the rotated slab
+  if (!xt) return -1;
   if (kmeans_device(xt, dpad_, num, d_, nlist_, kp, d_centroids_, dpad_, st, nullptr)) return -1;
   if (train_extra(xt, num, s)) return -1;
   GB_CUDA(cudaStreamSynchronize(st));
@@ -944,6 +948,8 @@ int IVFFlatIndex::append_batch(const float* x, int64_t n, int64_t vid0, const in
 int IVFFlatIndex::index_batch(const float* x, int64_t n, int64_t vid0, const uint8_t* del_bitmap) {
   cudaStream_t st = build_stream_;
   Scratch s(st);
+  x = transform_dev(x, n, s);  // OPQ rotation; the raw store keeps the original rows
+  if (!x) return -1;
   GB_ALLOC(d_assign, int32_t, n, s);
   if (assign_dev(x, dpad_, n, d_assign, s)) return -1;
   std::vector<int32_t> h_list(n), h_pos(n);
@@ -1264,9 +1270,23 @@ int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int me
   return 0;
 }
 
+// When a transform sits in front of the index the scan works on transformed queries while the exact re-rank
+// needs the original ones: the search entry points leave both base pointers here for scan_dev (same thread).
+static thread_local const float* tls_xq_transformed = nullptr;
+static thread_local const float* tls_xq_raw = nullptr;
+static const float* raw_queries_for(const float* xq) {
+  return tls_xq_transformed && tls_xq_raw ? tls_xq_raw + (xq - tls_xq_transformed) : xq;
+}
+
 // GammaIVFFlatIndex::Search (gamma_index_ivfflat.cc:524-577)
-int IVFFlatIndex::search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq,
+int IVFFlatIndex::search_keys_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq_in,
                                   int k, unsigned long long* out_keys, Scratch& s) {
+  const float* xq = transform_dev(xq_in, nq, s);
+  if (!xq) return -1;
+  struct TlsGuard {
+    TlsGuard(const float* t, const float* r) { tls_xq_transformed = t == r ? nullptr : t, tls_xq_raw = r; }
+    ~TlsGuard() { tls_xq_transformed = tls_xq_raw = nullptr; }
+  } guard(xq, xq_in);
   const int nprobe = resolve_nprobe(ctx);
   const int QB = 16384;
   for (int q0 = 0; q0 < nq; q0 += QB) {
@@ -1292,7 +1312,8 @@ int IVFFlatIndex::coarse_search_host(int nq, const float* x, int nprobe, float* 
   GB_CUDA(cudaMemcpy2DAsync(dq, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, nq, cudaMemcpyHostToDevice, st));
   GB_ALLOC(ids, int32_t, (size_t)nq * nprobe, s);
   GB_ALLOC(dis, float, (size_t)nq * nprobe, s);
-  if (coarse_dev(nq, dq, nprobe, mp_.metric, ids, dis, s)) return -1;
+  const float* dqt = transform_dev(dq, nq, s);
+  if (!dqt || coarse_dev(nq, dqt, nprobe, mp_.metric, ids, dis, s)) return -1;
   std::vector<int32_t> h((size_t)nq * nprobe);
   GB_CUDA(cudaMemcpyAsync(h.data(), ids, h.size() * 4, cudaMemcpyDeviceToHost, st));
   GB_CUDA(cudaMemcpyAsync(out_dis, dis, h.size() * 4, cudaMemcpyDeviceToHost, st));
@@ -1324,7 +1345,12 @@ int IVFFlatIndex::search_preassigned_host(const SearchContext& ctx, int nq, cons
   if (upload_bitmaps(ctx, &f, s)) return -1;
   int metric = ctx.params.metric >= 0 ? ctx.params.metric : mp_.metric;
   GB_ALLOC(okeys, unsigned long long, (size_t)nq * k, s);
-  if (scan_dev(ctx, f, metric, nq, dq, k, ids, dis, nprobe, okeys, s)) return -1;
+  const float* dqt = transform_dev(dq, nq, s);
+  if (!dqt) return -1;
+  tls_xq_transformed = dqt == dq ? nullptr : dqt, tls_xq_raw = dq;
+  const int src = scan_dev(ctx, f, metric, nq, dqt, k, ids, dis, nprobe, okeys, s);
+  tls_xq_transformed = tls_xq_raw = nullptr;
+  if (src) return -1;
   GB_ALLOC(dd, float, (size_t)nq * k, s);
   GB_ALLOC(di, int64_t, (size_t)nq * k, s);
   GB_CUDA(launch_decode_keys(okeys, k, nq, k, metric, dd, di, 0, st));
@@ -1342,8 +1368,217 @@ IVFPQIndex::IVFPQIndex(int d, const ModelParams& mp, int device, int seg_shift)
   dsub_ = d / M_;
   cudaMalloc(&d_pq_, (size_t)M_ * 256 * dsub_ * 4);
   cudaMemset(d_pq_, 0, (size_t)M_ * 256 * dsub_ * 4);
+  if (mp.opq_nsubvector > 0) {  // faiss::OPQMatrix(d, opq_nsubvector, d) (gamma_index_ivfpq.cc:168-178)
+    cudaMalloc(&d_opq_, (size_t)d * dpad_ * 4);
+    cudaMemset(d_opq_, 0, (size_t)d * dpad_ * 4);
+  }
 }
+
+// ---- OPQ (faiss::OPQMatrix restated; VectorTransform.cpp of faiss v1.14.1 is not vendored) -------------
+// train: centre the (sub-sampled, <= 65536) training set, start from a random orthonormal matrix, then 50
+// rounds of { project; train a PQ on the projection (40 k-means iterations in the first round, 4 hot-started
+// ones afterwards, <= 1000 points per centroid); reconstruct; solve the orthogonal Procrustes problem
+// min ||X R^T - Y|| by an SVD of X^T Y }.  The projection and X^T Y run on the device, the d x d SVD (one-sided
+// Jacobi, double precision) on the host.  The random start cannot reproduce faiss's generator, so parity with
+// the reference is statistical (recall), as for k-means.
+namespace {
+// A (d x d2, row-major) = U diag(s) V^T by one-sided Jacobi on the columns; returns U (d x d2) and V (d2 x d2)
+void jacobi_svd(std::vector<double>& a, int d, int d2, std::vector<double>* u, std::vector<double>* v) {
+  v->assign((size_t)d2 * d2, 0.0);
+  for (int i = 0; i < d2; i++) (*v)[(size_t)i * d2 + i] = 1.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+    for (int p = 0; p < d2 - 1; p++)
+      for (int q = p + 1; q < d2; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < d; i++) {
+          const double x = a[(size_t)i * d2 + p], y = a[(size_t)i * d2 + q];
+          alpha += x * x, beta += y * y, gamma += x * y;
+        }
+        if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta) || gamma == 0) continue;
+        off = std::max(off, fabs(gamma) / sqrt(alpha * beta + 1e-300));
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int i = 0; i < d; i++) {
+          const double x = a[(size_t)i * d2 + p], y = a[(size_t)i * d2 + q];
+          a[(size_t)i * d2 + p] = c * x - sn * y, a[(size_t)i * d2 + q] = sn * x + c * y;
+        }
+        for (int i = 0; i < d2; i++) {
+          const double x = (*v)[(size_t)i * d2 + p], y = (*v)[(size_t)i * d2 + q];
+          (*v)[(size_t)i * d2 + p] = c * x - sn * y, (*v)[(size_t)i * d2 + q] = sn * x + c * y;
+        }
+      }
+    if (off < 1e-12) break;
+  }
+  u->assign((size_t)d * d2, 0.0);
+  for (int j = 0; j < d2; j++) {
+    double nrm = 0;
+    for (int i = 0; i < d; i++) nrm += a[(size_t)i * d2 + j] * a[(size_t)i * d2 + j];
+    nrm = sqrt(nrm);
+    for (int i = 0; i < d; i++) (*u)[(size_t)i * d2 + j] = nrm > 1e-300 ? a[(size_t)i * d2 + j] / nrm : (i == j ? 1.0 : 0.0);
+  }
+}
+}  // namespace
+
+int IVFPQIndex::set_opq(const float* host_A) {
+  if (!d_opq_) {
+    set_last_error("index was created without opq");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  GB_CUDA(cudaMemset(d_opq_, 0, (size_t)d_ * dpad_ * 4));
+  GB_CUDA(cudaMemcpy2D(d_opq_, (size_t)dpad_ * 4, host_A, (size_t)d_ * 4, (size_t)d_ * 4, d_, cudaMemcpyHostToDevice));
+  opq_trained_ = true;
+  return 0;
+}
+int IVFPQIndex::get_opq(float* host_A) const {
+  if (!d_opq_) {
+    set_last_error("index was created without opq");
+    return -1;
+  }
+  cudaSetDevice(device_);
+  GB_CUDA(cudaMemcpy2D(host_A, (size_t)d_ * 4, d_opq_, (size_t)dpad_ * 4, (size_t)d_ * 4, d_, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// y = A x for n rows (stride dpad, padding columns zero): one exact fp32 contraction against the rows of A
+const float* IVFPQIndex::transform_dev(const float* x, int64_t n, Scratch& s) {
+  if (!d_opq_ || !opq_trained_ || n <= 0) return x;
+  cudaStream_t st = s.stream();
+  float* y = s.alloc_n<float>((size_t)n * dpad_);
+  if (!y) return nullptr;
+  if (dpad_ != d_ && cudaMemsetAsync(y, 0, (size_t)n * dpad_ * 4, st) != cudaSuccess) return nullptr;
+  for (int64_t r0 = 0; r0 < n; r0 += (1 << 20)) {
+    const int nr = (int)std::min<int64_t>(n - r0, 1 << 20);
+    if (launch_dist_matrix(x + r0 * dpad_, dpad_, nr, d_opq_, dpad_, d_, dpad_, kMetricIP, y + r0 * dpad_, dpad_, st) !=
+        cudaSuccess) {
+      set_last_error("opq apply failed");
+      return nullptr;
+    }
+  }
+  return y;
+}
+
+int IVFPQIndex::apply_opq_host(const float* x, int64_t n, float* out) {
+  cudaSetDevice(device_);
+  cudaStream_t st = thread_stream(device_);
+  std::shared_lock<std::shared_mutex> lk(mu_);
+  Scratch s(st);
+  GB_ALLOC(dx, float, (size_t)n * dpad_, s);
+  GB_CUDA(cudaMemsetAsync(dx, 0, (size_t)n * dpad_ * 4, st));
+  GB_CUDA(cudaMemcpy2DAsync(dx, (size_t)dpad_ * 4, x, (size_t)d_ * 4, (size_t)d_ * 4, n, cudaMemcpyHostToDevice, st));
+  const float* y = transform_dev(dx, n, s);
+  if (!y) return -1;
+  GB_CUDA(cudaMemcpy2DAsync(out, (size_t)d_ * 4, y, (size_t)dpad_ * 4, (size_t)d_ * 4, n, cudaMemcpyDeviceToHost, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+const float* IVFPQIndex::train_transform(const float* xt, int64_t n_in, Scratch& s) {
+  if (!d_opq_) return xt;
+  if (opq_trained_) return transform_dev(xt, n_in, s);
+  cudaStream_t st = s.stream();
+  const int d = d_, Mo = mp_.opq_nsubvector, dso = d / Mo, dsp = (int)round_up(dso, 4);
+  int64_t n = std::min<int64_t>(n_in, 256 * 256);  // max_train_points
+  const float* xs = xt;
+  if (n < n_in) {
+    std::vector<int32_t> perm;
+    rand_perm_mt(perm, n_in, 1234);
+    int32_t* d_idx = s.alloc_n<int32_t>(n);
+    float* sub = s.alloc_n<float>((size_t)n * dpad_);
+    if (!d_idx || !sub) return nullptr;
+    if (cudaMemcpyAsync(d_idx, perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        launch_gather_rows(xt, dpad_, d_idx, n, dpad_, sub, dpad_, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return nullptr;
+    xs = sub;
+  }
+  const int64_t ldn = round_up(n, 4);
+  float* xc = s.alloc_n<float>((size_t)n * dpad_);      // centred training set
+  float* xproj = s.alloc_n<float>((size_t)n * dpad_);
+  float* recon = s.alloc_n<float>((size_t)n * dpad_);
+  float* xT = s.alloc_n<float>((size_t)d * ldn);
+  float* rT = s.alloc_n<float>((size_t)d * ldn);
+  float* xxr = s.alloc_n<float>((size_t)d * dpad_);
+  float* slice = s.alloc_n<float>((size_t)n * dsp);
+  float* cent = s.alloc_n<float>((size_t)Mo * 256 * dsp);  // per-subspace centroids, kept across rounds
+  float* pqc = s.alloc_n<float>((size_t)Mo * 256 * dso);
+  uint8_t* codes = s.alloc_n<uint8_t>((size_t)n * Mo);
+  if (!xc || !xproj || !recon || !xT || !rT || !xxr || !slice || !cent || !pqc || !codes) return nullptr;
+  auto ck = [](cudaError_t e) { return e == cudaSuccess; };
+  if (!ck(launch_center_rows(xs, dpad_, n, d, xc, dpad_, st)) || !ck(cudaMemsetAsync(xT, 0, (size_t)d * ldn * 4, st)) ||
+      !ck(cudaMemsetAsync(rT, 0, (size_t)d * ldn * 4, st)) || !ck(cudaMemsetAsync(recon, 0, (size_t)n * dpad_ * 4, st)) ||
+      !ck(launch_transpose(xc, dpad_, n, d, xT, ldn, st)))
+    return nullptr;
+  // random orthonormal start: Gaussian matrix (mt19937, seed 1234), Gram-Schmidt on the rows
+  std::vector<double> R((size_t)d * d);
+  {
+    std::mt19937 rng(1234);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    for (auto& v : R) v = nd(rng);
+    for (int i = 0; i < d; i++) {
+      for (int p = 0; p < i; p++) {
+        double dot = 0;
+        for (int j = 0; j < d; j++) dot += R[(size_t)i * d + j] * R[(size_t)p * d + j];
+        for (int j = 0; j < d; j++) R[(size_t)i * d + j] -= dot * R[(size_t)p * d + j];
+      }
+      double nrm = 0;
+      for (int j = 0; j < d; j++) nrm += R[(size_t)i * d + j] * R[(size_t)i * d + j];
+      nrm = sqrt(nrm);
+      for (int j = 0; j < d; j++) R[(size_t)i * d + j] /= nrm;
+    }
+  }
+  std::vector<float> Rf((size_t)d * d), hx((size_t)d * dpad_);
+  std::vector<double> a, U, V;
+  const int niter = 50, niter_pq_0 = 40, niter_pq = 4;
+  for (int it = 0; it < niter; it++) {
+    for (size_t i = 0; i < R.size(); i++) Rf[i] = (float)R[i];
+    if (!ck(cudaMemsetAsync(d_opq_, 0, (size_t)d * dpad_ * 4, st)) ||
+        !ck(cudaMemcpy2DAsync(d_opq_, (size_t)dpad_ * 4, Rf.data(), (size_t)d * 4, (size_t)d * 4, d, cudaMemcpyHostToDevice, st)) ||
+        !ck(cudaMemsetAsync(xproj, 0, (size_t)n * dpad_ * 4, st)) ||
+        !ck(launch_dist_matrix(xc, dpad_, (int)n, d_opq_, dpad_, d, dpad_, kMetricIP, xproj, dpad_, st)))
+      return nullptr;
+    KMeansParams kp;
+    kp.niter = it == 0 ? niter_pq_0 : niter_pq;
+    kp.max_points_per_centroid = 1000;
+    kp.hot_start = it > 0;
+    for (int m = 0; m < Mo; m++) {
+      if (!ck(launch_slice_cols(xproj, dpad_, n, m * dso, dso, slice, dsp, st))) return nullptr;
+      if (kmeans_device(slice, dsp, n, dso, 256, kp, cent + (size_t)m * 256 * dsp, dsp, st, nullptr)) return nullptr;
+      if (!ck(cudaMemcpy2DAsync(pqc + (size_t)m * 256 * dso, (size_t)dso * 4, cent + (size_t)m * 256 * dsp, (size_t)dsp * 4,
+                                (size_t)dso * 4, 256, cudaMemcpyDeviceToDevice, st)))
+        return nullptr;
+    }
+    if (!ck(launch_pq_encode(xproj, dpad_, n, nullptr, 0, nullptr, pqc, Mo, dso, codes, st)) ||
+        !ck(launch_pq_decode(codes, n, pqc, Mo, dso, recon, dpad_, st)) || !ck(launch_transpose(recon, dpad_, n, d, rT, ldn, st)) ||
+        !ck(launch_dist_matrix(xT, ldn, d, rT, ldn, d, (int)ldn, kMetricIP, xxr, dpad_, st)) ||
+        !ck(cudaMemcpyAsync(hx.data(), xxr, (size_t)d * dpad_ * 4, cudaMemcpyDeviceToHost, st)) || !ck(cudaStreamSynchronize(st)))
+      return nullptr;
+    a.assign((size_t)d * d, 0.0);  // X^T Y, d x d
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) a[(size_t)i * d + j] = hx[(size_t)i * dpad_ + j];
+    jacobi_svd(a, d, d, &U, &V);
+    // R^T = U V^T  =>  R[i][j] = sum_k V[i][k] U[j][k]
+    for (int i = 0; i < d; i++)
+      for (int j = 0; j < d; j++) {
+        double acc = 0;
+        for (int kk = 0; kk < d; kk++) acc += V[(size_t)i * d + kk] * U[(size_t)j * d + kk];
+        R[(size_t)i * d + j] = acc;
+      }
+  }
+  for (size_t i = 0; i < R.size(); i++) Rf[i] = (float)R[i];
+  if (!ck(cudaMemsetAsync(d_opq_, 0, (size_t)d * dpad_ * 4, st)) ||
+      !ck(cudaMemcpy2DAsync(d_opq_, (size_t)dpad_ * 4, Rf.data(), (size_t)d * 4, (size_t)d * 4, d, cudaMemcpyHostToDevice, st)) ||
+      !ck(cudaStreamSynchronize(st)))
+    return nullptr;
+  opq_trained_ = true;
+  return transform_dev(xt, n_in, s);
+}
+
 IVFPQIndex::~IVFPQIndex() {
+  if (d_opq_) cudaFree(d_opq_);
   cudaFree(d_pq_);
   cudaFree(d_table_);
 }
@@ -1492,8 +1727,9 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
     GB_CUDA(cudaMemcpyAsync(out_keys, partial, (size_t)nq * kk * 8, cudaMemcpyDeviceToDevice, st));
   }
   if (rerank) {
-    GB_CUDA(launch_rerank(adc, kk, nq, xq, dpad_, dpad_, store_->d_segs(), store_->seg_shift(), dpad_, k, metric, f,
-                          out_keys, st));
+    // "for opq, rerank need raw vector" (gamma_index_ivfpq.cc:735): original queries against the raw store
+    GB_CUDA(launch_rerank(adc, kk, nq, raw_queries_for(xq), dpad_, dpad_, store_->d_segs(), store_->seg_shift(), dpad_, k,
+                          metric, f, out_keys, st));
   }
   return 0;
 }
@@ -1530,6 +1766,11 @@ Index* create_index(const std::string& type, int d, const ModelParams& mp, int d
     }
     if (mp.nbits != 8) {
       set_last_error("only nbits_per_idx = 8 is supported");
+      return nullptr;
+    }
+    if (mp.opq_nsubvector > 0 && d % mp.opq_nsubvector != 0) {  // gamma_index_ivfpq.cc:169-176
+      set_last_error(std::to_string(d) + " % " + std::to_string(mp.opq_nsubvector) +
+                     " != 0, opq nsubvector should be divisible by dimension.");
       return nullptr;
     }
     if (mp.ncentroids <= 0 || mp.nprobe > mp.ncentroids) {

@@ -141,6 +141,7 @@ struct ModelParams {  // index/impl/gamma_index_ivfpq.h:1031-1257, gamma_index_i
   int training_threshold = 0;   // 0 => engine default
   int bucket_init_size = 1000;
   int bucket_max_size = 1280000;
+  int opq_nsubvector = 0;       // > 0: OPQ rotation in front of the IVFPQ index (gamma_index_ivfpq.h:1202-1216)
 };
 
 struct RetrievalParams {  // gamma_index_ivfpq.cc:233-294, gamma_index_ivfflat.cc:293-340
@@ -277,6 +278,7 @@ struct KMeansParams {
   int64_t seed = 1234;
   bool spherical = false;
   int max_points_per_centroid = 256;
+  bool hot_start = false;  // keep the centroids passed in as the initial state (ProductQuantizer::Train_hot_start)
 };
 int kmeans_device(const float* x, int64_t ldx, int64_t n, int d, int k, const KMeansParams& kp, float* centroids,
                   int64_t ldc, cudaStream_t st, std::vector<float>* obj);
@@ -328,6 +330,11 @@ class IVFFlatIndex : public Index {
   virtual int append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,
                            const int32_t* d_assign, Scratch& s);
   virtual int train_extra(const float* xtrain, int64_t n, Scratch& s) { (void)xtrain; (void)n; (void)s; return 0; }
+  // vector transform in front of the index (OPQ, gamma_index_ivfpq.cc:362-364, 422, 470, 585-590): applied to the
+  // training slab (which also trains it), to vectors on their way into the lists and to queries; the raw store
+  // and the exact re-rank keep the original vectors.  Default: identity (returns x).
+  virtual const float* train_transform(const float* xt, int64_t n, Scratch& s) { (void)n; (void)s; return xt; }
+  virtual const float* transform_dev(const float* x, int64_t n, Scratch& s) { (void)n; (void)s; return x; }
 
   // index rows [vid0, vid0+n) (device pointer x, stride dpad) into the lists
   int index_batch(const float* x, int64_t n, int64_t vid0, const uint8_t* del_bitmap);
@@ -389,9 +396,20 @@ class IVFPQIndex : public IVFFlatIndex {
   int train_extra(const float* xtrain, int64_t n, Scratch& s) override;
   int rebuild_table(cudaStream_t st);
 
+  const float* train_transform(const float* xt, int64_t n, Scratch& s) override;
+  const float* transform_dev(const float* x, int64_t n, Scratch& s) override;
+
   int M_, dsub_;
   float* d_pq_ = nullptr;     // [M][256][dsub]
   float* d_table_ = nullptr;  // [nlist][M][256] (L2 only)
+  float* d_opq_ = nullptr;    // [d][dpad] rows of the OPQ rotation A (y = A x); nullptr: no OPQ
+  bool opq_trained_ = false;
+
+ public:
+  bool has_opq() const { return d_opq_ != nullptr; }
+  int set_opq(const float* host_A);        // d x d row-major; marks the rotation trained
+  int get_opq(float* host_A) const;
+  int apply_opq_host(const float* x, int64_t n, float* out);  // test hook: y = A x through the device path
 };
 
 // reflector (index/reflector.h:68-80): type name -> index object

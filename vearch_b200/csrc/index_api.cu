@@ -53,6 +53,15 @@ bool parse_model_params(const std::string& text, ModelParams* mp, std::string* e
     }
     if (v > 0) mp->nsubvector = v;
   }
+  if (const JsonValue* opq = jv.get("opq")) {  // gamma_index_ivfpq.h:1202-1216
+    if (opq->type == JsonValue::Object && opq->get_int("nsubvector", &v)) {
+      if (v < -1) {
+        *err = "invalid opq_nsubvector = " + std::to_string(v);
+        return false;
+      }
+      if (v > 0) mp->opq_nsubvector = v;
+    }
+  }
   if (jv.get_int("nbits_per_idx", &v)) {
     if (v < -1) {
       *err = "invalid nbits_per_idx =" + std::to_string(v);
@@ -281,6 +290,25 @@ int gb_index_get_pq_centroids(gb_index* index, float* pqc) {
 int gb_index_get_precomputed_table(gb_index* index, float* table) {
   PQ_OR_FAIL(pq, index);
   return pq->get_precomputed_table(table);
+}
+int gb_index_has_opq(gb_index* index) {
+  IVFPQIndex* pq = index && index->impl ? dynamic_cast<IVFPQIndex*>(index->impl) : nullptr;
+  return pq && pq->has_opq() ? 1 : 0;
+}
+int gb_index_set_opq(gb_index* index, const float* A) {
+  IDX_OR_FAIL(index);
+  IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index->impl);
+  return pq ? pq->set_opq(A) : -1;
+}
+int gb_index_get_opq(gb_index* index, float* A) {
+  IDX_OR_FAIL(index);
+  IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index->impl);
+  return pq ? pq->get_opq(A) : -1;
+}
+int gb_index_apply_opq(gb_index* index, int64_t n, const float* x, float* out) {
+  IDX_OR_FAIL(index);
+  IVFPQIndex* pq = dynamic_cast<IVFPQIndex*>(index->impl);
+  return pq ? pq->apply_opq_host(x, n, out) : -1;
 }
 int gb_index_mirror_builds(gb_index* index) {
   if (!index || !index->impl) return -1;

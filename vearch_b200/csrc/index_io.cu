@@ -18,7 +18,7 @@
 //                per non-empty list: codes[size * code_bytes], i64 ids[size] (top bit = tombstone)
 //   IvFl only  : i32 indexed_count
 // An IndexHNSWFlat coarse quantiser ("IHNf") is read for its centroids (the graph is skipped: the coarse
-// search here is exact); Dump always writes the IndexFlat form.  OPQ blocks are rejected: SURVEY 8f N-4.
+// search here is exact); Dump always writes the IndexFlat form.  An OPQ block ("LTra") follows the product quantizer when the table has opq.
 #include <errno.h>
 #include <stdio.h>
 #include <string.h>
@@ -147,6 +147,13 @@ int IVFPQIndex::dump_gamma_extra(FILE* f) {
   bool ok = wr<uint8_t>(f, 1) && wr<uint64_t>(f, (uint64_t)M_) && wr<uint64_t>(f, (uint64_t)d_) &&
             wr<uint64_t>(f, (uint64_t)M_) && wr<uint64_t>(f, 8) && wr<uint64_t>(f, (uint64_t)pq.size()) &&
             wr_bytes(f, pq.data(), pq.size() * 4);
+  if (ok && has_opq()) {  // write_opq (index_io.cc:230-246): "LTra", have_bias, A, b, d_in, d_out, is_trained
+    std::vector<float> A((size_t)d_ * d_);
+    if (get_opq(A.data())) return -1;
+    ok = wr<uint32_t>(f, fourcc("LTra")) && wr<uint8_t>(f, 0) && wr<uint64_t>(f, (uint64_t)A.size()) &&
+         wr_bytes(f, A.data(), A.size() * 4) && wr<uint64_t>(f, 0) && wr<int32_t>(f, d_) && wr<int32_t>(f, d_) &&
+         wr<uint8_t>(f, 1);
+  }
   return ok ? 0 : -1;
 }
 
@@ -280,6 +287,19 @@ int IVFPQIndex::load_gamma_extra(FILE* f) {
                 " nbits=" + std::to_string(nbits));
   std::vector<float> pq((size_t)n);
   if (!rd_bytes(f, pq.data(), pq.size() * 4)) return fail("truncated product quantizer");
+  if (has_opq()) {  // read_opq (index_io.cc:248-270); whether the block is there is decided by the table's params
+    uint32_t h = 0;
+    uint8_t have_bias = 0, trained = 0;
+    uint64_t na = 0, nb = 0;
+    int32_t din = 0, dout = 0;
+    if (!rd(f, &h) || h != fourcc("LTra") || !rd(f, &have_bias) || !rd(f, &na) || na != (uint64_t)d_ * d_)
+      return fail("bad OPQ block (table has opq, file does not match)");
+    std::vector<float> A((size_t)na);
+    if (!rd_bytes(f, A.data(), A.size() * 4) || !rd(f, &nb) || fseek(f, (long)(nb * 4), SEEK_CUR) || !rd(f, &din) ||
+        !rd(f, &dout) || !rd(f, &trained) || din != d_ || dout != d_ || have_bias)
+      return fail("bad OPQ block");
+    if (set_opq(A.data())) return -1;
+  }
   return set_pq_centroids(pq.data());  // also recomputes the precomputed table (ivfpq.cc:1093-1095)
 }
 

@@ -128,6 +128,15 @@ cudaError_t launch_ivf_listmajor_topk(const float* xq, int64_t ldq, int d, const
                                       int nseg_max, int metric, FilterArgs f, unsigned long long* tau_g,
                                       unsigned long long* out, cudaStream_t st);
 
+// ---- OPQ training helpers (kernels_build.cu) ---------------------------------------------------
+// out[i][j] = x[i][j] - mean_j (columns >= d zeroed up to ldo); mean computed on device
+cudaError_t launch_center_rows(const float* x, int64_t ldx, int64_t n, int d, float* out, int64_t ldo, cudaStream_t st);
+// out[j][i] = x[i][j]  (n x d -> d x n, row stride ldo >= n)
+cudaError_t launch_transpose(const float* x, int64_t ldx, int64_t n, int d, float* out, int64_t ldo, cudaStream_t st);
+// recon[i][m * dsub + j] = pq[m][codes[i][m]][j]
+cudaError_t launch_pq_decode(const uint8_t* codes, int64_t n, const float* pq_centroids, int M, int dsub, float* recon,
+                             int64_t ldr, cudaStream_t st);
+
 // ---- K4/K5: IVF-PQ look-up tables + ADC scan --------------------------------------------
 // ip[q][m][c] = <x_q|m, pq_m[c]>   (pq.compute_inner_prod_table)
 cudaError_t launch_pq_ip_table(const float* xq, int64_t ldq, int nq, const float* pq_centroids, int M, int dsub,

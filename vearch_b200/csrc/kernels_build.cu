@@ -122,7 +122,91 @@ __global__ void ivf_append_codes_kernel(const uint8_t* __restrict__ codes, int64
 
 inline unsigned blocks_for(int64_t total, int bs) { return (unsigned)((total + bs - 1) / bs); }
 
+// column means, one CTA per column (rows strided over the threads, tree reduction in shared memory)
+__global__ void __launch_bounds__(256)
+    col_mean_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, float* __restrict__ mean) {
+  __shared__ double acc[256];
+  const int j = blockIdx.x;
+  double a = 0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) a += x[i * ldx + j];
+  acc[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) acc[threadIdx.x] += acc[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mean[j] = (float)(acc[0] / (double)n);
+}
+
+__global__ void center_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d, const float* __restrict__ mean,
+                                   float* __restrict__ out, int64_t ldo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * ldo) return;
+  const int64_t i = idx / ldo;
+  const int j = (int)(idx - i * ldo);
+  out[idx] = j < d ? x[i * ldx + j] - mean[j] : 0.f;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, int d, float* __restrict__ out,
+                                 int64_t ldo) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t i = i0 + r;
+    const int j = j0 + threadIdx.x;
+    tile[r][threadIdx.x] = (i < n && j < d) ? x[i * ldx + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r;
+    const int64_t i = i0 + threadIdx.x;
+    if (j < d && i < n) out[(int64_t)j * ldo + i] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void pq_decode_kernel(const uint8_t* __restrict__ codes, int64_t n, const float* __restrict__ pq, int M, int dsub,
+                                 float* __restrict__ recon, int64_t ldr) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int d = M * dsub;
+  if (idx >= n * d) return;
+  const int64_t i = idx / d;
+  const int c = (int)(idx - i * d);
+  const int m = c / dsub, j = c - m * dsub;
+  recon[i * ldr + c] = pq[((int64_t)m * 256 + codes[i * M + m]) * dsub + j];
+}
+
 }  // namespace
+
+cudaError_t launch_center_rows(const float* x, int64_t ldx, int64_t n, int d, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  float* mean = nullptr;
+  cudaError_t e = cudaMallocAsync(&mean, sizeof(float) * d, st);
+  if (e != cudaSuccess) return e;
+  col_mean_kernel<<<d, 256, 0, st>>>(x, ldx, n, mean);
+  note_launch();
+  center_rows_kernel<<<blocks_for(n * ldo, 256), 256, 0, st>>>(x, ldx, n, d, mean, out, ldo);
+  note_launch();
+  cudaFreeAsync(mean, st);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const float* x, int64_t ldx, int64_t n, int d, float* out, int64_t ldo, cudaStream_t st) {
+  if (n <= 0 || d <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32)), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(x, ldx, n, d, out, ldo);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pq_decode(const uint8_t* codes, int64_t n, const float* pq_centroids, int M, int dsub, float* recon,
+                             int64_t ldr, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  pq_decode_kernel<<<blocks_for(n * M * dsub, 256), 256, 0, st>>>(codes, n, pq_centroids, M, dsub, recon, ldr);
+  note_launch();
+  return cudaGetLastError();
+}
+
 
 cudaError_t launch_segment_mean(const float* x, int64_t ldx, int d, const int32_t* perm, const int32_t* off, int k,
                                 float* centroids, int64_t ldc, cudaStream_t st) {

@@ -207,6 +207,26 @@ class GammaIndex:
         _check(_lib.lib().gb_index_get_precomputed_table(self._h, _ptr(out)), "get_precomputed_table")
         return out
 
+    @property
+    def has_opq(self):
+        return bool(_lib.lib().gb_index_has_opq(self._h))
+
+    def set_opq(self, A):
+        A = _f32(A)
+        assert A.shape == (self.d, self.d)
+        _check(_lib.lib().gb_index_set_opq(self._h, _ptr(A)), "set_opq")
+
+    def get_opq(self):
+        A = np.empty((self.d, self.d), np.float32)
+        _check(_lib.lib().gb_index_get_opq(self._h, _ptr(A)), "get_opq")
+        return A
+
+    def apply_opq(self, x):
+        x = _f32(x)
+        out = np.empty_like(x)
+        _check(_lib.lib().gb_index_apply_opq(self._h, x.shape[0], _ptr(x), _ptr(out)), "apply_opq")
+        return out
+
     def list_len(self, l):
         return int(_lib.lib().gb_index_list_len(self._h, l))
 
