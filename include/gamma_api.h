@@ -15,12 +15,12 @@
  * 0 ok, 1 not found, 2 index error, 3 not supported, 4 invalid argument, 5 IO error, 6 busy,
  * 7 timed out, 8 memory exceeded, 9 cancelled.
  *
- * Scope of this build (DESIGN.md): full semantics for Init / Close / CreateTable /
- * AddOrUpdateDoc / DeleteDoc / GetDocByID / GetDocByDocID / BuildIndex / Search /
+ * Scope of this build (DESIGN.md, INTEGRATION.md): full semantics for Init / Close / CreateTable /
+ * AddOrUpdateDoc / DeleteDoc / GetDocByID / GetDocByDocID / BuildIndex / Search / Query /
  * GetEngineStatus / GetMemoryInfo / SetConfig / GetConfig / Dump / Load / SetKillStatus /
- * DeleteKillStatus for tables with ONE vector field indexed as FLAT, IVFFLAT or IVFPQ;
- * Query, Backup, RebuildIndex, AddFieldIndexWithParams, RemoveFieldIndex (scalar-table
- * features outside the vector hot path) return kNotSupported / a non-zero code.
+ * DeleteKillStatus / AddFieldIndexWithParams / RemoveFieldIndex for tables whose vector fields are
+ * indexed as FLAT, IVFFLAT or IVFPQ (optionally with OPQ); Backup returns kNotSupported, RebuildIndex
+ * reports "nothing to do", SetMemoryLimitConfig is a no-op (vectors live in HBM).
  */
 #ifndef GAMMA_API_H_
 #define GAMMA_API_H_

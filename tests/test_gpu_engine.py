@@ -352,6 +352,15 @@ def test_scalar_filters_restrict_the_candidate_set(tmp_path, data):
                dict(term_filters=[("nofield", b"x")])):
         res = e.search(xq, 5, **kw)
         assert len(res) == NQ and all(r["items"] == [] and "no result" in r["msg"] for r in res)
+    # AddFieldIndexWithParams / RemoveFieldIndex switch a field's filterability (engine.cc:1471-1600)
+    e.add_field_index("plain")
+    res = e.search(xq, 5, index_params={"nprobe": 16}, range_filters=[("plain", i32(2990), b"", True, False)])
+    assert all(int(k[3:]) >= 2990 for row in keys_of(res) for k in row) and len(keys_of(res)[0]) == 5
+    e.remove_field_index("plain")
+    assert e.search(xq, 5, range_filters=[("plain", i32(2990), b"", True, False)])[0]["items"] == []
+    with pytest.raises(eng_mod().GammaStatusError) as ei:
+        e.add_field_index("emb")
+    assert ei.value.code == 3
     # brute-force path (FLAT kernel) honours the same bitmap
     res = e.search(xq, 5, is_brute_search=1, range_filters=[("price", i32(100), i32(300), True, False)])
     fb = np.packbits((price >= 100) & (price < 300) & alive, bitorder="little")

@@ -971,6 +971,18 @@ Status Engine::Query(const QueryRequestPB& req, std::string* pb_out) {
   return Status::OK();
 }
 
+Status Engine::SetFieldIndexed(const std::string& field, bool indexed) {
+  if (!created_table_) return Status::Make(kIOError, "table not initialized");
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  int dim = 0;
+  if (index_of(field, &dim))
+    return Status::Make(kNotSupported, "the index of vector field " + field + " is fixed when the table is created");
+  auto it = field_idx_.find(field);
+  if (it == field_idx_.end()) return Status::Make(kInvalidArgument, "field " + field + " not found");
+  fields_[it->second].indexed = indexed;
+  return Status::OK();
+}
+
 // Engine::BuildIndex / Engine::Indexing (search/engine.cc:951-988, 1091-1142)
 int Engine::BuildIndex() {
   if (!created_table_) return -1;

@@ -107,6 +107,9 @@ class Engine {
   int Load();
   const std::string& space_name() const { return space_name_; }
   void quiesce();  // stop the indexing thread (also from an atexit hook for engines never Closed)
+  // Engine::AddFieldIndex / RemoveFieldIndex (search/engine.cc:1471-1600): here a scalar field's "index" is
+  // the permission to filter on it (filters scan the in-memory column), so both are a flag flip
+  Status SetFieldIndexed(const std::string& field, bool indexed);
 
   // cooperative cancellation (c_api/api_data/request_context.h:51-88)
   static void SetKill(const std::string& request_id, int partition_id, int reason);

@@ -167,15 +167,24 @@ struct CStatus Backup(void*, int) {
   return c;
 }
 
-struct CStatus AddFieldIndexWithParams(void*, const char*, int, const char*, int, const char*, int) {
+struct CStatus AddFieldIndexWithParams(void* engine, const char* field_name, int field_name_len, const char*, int,
+                                       const char*, int) {
   struct CStatus c;
-  to_cstatus(gb::Status::Make(gb::kNotSupported, "scalar field indexes are outside the vector hot path"), &c);
+  if (!engine || !field_name) {
+    to_cstatus(gb::Status::Make(gb::kInvalidArgument, "null engine"), &c);
+    return c;
+  }
+  to_cstatus(static_cast<Engine*>(engine)->SetFieldIndexed(std::string(field_name, (size_t)field_name_len), true), &c);
   return c;
 }
 
-struct CStatus RemoveFieldIndex(void*, const char*, int) {
+struct CStatus RemoveFieldIndex(void* engine, const char* field_name, int field_name_len) {
   struct CStatus c;
-  to_cstatus(gb::Status::Make(gb::kNotSupported, "scalar field indexes are outside the vector hot path"), &c);
+  if (!engine || !field_name) {
+    to_cstatus(gb::Status::Make(gb::kInvalidArgument, "null engine"), &c);
+    return c;
+  }
+  to_cstatus(static_cast<Engine*>(engine)->SetFieldIndexed(std::string(field_name, (size_t)field_name_len), false), &c);
   return c;
 }
 

@@ -176,6 +176,14 @@ class GammaEngine:
                                          index_params=json.dumps(index_params) if index_params else "", **kw)
         return wire.decode_search_response(self.search_raw(req))
 
+    def add_field_index(self, field):
+        f = field.encode()
+        _status(_api().AddFieldIndexWithParams(self._h, f, len(f), b"", 0, b"", 0))
+
+    def remove_field_index(self, field):
+        f = field.encode()
+        _status(_api().RemoveFieldIndex(self._h, f, len(f)))
+
     def dump(self):
         return _api().Dump(self._h)
 
