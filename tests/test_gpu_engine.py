@@ -486,3 +486,29 @@ def test_multi_vector_table_join_and_weighted_rank(tmp_path, data):
     after = keys_of(e2.search(xq, topn, is_brute_search=1, extra_vec_queries=[("img", imq)], multi_vector_rank=1))
     assert after == before
     e2.close()
+
+
+def test_rebuild_index_retrains_and_reindexes(tmp_path, data):
+    """RebuildIndex (search/engine.cc:991-1089): a no-op on an engine that is not indexing; otherwise the
+    index of every vector field is dropped, trained again on the current vectors and refilled."""
+    db, xq = data
+    e = make_engine(tmp_path, "IVFPQ", {"ncentroids": 16, "nprobe": 16, "nsubvector": 8, "metric_type": "L2",
+                                        "training_threshold": 1000})
+    assert e.rebuild_index() == 0  # "index not running, no need to rebuild!"
+    add_all(e, db[:2500])
+    e.wait_indexed(2500)
+    before = e.search(xq, 10, index_params={"nprobe": 16, "recall_num": 100})
+    for i in range(0, 300):
+        e.delete_doc(f"doc{i}")
+    assert e.rebuild_index() == 0
+    st = e.wait_indexed(2500)
+    assert st["index_status"] == 2 and st["doc_num"] == 2200
+    after = e.search(xq, 10, index_params={"nprobe": 16, "recall_num": 100})
+    alive = np.ones(2500, bool)
+    alive[:300] = False
+    _, gt = orc.flat_search(db[:2500], xq, 1, L2, del_bitmap=np.packbits(~alive, bitorder="little"))
+    got = keys_of(after)
+    assert np.mean([f"doc{gt[q, 0]}" in got[q] for q in range(NQ)]) >= 0.9
+    assert all(int(k[3:]) >= 300 for row in got for k in row) and len(before) == len(after)
+    assert e.rebuild_index(describe=1) == 0 and e.status()["index_status"] == 2  # describe: the thread is only stopped
+    e.close()

@@ -993,6 +993,32 @@ int Engine::BuildIndex() {
   return 0;
 }
 
+// Engine::RebuildIndex: only acts on a running, indexed engine; stops the indexing thread, drops the index
+// structures of every vector field (the raw vectors stay) and starts over: train on the current first
+// training_threshold vectors, re-add everything.  Both reference variants (build the new indexes aside, or
+// drop first) end in the same state; here the old index is dropped first, so searches in between see the
+// "index not trained" / brute-force rules of an un-indexed table.
+int Engine::RebuildIndex(int drop_before_rebuild, int limit_cpu, int describe) {
+  (void)drop_before_rebuild;
+  (void)limit_cpu;
+  if (!created_table_) return -1;
+  if (indexing_state_.load() != 2 || index_status_.load() == 0) return 0;  // "index not running, no need to rebuild!"
+  quiesce();
+  indexing_state_.store(0);
+  if (describe) return 0;
+  cudaSetDevice(device_);
+  {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    if (flush_pending_locked()) return -1;
+  }
+  if (index_->reset_index()) return -1;
+  for (auto& e : extra_)
+    if (e.index->reset_index()) return -1;
+  index_status_.store(0);
+  if (refresh_interval_ >= 0 && max_docid_ - delete_num_ >= training_threshold_) return BuildIndex();
+  return 0;
+}
+
 void Engine::indexing_loop() {
   cudaSetDevice(device_);
   int expected = 1;

@@ -99,6 +99,7 @@ class Engine {
   Status Search(const SearchRequestPB& req, std::string* pb_out);
   Status Query(const QueryRequestPB& req, std::string* pb_out);  // search/engine.cc:404-523
   int BuildIndex();
+  int RebuildIndex(int drop_before_rebuild, int limit_cpu, int describe);  // search/engine.cc:991-1089
   std::string EngineStatus();
   std::string MemoryInfo();
   int SetConfig(const std::string& json);

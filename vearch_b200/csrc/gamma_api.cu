@@ -105,11 +105,8 @@ int GetDocByDocID(void* engine, int docid, char next, char** doc_str, int* len) 
 
 int BuildIndex(void* engine) { return engine ? static_cast<Engine*>(engine)->BuildIndex() : -1; }
 
-int RebuildIndex(void* engine, int, int, int) {
-  // RebuildIndex only acts on a running index and re-trains in place (engine.cc:991-1089);
-  // not offered by this build: report "nothing to do" exactly like an idle reference engine.
-  (void)engine;
-  return 0;
+int RebuildIndex(void* engine, int drop_before_rebuild, int limit_cpu, int describe) {
+  return engine ? static_cast<Engine*>(engine)->RebuildIndex(drop_before_rebuild, limit_cpu, describe) : -1;
 }
 
 int Dump(void* engine) { return engine ? static_cast<Engine*>(engine)->Dump() : -1; }

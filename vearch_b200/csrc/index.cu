@@ -1006,6 +1006,20 @@ int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
   return 0;
 }
 
+int IVFFlatIndex::reset_index() {
+  std::lock_guard<std::mutex> bg(build_mu_);
+  cudaSetDevice(device_);
+  std::unique_lock<std::shared_mutex> lk(mu_);
+  std::unique_lock<std::shared_mutex> ml(mirror_rw_);
+  cudaDeviceSynchronize();  // kernels of earlier device-resident searches may still read the lists
+  lists_.reset();
+  vid2pos_.clear();
+  mirror_.lens.clear();
+  indexed_count_ = 0;
+  trained_ = false;
+  return 0;
+}
+
 int IVFFlatIndex::compact_lists() {
   std::lock_guard<std::mutex> bg(build_mu_);
   if (!lists_) return 0;

@@ -192,6 +192,9 @@ class Index {
   int search_direct(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
   int search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
                     int64_t* out_ids_dev, cudaStream_t st);
+  // forget the trained state and the index structures, keep the raw vectors (Engine::RebuildIndex ->
+  // VectorManager::ReCreateVectorIndexes, search/engine.cc:991-1089): the next train() starts over
+  virtual int reset_index() { return 0; }
   virtual int64_t index_mem_bytes() const { return 0; }
   // stop the background worker (request coalescer); also run from an atexit hook for objects the host
   // never closed, so no thread of ours is inside the CUDA runtime while it is being torn down
@@ -291,6 +294,7 @@ class IVFFlatIndex : public Index {
   int train() override;
   int add_pending(const uint8_t* del_bitmap) override;
   int update_vector(int64_t vid, const float* x) override;
+  int reset_index() override;
   int64_t index_mem_bytes() const override;
   int nlist() const { return nlist_; }
   // parity hooks: exchange index state with the oracle
@@ -389,6 +393,14 @@ class IVFPQIndex : public IVFFlatIndex {
                Scratch& s) override;
   int code_bytes() const override { return M_; }
   const char* gamma_file_name() const override;
+
+ public:
+  int reset_index() override {
+    opq_trained_ = false;
+    return IVFFlatIndex::reset_index();
+  }
+
+ protected:
   int dump_gamma_extra(FILE* f) override;
   int load_gamma_extra(FILE* f) override;
   int append_batch(const float* x, int64_t n, int64_t vid0, const int32_t* d_list, const int32_t* d_pos,

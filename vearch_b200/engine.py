@@ -176,6 +176,9 @@ class GammaEngine:
                                          index_params=json.dumps(index_params) if index_params else "", **kw)
         return wire.decode_search_response(self.search_raw(req))
 
+    def rebuild_index(self, drop_before_rebuild=1, limit_cpu=0, describe=0):
+        return _api().RebuildIndex(self._h, drop_before_rebuild, limit_cpu, describe)
+
     def add_field_index(self, field):
         f = field.encode()
         _status(_api().AddFieldIndexWithParams(self._h, f, len(f), b"", 0, b"", 0))
