@@ -18,9 +18,9 @@
  * Scope of this build: full semantics for Init / Close / CreateTable /
  * AddOrUpdateDoc / DeleteDoc / GetDocByID / GetDocByDocID / BuildIndex / Search / Query /
  * GetEngineStatus / GetMemoryInfo / SetConfig / GetConfig / Dump / Load / SetKillStatus /
- * DeleteKillStatus / AddFieldIndexWithParams / RemoveFieldIndex for tables whose vector fields are
- * indexed as FLAT, IVFFLAT or IVFPQ (optionally with OPQ); Backup returns kNotSupported, RebuildIndex
- * reports "nothing to do", SetMemoryLimitConfig is a no-op (vectors live in HBM).
+ * DeleteKillStatus / AddFieldIndexWithParams / RemoveFieldIndex / RebuildIndex for tables whose vector
+ * fields are indexed as FLAT, IVFFLAT or IVFPQ (optionally with OPQ); Backup returns kNotSupported,
+ * SetMemoryLimitConfig is a no-op (vectors live in HBM).
  */
 #ifndef GAMMA_API_H_
 #define GAMMA_API_H_
