@@ -125,6 +125,25 @@ def test_scalar_filters_cross_the_wire_like_the_official_runtime():
             dict(field="color", lower=b"red".hex(), upper="", include_lower=False, include_upper=False, is_term=True, is_union=0)]
 
 
+def test_multi_vector_request_crosses_the_wire_like_the_official_runtime():
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_golden
+    cls = gen_golden.classes()
+    q1 = np.arange(16, dtype=np.float32).reshape(2, 8)
+    q2 = np.arange(8, dtype=np.float32).reshape(2, 4) + 100
+    ranker = '{"type": "WeightedRanker", "params": [0.25, 0.75]}'
+    mine = wire.encode_search_request("emb", q1, 7, extra_vec_queries=[("img", q2)], ranker=ranker, multi_vector_rank=1)
+    m = cls["SearchRequest"]()
+    m.ParseFromString(mine)
+    assert [(v.name, v.value) for v in m.vec_fields] == [("emb", q1.tobytes()), ("img", q2.tobytes())]
+    assert m.ranker == ranker and m.multi_vector_rank == 1 and m.req_num == 2 and m.topN == 7
+    rc, out = _call_json(_lib.lib().gb_debug_parse_search_request, m.SerializeToString())
+    got = json.loads(out)
+    assert rc == 0 and got["multi_vector_rank"] == 1
+    assert [(v["name"], v["value_len"]) for v in got["vec_fields"]] == [("emb", 64), ("img", 32)]
+
+
 def test_query_request_encoder_matches_official_runtime():
     import struct
     import sys
