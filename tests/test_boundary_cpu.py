@@ -212,6 +212,74 @@ def test_flatbuffers_table_parsed_by_cpp():
     assert json.loads(_call_json(_lib.lib().gb_debug_parse_table, tb2)[1])["refresh_interval"] == 1000
 
 
+FB = os.path.join(GOLD, "fb")
+
+
+@pytest.mark.parametrize("name", ["table_official_full.fb", "table_official_minimal.fb", "table_official_empty_vectors.fb"])
+def test_readers_accept_reference_written_table_bytes(name):
+    """Bytes written by the reference's vendored flatbuffers runtime + flatc-generated builders
+    (tests/golden/make_fb_golden.cc, compiled against /root/reference/internal/engine/third_party/flatbuffers and
+    idl/fbs-gen/c/table_generated.h): the C++ reader of libgamma.so must see what the reference's own reader sees
+    (official.json), incl. default-omitted scalars and absent / empty vectors."""
+    exp = json.load(open(os.path.join(FB, "official.json")))[name]
+    raw = open(os.path.join(FB, name), "rb").read()
+    rc, out = _call_json(_lib.lib().gb_debug_parse_table, raw)
+    assert rc == 0
+    got = json.loads(out)
+    assert exp["verified"]
+    for k in ("name", "refresh_interval", "enable_id_cache", "enable_realtime"):
+        assert got[k] == exp[k], k
+    assert got["fields"] == exp["fields"]
+    assert [(v["name"], v["dimension"], v["store_type"]) for v in got["vectors"]] == \
+        [(v["name"], v["dimension"], v["store_type"] or "") for v in exp["vectors"]]
+    assert [(i["name"], i["type"], i["field_name"], i["params"]) for i in got["indexes"]] == \
+        [(i["name"], i["type"], i["field_name"], i["params"]) for i in exp["indexes"]]
+    # truncation is rejected, never read out of range
+    for cut in (1, 7, len(raw) // 2):
+        rc, _ = _call_json(_lib.lib().gb_debug_parse_table, raw[:-cut])
+        assert rc in (0, -1)
+
+
+@pytest.mark.parametrize("name", ["doc_official_bytes.fb", "doc_official_gostring.fb"])
+def test_readers_accept_reference_written_doc_bytes(name):
+    """gamma_api.Doc as api_data/doc.cc writes it ([ubyte] value) and as the Go SDK writes it (value through
+    CreateString, sdk/go/gamma/doc.go:28-42): both readers recover the same fields the reference's reader does."""
+    exp = json.load(open(os.path.join(FB, "official.json")))[name]
+    raw = open(os.path.join(FB, name), "rb").read()
+    want = {f["name"]: (bytes.fromhex(f["value_hex"]), f["data_type"]) for f in exp["fields"]}
+    assert exp["verified"] and len(want) == 5
+    assert wire.parse_doc(raw) == want                                   # Python reader
+    rc, out = _call_json(_lib.lib().gb_debug_roundtrip_doc, raw)         # C++ reader -> C++ builder
+    assert rc == 0 and wire.parse_doc(out) == want
+    assert np.array_equal(np.frombuffer(want["emb"][0], np.float32), 1.0 + 0.5 * np.arange(64, dtype=np.float32))
+
+
+def test_our_builders_emit_bytes_the_official_verifier_accepted():
+    """ours_*.fb were produced by this repo's writers and passed the reference runtime's Verifier + generated reader
+    (ours.json, written by tests/golden/gen_fb_golden.py).  The writers must still emit exactly those bytes."""
+    sys_path = os.path.join(GOLD)
+    import sys
+    sys.path.insert(0, sys_path)
+    import gen_fb_golden
+    ours = json.load(open(os.path.join(FB, "ours.json")))
+    built = gen_fb_golden.our_buffers()
+    assert sorted(n + ".fb" for n in built) == sorted(ours)
+    for name, (kind, buf) in built.items():
+        assert ours[name + ".fb"]["verified"]
+        assert buf == open(os.path.join(FB, name + ".fb"), "rb").read(), f"{name}: builder output changed; re-run gen_fb_golden.py"
+    t = ours["ours_table_py.fb"]
+    assert t["name"] == "ts_space" and t["refresh_interval"] == 250 and t["enable_id_cache"] == 1 and t["enable_realtime"] == 1
+    assert [(v["name"], v["dimension"]) for v in t["vectors"]] == [("emb", 128), ("img", 16)]
+    assert [(i["type"], i["field_name"]) for i in t["indexes"]] == [("IVFPQ", "emb"), ("FLAT", "img")]
+    assert ours["ours_table_py_defaults.fb"]["refresh_interval"] == 1000
+    d = {f["name"]: (bytes.fromhex(f["value_hex"]), f["data_type"]) for f in ours["ours_doc_py_string.fb"]["fields"]}
+    assert d["_id"] == (b"doc-00042", wire.DT_STRING) and d["price"][0] == (-7).to_bytes(4, "little", signed=True)
+    assert ours["ours_doc_py_bytes.fb"]["fields"] == ours["ours_doc_py_string.fb"]["fields"]
+    dc = {f["name"]: f["value_hex"] for f in ours["ours_doc_cpp_roundtrip.fb"]["fields"]}
+    off = {f["name"]: f["value_hex"] for f in json.load(open(os.path.join(FB, "official.json")))["doc_official_gostring.fb"]["fields"]}
+    assert dc == off  # C++ reader + C++ builder: nothing lost between the official bytes and the official reader
+
+
 def test_oracle_matches_known_answer_vectors():
     g = np.load(os.path.join(GOLD, "flat_small.npz"))
     db, xq = g["db"].astype(np.float32), g["xq"].astype(np.float32)

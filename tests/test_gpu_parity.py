@@ -426,6 +426,70 @@ def test_ivfpq_train_on_device_recall():
     idx.close()
 
 
+@pytest.mark.parametrize("metric", [L2, IP])
+@pytest.mark.parametrize("d,M,data", [(128, 16, "float"), (128, 16, "int"), (64, 8, "float"), (64, 16, "float"),
+                                      (128, 8, "float"), (96, 12, "float")])
+def test_ivfpq_listmajor_tensor_core_filter_matches_oracle(metric, d, M, data):
+    """Many queries per list => the IVF-PQ scan runs list-major (kernels_pqtc.cu): exact LUT scan of the
+    first probes -> per-query bound -> bf16 tcgen05 FILTER over the other probes -> candidates re-scored
+    with the reference arithmetic.  The filter must never lose an entry: ADC scores bit-equal to the
+    oracle and ids equal (tie-aware) on float data (every mantissa bit in use) as on integer data, at
+    k = 10 and at re-rank depth 400, with tombstones, deletion bitmap, missing probes, score window."""
+    n, nq, nlist, nprobe = 40000, 900, 16, 6
+    if data == "int":
+        db, xq = synth.sift_like(n, d, seed=195), synth.sift_like(nq, d, seed=196)
+    else:
+        rng = np.random.default_rng(197)
+        centers = rng.normal(0, 1, (64, d)).astype(np.float32)
+        db = (centers[rng.integers(0, 64, n)] + 0.35 * rng.normal(0, 1, (n, d))).astype(np.float32)
+        xq = (centers[rng.integers(0, 64, nq)] + 0.35 * rng.normal(0, 1, (nq, d))).astype(np.float32)
+    cent, _, _ = orc.kmeans(db[:4000], nlist, niter=5)
+    a = orc.assign(cent, db, metric)
+    pqc = orc.pq_train(db[:6000] - cent[a[:6000]], M, niter=4)
+    idx = gi().GammaIndex("IVFPQ", d, {"ncentroids": nlist, "nprobe": nprobe, "nsubvector": M,
+                                       "metric_type": mt(metric)})
+    idx.set_centroids(cent)
+    idx.set_pq_centroids(pqc)
+    idx.add_vectors(db)
+    idx.add_pending()
+    off, codes, ids = idx.export_lists()
+    T = orc.ivfpq_precompute_table(cent, pqc) if metric == L2 else None
+    cd, keys = orc.coarse_search(cent, xq, nprobe, metric)
+    keys[5, 2] = -1   # "not enough centroids" (gamma_index_ivfpq.cc:640)
+    keys[7, 0] = -1   # ... in the probe the bound comes from
+    deleted = np.random.default_rng(2).random(n) < 0.2
+    delb = np.packbits(deleted, bitorder="little")
+    idx.tombstone(int(np.searchsorted(off, 0, side="right") - 1), 0)
+    ids2 = ids.copy()
+    ids2[0] |= orc.DEL_MASK
+    for kk, kw in [(10, {}), (400, {}), (10, {"del_bitmap": delb}), (100, {"del_bitmap": delb})]:
+        dg, ig = idx.search_preassigned(xq, kk, keys, cd, **kw)
+        assert idx.last_scan_kernel == "pqtc_scan_kernel"
+        do, io = orc.ivfpq_search_preassigned(off, codes, ids2, cent, pqc, T, xq, kk, keys, cd, metric, **kw)
+        assert_same_results(dg, ig, do, io)
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids2, cent, pqc, T, xq, 50, keys, cd, metric)
+    lo, hi = float(min(do[0, 3], do[0, 40])), float(max(do[0, 3], do[0, 40]))
+    dg, ig = idx.search_preassigned(xq, 50, keys, cd, min_score=lo, max_score=hi)
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids2, cent, pqc, T, xq, 50, keys, cd, metric, min_score=lo,
+                                          max_score=hi)
+    assert_same_results(dg, ig, do, io)
+    # exact re-rank on top of the filtered ADC stage: same final answer as the LUT-only pipeline
+    dr, ir = idx.search_preassigned(xq, 10, keys, cd, params={"recall_num": 400})
+    dc, ic = idx.search_preassigned(xq, 400, keys, cd)
+    for q in range(0, nq, 37):
+        cand = ic[q][ic[q] >= 0]
+        v = db[cand]
+        exact = (((xq[q] - v) ** 2).sum(1) if metric == L2 else v @ xq[q]).astype(np.float32)
+        order = np.lexsort((cand, exact if metric == L2 else -exact))[:10]
+        assert np.allclose(dr[q][: len(order)], exact[order], rtol=1e-5)
+    # a small batch of the same index goes through the LUT kernel and must agree with the big one
+    d1, i1 = idx.search_preassigned(xq[:3], 10, keys[:3], cd[:3])
+    assert idx.last_scan_kernel == "ivfpq_scan_kernel"
+    d2, i2 = idx.search_preassigned(xq, 10, keys, cd)
+    assert np.array_equal(d1, d2[:3]) and np.array_equal(i1, i2[:3])
+    idx.close()
+
+
 # ----------------------------------------------------------------------------------------------
 # K7 merge / multi-partition
 # ----------------------------------------------------------------------------------------------

@@ -30,6 +30,20 @@ static bool tc_enabled() {
   return v != 0;
 }
 
+// SM count of a device, queried once (grids of the persistent kernels, work-splitting heuristics)
+static int sm_count(int device) {
+  static std::mutex mu;
+  static std::vector<int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= device) cache.resize(device + 1, 0);
+  if (!cache[device]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    cache[device] = n;
+  }
+  return cache[device];
+}
+
 static cudaStream_t thread_stream(int device) {
   static thread_local cudaStream_t st[64] = {nullptr};
   if (device < 0 || device >= 64) return nullptr;
@@ -1595,6 +1609,8 @@ IVFPQIndex::~IVFPQIndex() {
   if (d_opq_) cudaFree(d_opq_);
   cudaFree(d_pq_);
   cudaFree(d_table_);
+  cudaFree(d_cb16_);
+  cudaFree(d_cbnrm_);
 }
 int IVFPQIndex::training_threshold() const {
   // gamma_index_ivfpq.cc:139-144: default max(nlist*200, 256); Indexing() clamps like IVFFLAT (:304-329)
@@ -1610,6 +1626,13 @@ int64_t IVFPQIndex::index_mem_bytes() const {
          (d_table_ ? (int64_t)nlist_ * M_ * 256 * 4 : 0);
 }
 int IVFPQIndex::rebuild_table(cudaStream_t st) {
+  // tables of the tensor-core filter (kernels_pqtc.cu): bf16 codebook pre-scaled by -2 (L2) / -1 (IP),
+  // centroid norms, and the bound on |r| its error margin uses
+  if (pqtc_supported(M_, dsub_)) {
+    if (!d_cb16_) GB_CUDA(cudaMalloc(&d_cb16_, (size_t)M_ * 256 * dsub_ * 2));
+    if (!d_cbnrm_) GB_CUDA(cudaMalloc(&d_cbnrm_, ((size_t)M_ * 256 + 4) * 4));
+    GB_CUDA(launch_pqtc_tables(d_pq_, M_, dsub_, mp_.metric, d_cb16_, d_cbnrm_, d_cbnrm_ + (size_t)M_ * 256, st));
+  }
   if (mp_.metric != kMetricL2) return 0;  // IP: tab = ip table, dis0 = <x, centroid>
   if (!d_table_) GB_CUDA(cudaMalloc(&d_table_, (size_t)nlist_ * M_ * 256 * 4));
   GB_CUDA(launch_pq_precompute_table(d_centroids_, dpad_, nlist_, d_pq_, M_, dsub_, d_table_, st));
@@ -1706,6 +1729,134 @@ int IVFPQIndex::encode_host(const float* x, int64_t n, const int64_t* assign, ui
   return 0;
 }
 
+// GB_PQTC=0: never use the tensor-core filter (exact LUT kernel for every probe); GB_PQTC=2: use it
+// whenever the shape allows, whatever the batch size (tests)
+static int pqtc_mode() {  // read per call: tests flip it between searches of one process
+  const char* e = getenv("GB_PQTC");
+  return e ? atoi(e) : 1;
+}
+// test hook: scales the filter's error margin (1 = the rigorous bound, 0 = no margin at all)
+static float pqtc_eps_scale() {
+  const char* e = getenv("GB_PQTC_EPS");
+  return e ? (float)atof(e) : 1.0f;
+}
+
+// List-major IVF-PQ scan (kernels_pqtc.cu): exact scan of the first pa probes -> per-query bound ->
+// tensor-core filter over the remaining probes -> exact re-score of the candidates.  Returns 1 when
+// the batch / shape does not qualify (caller runs the exact kernel over all probes).
+int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const float* xq, int kk, const float* ip,
+                                  const int32_t* probe_ids, const float* coarse_dis, int nprobe,
+                                  unsigned long long* adc_out, Scratch& s) {
+  const int mode = pqtc_mode();
+  if (!mode || !tc_enabled() || !d_cb16_ || !pqtc_supported(M_, dsub_) || dpad_ != d_) return 1;
+  if (kk > 2048 || nprobe < 2) return 1;
+  const int64_t npairs = (int64_t)nq * nprobe;
+  if (mode != 2 && npairs < (int64_t)nlist_ * 32) return 1;  // < 32 queries per list on average
+  cudaStream_t st = s.stream();
+  ListDirectory dir = lists_->directory();
+  // phase A depth: enough probes to expect >= 4 k' entries, so its k'-th score is a usable bound
+  const int64_t avg_len = std::max<int64_t>(1, lists_->total() / std::max(1, nlist_));
+  int pa = (int)std::min<int64_t>(nprobe - 1, std::max<int64_t>(1, (4 * (int64_t)kk + avg_len - 1) / avg_len));
+  if (const char* e = getenv("GB_PQTC_PA")) pa = std::max(1, std::min(nprobe - 1, atoi(e)));
+  const int cap = std::max(1024, std::min(8192, next_pow2(4 * kk)));
+  const int nsm = sm_count(device_);
+
+  // ---- phase A: exact keys of probes [0, pa) ----
+  const int pgA = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)pa * nq / ((int64_t)nsm * 32)));
+  const int ngA = (pa + pgA - 1) / pgA;
+  GB_ALLOC(partA, unsigned long long, (size_t)nq * ngA * kk, s);
+  GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, pa, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe));
+  unsigned long long* keysA = partA;
+  if (ngA > 1) {
+    keysA = s.alloc_n<unsigned long long>((size_t)nq * kk);
+    if (!keysA) return -1;
+    GB_CUDA(launch_select_keys(partA, (int64_t)ngA * kk, nq, ngA * kk, kk, keysA, kk, st));
+  }
+
+  // ---- phase B: group the remaining pairs by list, stage the operand tiles, filter ----
+  const int nseg = (int)std::min<int64_t>(64, std::max<int64_t>(1, (lists_->max_len() + kLmkSegRows - 1) / kLmkSegRows));
+  const int64_t max_groups = npairs / 128 + nlist_;
+  const int64_t max_items = max_groups * nseg;
+  if (max_items > INT32_MAX) return 1;
+  GB_ALLOC(d_masked, int32_t, npairs, s);
+  GB_ALLOC(d_cnt, int32_t, nlist_, s);
+  GB_ALLOC(d_start, int32_t, nlist_, s);
+  GB_ALLOC(d_cursor, int32_t, nlist_, s);
+  GB_ALLOC(d_item_start, int32_t, nlist_, s);
+  GB_ALLOC(d_grp_start, int32_t, nlist_, s);
+  GB_ALLOC(d_totals, int64_t, 3, s);
+  GB_ALLOC(d_pair_j, int64_t, npairs, s);
+  GB_ALLOC(d_items, LmTile, max_items, s);
+  GB_ALLOC(d_cand_cnt, int, nq, s);
+  const size_t tile_bytes = (size_t)(d_ / 8) * 2048;
+  const size_t a_bytes = (size_t)max_groups * tile_bytes;
+  const size_t meta_bytes = (size_t)max_groups * 128 * pqtc_pair_meta_bytes();
+  const size_t cand_bytes = (size_t)nq * cap * 8;
+  unsigned char* big = static_cast<unsigned char*>(big_acquire(a_bytes + meta_bytes + cand_bytes, st));
+  if (!big) return -1;
+  auto rel_fn = [this, big, st](void*) { big_release(big, st); };
+  std::unique_ptr<void, decltype(rel_fn)> rel(big, rel_fn);
+  unsigned char* a_scratch = big;
+  void* meta = big + a_bytes;
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(big + a_bytes + meta_bytes);
+  GB_CUDA(cudaMemsetAsync(d_cand_cnt, 0, sizeof(int) * nq, st));
+  GB_CUDA(launch_pqtc_mask_probes(probe_ids, npairs, nprobe, pa, d_masked, st));
+  GB_CUDA(launch_lmk_group(d_masked, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
+                           d_pair_j, d_items, st));
+  GB_CUDA(launch_pq_stage_pairs(xq, dpad_, d_, d_centroids_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe,
+                                coarse_dis, keysA, kk, kk, d_cbnrm_ + (size_t)M_ * 256, f, metric, pqtc_eps_scale(), a_scratch,
+                                meta, d_cand_cnt, cap, st));
+  GB_CUDA(launch_pqtc_scan(a_scratch, meta, d_cb16_, d_cbnrm_, d_items, (int)max_items, d_totals, dir, M_, dsub_, f, metric,
+                           d_cand_cnt, cand, cap, nsm, st));
+
+  // ---- phase C: candidates -> reference arithmetic, merged with phase A's keys ----
+  GB_CUDA(launch_pq_rescore(ip, nq, probe_ids, coarse_dis, nprobe, dir, M_, d_table_, d_cand_cnt, cand, cap, keysA, kk, kk,
+                            metric, f, adc_out, st));
+  // queries whose candidate list overflowed (or that had no bound): exact kernel over all probes, flag-gated
+  const int ngF = (nprobe + 31) / 32;
+  GB_ALLOC(partF, unsigned long long, (size_t)nq * ngF * kk, s);
+  GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, 32, dir, M_, d_table_, kk, metric, f, partF, st, nprobe,
+                            d_cand_cnt, cap));
+  GB_CUDA(launch_pq_fallback_merge(d_cand_cnt, cap, nq, partF, ngF, kk, adc_out, st));
+  if (const char* dump = getenv("GB_PQTC_DUMP")) {  // debugging aid: candidate lists + phase A keys to a file
+    std::vector<int> h(nq);
+    std::vector<unsigned long long> hc((size_t)nq * cap), hk((size_t)nq * kk);
+    GB_CUDA(cudaMemcpyAsync(h.data(), d_cand_cnt, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(hc.data(), cand, hc.size() * 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaMemcpyAsync(hk.data(), keysA, hk.size() * 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    int64_t ht[3];
+    GB_CUDA(cudaMemcpy(ht, d_totals, sizeof(ht), cudaMemcpyDeviceToHost));
+    std::vector<int64_t> hpj((size_t)npairs);
+    std::vector<LmTile> hit((size_t)ht[1]);
+    GB_CUDA(cudaMemcpy(hpj.data(), d_pair_j, hpj.size() * 8, cudaMemcpyDeviceToHost));
+    GB_CUDA(cudaMemcpy(hit.data(), d_items, hit.size() * sizeof(LmTile), cudaMemcpyDeviceToHost));
+    if (FILE* fp = fopen(dump, "wb")) {
+      const int hdr[8] = {nq, cap, kk, pa, (int)ht[1], (int)npairs, (int)sizeof(LmTile), (int)ht[2]};
+      fwrite(hdr, 4, 8, fp);
+      fwrite(h.data(), 4, h.size(), fp);
+      fwrite(hc.data(), 8, hc.size(), fp);
+      fwrite(hk.data(), 8, hk.size(), fp);
+      fwrite(hpj.data(), 8, hpj.size(), fp);
+      fwrite(hit.data(), sizeof(LmTile), hit.size(), fp);
+      fclose(fp);
+    }
+  }
+  if (getenv("GB_PQTC_STATS")) {  // diagnostics: candidates per query, overflowed queries
+    std::vector<int> h(nq);
+    GB_CUDA(cudaMemcpyAsync(h.data(), d_cand_cnt, sizeof(int) * nq, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    long long tot = 0, over = 0, mx = 0;
+    for (int v : h) {
+      if (v > cap) over++;
+      else tot += v, mx = std::max<long long>(mx, v);
+    }
+    fprintf(stderr, "[pqtc] nq=%d k'=%d pa=%d cap=%d: candidates mean %.1f max %lld, overflowed queries %lld\n", nq, kk, pa,
+            cap, nq > over ? (double)tot / (nq - over) : 0.0, mx, over);
+  }
+  return 0;
+}
+
 // GammaIVFPQIndex::search_preassigned (gamma_index_ivfpq.cc:730-947)
 int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metric, int nq, const float* xq, int k,
                          const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* out_keys,
@@ -1719,26 +1870,37 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
   const bool rerank = ctx.params.recall_num > 0;
   int kk = k;
   if (ctx.params.recall_num > k) kk = ctx.params.recall_num;
-  if (kk > 4096) kk = 4096;
+  if (kk > 4096) {
+    set_last_error("IVFPQ: recall_num / topn above 4096 is not supported");
+    return -1;
+  }
   GB_ALLOC(ip, float, (size_t)nq * M_ * 256, s);
   GB_CUDA(launch_pq_ip_table(xq, dpad_, nq, d_pq_, M_, dsub_, ip, st));
-  int pg = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)nprobe * nq / (148 * 32)));
-  int ngroups = (nprobe + pg - 1) / pg;
-  GB_ALLOC(partial, unsigned long long, (size_t)nq * ngroups * kk, s);
-  last_scan_kernel_ = "ivfpq_scan_kernel";
-  scan_timer_begin(st);
-  GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, pg, lists_->directory(), M_, d_table_, kk, metric, f,
-                            partial, st));
-  scan_timer_end(st);
   unsigned long long* adc = out_keys;
-  if (rerank || ngroups > 1) {
-    if (rerank) {
-      adc = s.alloc_n<unsigned long long>((size_t)nq * kk);
-      if (!adc) return -1;
-    }
-    GB_CUDA(launch_select_keys(partial, (int64_t)ngroups * kk, nq, ngroups * kk, kk, adc, kk, st));
+  if (rerank) {
+    adc = s.alloc_n<unsigned long long>((size_t)nq * kk);
+    if (!adc) return -1;
+  }
+  scan_timer_begin(st);
+  int lm = scan_listmajor_pq(f, metric, nq, xq, kk, ip, probe_ids, coarse_dis, nprobe, adc, s);
+  if (lm < 0) return -1;
+  if (lm == 0) {
+    last_scan_kernel_ = "pqtc_scan_kernel";
+    scan_timer_end(st);
   } else {
-    GB_CUDA(cudaMemcpyAsync(out_keys, partial, (size_t)nq * kk * 8, cudaMemcpyDeviceToDevice, st));
+    const int nsm = sm_count(device_);
+    int pg = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)nprobe * nq / ((int64_t)nsm * 32)));
+    int ngroups = (nprobe + pg - 1) / pg;
+    GB_ALLOC(partial, unsigned long long, (size_t)nq * ngroups * kk, s);
+    last_scan_kernel_ = "ivfpq_scan_kernel";
+    GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, pg, lists_->directory(), M_, d_table_, kk, metric, f,
+                              partial, st));
+    scan_timer_end(st);
+    if (ngroups > 1) {
+      GB_CUDA(launch_select_keys(partial, (int64_t)ngroups * kk, nq, ngroups * kk, kk, adc, kk, st));
+    } else {
+      GB_CUDA(cudaMemcpyAsync(adc, partial, (size_t)nq * kk * 8, cudaMemcpyDeviceToDevice, st));
+    }
   }
   if (rerank) {
     // "for opq, rerank need raw vector" (gamma_index_ivfpq.cc:735): original queries against the raw store

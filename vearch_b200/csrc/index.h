@@ -407,6 +407,10 @@ class IVFPQIndex : public IVFFlatIndex {
                    const int32_t* d_assign, Scratch& s) override;
   int train_extra(const float* xtrain, int64_t n, Scratch& s) override;
   int rebuild_table(cudaStream_t st);
+  // list-major scan through the tensor-core filter (kernels_pqtc.cu); 1 = not applicable
+  int scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const float* xq, int kk, const float* ip,
+                        const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* adc_out,
+                        Scratch& s);
 
   const float* train_transform(const float* xt, int64_t n, Scratch& s) override;
   const float* transform_dev(const float* x, int64_t n, Scratch& s) override;
@@ -414,6 +418,8 @@ class IVFPQIndex : public IVFFlatIndex {
   int M_, dsub_;
   float* d_pq_ = nullptr;     // [M][256][dsub]
   float* d_table_ = nullptr;  // [nlist][M][256] (L2 only)
+  uint16_t* d_cb16_ = nullptr;  // [M][256][dsub] bf16, pre-scaled (tensor-core filter)
+  float* d_cbnrm_ = nullptr;    // [M][256] |pq|^2, then rmax2
   float* d_opq_ = nullptr;    // [d][dpad] rows of the OPQ rotation A (y = A x); nullptr: no OPQ
   bool opq_trained_ = false;
 

@@ -1,0 +1,633 @@
+// K5, list-major: the IVF-PQ ADC scan of a large query batch as a filtered tensor-core contraction.
+//
+// Reference semantics: GammaIVFPQScanner::scan_list_with_table (index/impl/gamma_index_ivfpq.h:923-953)
+// driven by search_preassigned (gamma_index_ivfpq.cc:730-947): per (query, probed list, entry)
+//     dis = dis0 + sum_m tab[m][code[m]],   tab = T[list] - 2 ip[query]   (L2, precomputed-table form)
+//     dis = <x, centroid> + sum_m ip[query][m][code[m]]                    (inner product)
+// and the k' best (k' = recall_num or k) survive.  ivfpq_scan_kernel (kernels_ivfpq.cu) evaluates that
+// sum literally, 16 shared-memory gathers per (query, entry): it is bound by instruction issue and
+// LDS wavefronts, not by HBM.  When every list is probed by dozens of queries of the same batch the
+// same numbers are a dense contraction:
+//     sum_m tab[m][code[m]] = |r_e|^2 - 2 <x - c_list, r_e>,   r_e = the entry's PQ reconstruction,
+// i.e. (query, list) pairs x decoded entries.  This file computes THAT on tcgen05 in bf16 and uses it
+// only as a FILTER; every number that leaves the pipeline is recomputed with the reference's own
+// arithmetic, so results stay bit-identical to the LUT kernel and to the oracle:
+//
+//   phase A  the exact LUT kernel scans the first `pa` probes of every query and yields k' exact
+//            keys; its k'-th score B_q is an upper bound of the query's final k'-th score;
+//   phase B  (this file) for the remaining probes: pairs grouped by list (lmk_group), per group a
+//            bf16 operand tile of (x - c_list) rows staged once (pq_stage_pairs_kernel), then a
+//            persistent warp-specialised kernel (pqtc_scan_kernel) decodes 128 entries at a time
+//            from their codes into the second operand (codebook in shared memory, pre-scaled by -2),
+//            multiplies 128 pairs x 128 entries x d on the tensor core and compares
+//            acc + |r_e|^2 against  B_q - dis0 + eps(pair).  eps bounds |approximate - reference fp32|
+//            rigorously (bf16 rounding of both operands: 2^-7 |a||r| ; fp32 noise of both evaluations),
+//            so every entry whose reference score is <= B_q passes.  Passing entries (a few per
+//            query beyond k') are appended to the query's candidate list as (probe, position);
+//   phase C  pq_rescore_kernel re-evaluates the candidates with the reference arithmetic (same
+//            fmaf / add order as the LUT kernel), merges them with phase A's keys and keeps k'.
+//   A query whose candidate list overflows (no usable bound, adversarial data) is redone by the
+//   exact kernel over all its probes (flag-gated launch), so the result never depends on the filter.
+//
+// Operand layout: canonical no-swizzle K-major UMMA tiles of bf16 (8-row x 16-byte core matrices,
+// LBO 2048 = next core matrix along K, SBO 128 = next 8 rows).  With dsub = 8 a sub-quantiser's
+// centroid IS one 16-byte core-matrix row: decoding an entry is M x (LDS.128 from the codebook,
+// STS.128 into the tile), conflict-free on the store side (consecutive entries -> consecutive rows).
+//
+// Algorithmic bytes: (M + 8) per scanned entry per 128-pair group instead of per pair.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace gb {
+
+namespace {
+
+constexpr int PT_M = 128;          // pairs per group  (MMA M, TMEM lanes)
+constexpr int PT_N = 128;          // entries per tile (MMA N, accumulator columns)
+constexpr int PT_NT = 320;         // warps 0-3 epilogue, 4-7 decode, 8 TMA producer, 9 MMA issuer
+constexpr int PT_CS = 4;           // code stages
+constexpr int PT_KSUB = 256;
+
+struct PtShared {
+  uint64_t code_full[PT_CS], code_empty[PT_CS];
+  uint64_t b_full[2], b_empty[2], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+  alignas(16) float ne[2][PT_N];  // |r_e|^2 of the tile's entries, +inf = can never be returned
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  return r;
+}
+
+// ---- tables derived from the PQ codebook ---------------------------------------------------------
+// cb[m][c][0..dsub) = bf16(scale * pq[m][c][.]),  nrm[m][c] = |pq[m][c]|^2 (fp32, L2 only),
+// rmax2[0] = sum_m max_c |pq[m][c]|^2  (single CTA, M*256 threads-strided)
+__global__ void __launch_bounds__(256)
+    pqtc_tables_kernel(const float* __restrict__ pq, int M, int dsub, float scale, uint16_t* __restrict__ cb,
+                       float* __restrict__ nrm, float* __restrict__ rmax2) {
+  __shared__ float s_max[256];
+  float total = 0.f;
+  for (int m = 0; m < M; m++) {
+    const int c = threadIdx.x;
+    const float* p = pq + ((int64_t)m * PT_KSUB + c) * dsub;
+    float n2 = 0.f;
+    for (int j = 0; j < dsub; j++) {
+      const float v = p[j];
+      n2 = fmaf(v, v, n2);
+      const uint32_t b = pack_bf16x2(scale * v, 0.f);
+      cb[((int64_t)m * PT_KSUB + c) * dsub + j] = (uint16_t)(b & 0xFFFFu);
+    }
+    nrm[m * PT_KSUB + c] = n2;
+    s_max[c] = n2;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (c < off) s_max[c] = fmaxf(s_max[c], s_max[c + off]);
+      __syncthreads();
+    }
+    total += s_max[0];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rmax2[0] = total;
+}
+
+// ---- probes [0, pa) are phase A's: hide them from the grouping -----------------------------------
+__global__ void pqtc_mask_probes_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, int pa,
+                                        int32_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npairs) return;
+  out[j] = (int)(j % nprobe) < pa ? -1 : probe_ids[j];
+}
+
+// ---- per pair group: the A operand tile and the pairs' thresholds ---------------------------------
+struct PairMeta {
+  float thr;  // candidate  <=>  acc + ne <= thr
+  float lo;   // ... and acc + ne >= lo  (the other side of the score window, checked on the rare path)
+  int q, p;
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(PT_M)
+    pq_stage_pairs_kernel(const float* __restrict__ xq, int64_t ldq, int d, const float* __restrict__ coarse, int64_t ldc,
+                          const LmTile* __restrict__ items, const int64_t* __restrict__ totals,
+                          const int64_t* __restrict__ pair_j, int nprobe, const float* __restrict__ coarse_dis,
+                          const unsigned long long* __restrict__ bound_keys, int64_t bound_stride, int kprime,
+                          const float* __restrict__ rmax2, float min_score, float max_score, float eps_scale,
+                          unsigned char* __restrict__ a_scratch, PairMeta* __restrict__ meta, int* __restrict__ cand_cnt,
+                          int cap) {
+  if ((int64_t)blockIdx.x >= totals[1]) return;
+  const LmTile t = items[blockIdx.x];
+  if (t.seg != 0) return;  // one staging per pair group: the first item of the group owns the slot
+  const int r = threadIdx.x;
+  const int kc_n = d / 8;
+  unsigned char* tile = a_scratch + (int64_t)t.grp * ((int64_t)kc_n * 2048);
+  PairMeta pm{-INFINITY, INFINITY, -1, 0};
+  const float* x = nullptr;
+  const float* c = nullptr;
+  if (r < t.npairs) {
+    const int64_t j = pair_j[t.pair0 + r];
+    pm.q = (int)(j / nprobe);
+    pm.p = (int)(j - (int64_t)pm.q * nprobe);
+    x = xq + (int64_t)pm.q * ldq;
+    c = coarse + (int64_t)t.list * ldc;
+  }
+  float na2 = 0.f, nx2 = 0.f, nc2 = 0.f;
+  for (int kc = 0; kc < kc_n; kc++) {
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (x) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + kc * 8)), x1 = __ldg(reinterpret_cast<const float4*>(x + kc * 8 + 4));
+      float a[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (METRIC == kMetricL2) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(c + kc * 8)), c1 = __ldg(reinterpret_cast<const float4*>(c + kc * 8 + 4));
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          nx2 = fmaf(a[u], a[u], nx2);
+          nc2 = fmaf(cc[u], cc[u], nc2);
+          a[u] -= cc[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) na2 = fmaf(a[u], a[u], na2);
+      out.x = pack_bf16x2(a[0], a[1]), out.y = pack_bf16x2(a[2], a[3]);
+      out.z = pack_bf16x2(a[4], a[5]), out.w = pack_bf16x2(a[6], a[7]);
+    }
+    *reinterpret_cast<uint4*>(tile + (int64_t)kc * 2048 + r * 16) = out;
+  }
+  if (x) {
+    const float dis0 = coarse_dis[(int64_t)pm.q * nprobe + pm.p];
+    const unsigned long long bk = bound_keys[(int64_t)pm.q * bound_stride + kprime - 1];
+    const float R2 = rmax2[0], R = sqrtf(R2);
+    if (bk == kKeySentinel) {
+      // phase A found fewer than k' entries: no bound -> the exact kernel redoes this query
+      atomicMax(cand_cnt + pm.q, cap + 1);
+    } else {
+      const float B = ord2score((uint32_t)(bk >> 32), METRIC);
+      if (METRIC == kMetricL2) {
+        // |approx - reference| <= 2^-7 (1 + 2^-9) |a| |r|  (bf16 rounding of both operands, -2 scaling exact)
+        //   + fp32 noise of the two evaluations, bounded by 2^-17 of the magnitudes that enter them
+        const float Z = fabsf(dis0) + R2 + 2.f * (sqrtf(nx2) + sqrtf(nc2)) * R;
+        const float eps = eps_scale * (1.05f * 0.0078125f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
+        pm.thr = fminf(B, max_score) - dis0 + eps;
+        pm.lo = min_score - dis0 - eps;
+      } else {
+        // score = dis0 - acc (the codebook is staged negated); better = larger
+        const float Z = fabsf(dis0) + sqrtf(na2) * R;
+        const float eps = eps_scale * (1.05f * 0.00390625f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
+        pm.thr = dis0 - fmaxf(B, min_score) + eps;
+        pm.lo = dis0 - max_score - eps;
+      }
+    }
+  }
+  meta[(int64_t)t.grp * PT_M + r] = pm;
+}
+
+// ---- the scan ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pt_load32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// rare path of the epilogue: the 32 columns of one pair contain at least one candidate
+__device__ __noinline__ void pt_push_hits(const uint32_t (&v)[32], const float* ne32, float thr, float lo, int q, int p,
+                                          uint32_t pos0, int* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
+                                          int cap) {
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+    const float s = __uint_as_float(v[j]) + ne32[j];
+    if (s <= thr && s >= lo) {
+      const int slot = atomicAdd(cand_cnt + q, 1);
+      if (slot < cap) cand[(int64_t)q * cap + slot] = ((unsigned long long)(uint32_t)p << 32) | (pos0 + (uint32_t)j);
+    }
+  }
+}
+
+// M sub-quantisers of DSUB dimensions, d = M * DSUB, DSUB in {4, 8, 16, 32}; HAS_NORM: L2 (|r|^2 term)
+template <int M, int DSUB, bool HAS_NORM>
+__global__ void __launch_bounds__(PT_NT, 1)
+    pqtc_scan_kernel(const unsigned char* __restrict__ a_scratch, const PairMeta* __restrict__ meta,
+                     const uint16_t* __restrict__ cb_g, const float* __restrict__ nrm_g, const LmTile* __restrict__ items,
+                     const int64_t* __restrict__ totals, ListDirectory dir, FilterArgs f, int* __restrict__ cand_cnt,
+                     unsigned long long* __restrict__ cand, int cap) {
+  constexpr int D = M * DSUB;
+  constexpr int KC = D / 8;                // core matrices along K
+  constexpr int TILE = KC * 2048;          // one 128-row operand tile, bytes
+  constexpr int CB_BYTES = M * PT_KSUB * DSUB * 2;
+  constexpr int NRM_BYTES = HAS_NORM ? M * PT_KSUB * 4 : 0;
+  constexpr int CODE_STAGE = PT_N * M;
+  constexpr int UNIT = DSUB * 2;           // bytes of one centroid in the bf16 codebook
+  static_assert(D % 16 == 0 && M % 4 == 0, "shape");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ PtShared sh;
+  unsigned char* cb = smem;
+  float* nrm = reinterpret_cast<float*>(smem + CB_BYTES);
+  unsigned char* a_buf = smem + CB_BYTES + NRM_BYTES;
+  unsigned char* b_buf = a_buf + 2 * TILE;
+  unsigned char* code_buf = b_buf + 2 * TILE;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t n_items = totals[1];
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
+                 "n"(2 * PT_N)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int s = 0; s < PT_CS; s++) {
+      mbar_init(&sh.code_full[s], 1);       // producer's arrive.expect_tx; the bulk copy completes the phase
+      mbar_init(&sh.code_empty[s], PT_N);   // every decode thread has read its code
+    }
+    for (int b = 0; b < 2; b++) {
+      mbar_init(&sh.b_full[b], PT_N);       // every decode thread has written its row
+      mbar_init(&sh.b_empty[b], 1);         // tcgen05.commit
+      mbar_init(&sh.a_full[b], 1);          // bulk copy
+      mbar_init(&sh.a_empty[b], 1);         // tcgen05.commit after the item's last tile
+      mbar_init(&sh.acc_full[b], 1);        // tcgen05.commit
+      mbar_init(&sh.acc_empty[b], PT_M);    // every epilogue thread
+    }
+    mbar_fence_init();
+  }
+  // codebook (bf16, pre-scaled) and centroid norms: resident for the CTA's lifetime
+  for (int i = tid; i < CB_BYTES / 16; i += PT_NT)
+    reinterpret_cast<uint4*>(cb)[i] = __ldg(reinterpret_cast<const uint4*>(cb_g) + i);
+  if (HAS_NORM)
+    for (int i = tid; i < NRM_BYTES / 16; i += PT_NT)
+      reinterpret_cast<float4*>(nrm)[i] = __ldg(reinterpret_cast<const float4*>(nrm_g) + i);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = sh.tmem_base;
+
+  if (warp < 4) {
+    // ======================= epilogue: thread = pair =======================
+    uint32_t bn = 0;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const LmTile t = items[it];
+      const PairMeta pm = meta[(int64_t)t.grp * PT_M + tid];
+      const int ntiles = (t.nrows + PT_N - 1) / PT_N;
+      for (int i = 0; i < ntiles; i++, bn++) {
+        const int b = bn & 1;
+        mbar_wait(&sh.acc_full[b], (bn >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c0 = 0; c0 < PT_N; c0 += 32) {
+          uint32_t v[32];
+          pt_load32(tmem_d + lane_base + (uint32_t)(b * PT_N + c0), v);
+          const float* ne32 = &sh.ne[b][c0];
+          float mn = INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 n4 = *reinterpret_cast<const float4*>(ne32 + j4);
+            const float s0 = __uint_as_float(v[j4]) + n4.x, s1 = __uint_as_float(v[j4 + 1]) + n4.y;
+            const float s2 = __uint_as_float(v[j4 + 2]) + n4.z, s3 = __uint_as_float(v[j4 + 3]) + n4.w;
+            mn = fminf(mn, fminf(fminf(s0, s1), fminf(s2, s3)));
+          }
+          if (mn <= pm.thr)
+            pt_push_hits(v, ne32, pm.thr, pm.lo, pm.q, pm.p, (uint32_t)(t.row0 + i * PT_N + c0), cand_cnt, cand, cap);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&sh.acc_empty[b]);
+      }
+    }
+  } else if (warp < 8) {
+    // ======================= decode: thread = entry of the tile =======================
+    const int e = tid - 4 * 32;
+    uint32_t cn = 0, bn = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const LmTile t = items[it];
+      const int64_t* __restrict__ lids = dir.ids[t.list];
+      const int row_end = t.row0 + t.nrows;
+      const int ntiles = (t.nrows + PT_N - 1) / PT_N;
+      for (int i = 0; i < ntiles; i++, cn++, bn++) {
+        const int s = cn % PT_CS;
+        mbar_wait(&sh.code_full[s], (cn / PT_CS) & 1);
+        uint32_t w[M / 4];
+        {
+          const unsigned char* cp = code_buf + s * CODE_STAGE + e * M;
+          if (M % 16 == 0) {
+#pragma unroll
+            for (int u = 0; u < M / 16; u++) {
+              const uint4 q4 = reinterpret_cast<const uint4*>(cp)[u];
+              w[4 * u] = q4.x, w[4 * u + 1] = q4.y, w[4 * u + 2] = q4.z, w[4 * u + 3] = q4.w;
+            }
+          } else if (M % 8 == 0) {
+#pragma unroll
+            for (int u = 0; u < M / 8; u++) {
+              const uint2 q2 = reinterpret_cast<const uint2*>(cp)[u];
+              w[2 * u] = q2.x, w[2 * u + 1] = q2.y;
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < M / 4; u++) w[u] = reinterpret_cast<const uint32_t*>(cp)[u];
+          }
+        }
+        mbar_arrive(&sh.code_empty[s]);
+        // entries past the end of the segment decode whatever bytes the stage holds: finite values,
+        // masked by ne = +inf.  Tombstones (gamma_index_ivfpq.h:930) and the docid predicate
+        // (IsValid, :934-939) are resolved here, once per entry per 128 pairs.
+        const int row = t.row0 + i * PT_N + e;
+        bool valid = row < row_end;
+        if (valid) {
+          const int64_t raw = lids[row];
+          valid = raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw);
+        }
+        const int b = bn & 1;
+        mbar_wait(&sh.b_empty[b], ((bn >> 1) & 1) ^ 1);
+        unsigned char* brow = b_buf + b * TILE + e * 16;
+        float nsum = 0.f;
+#pragma unroll
+        for (int m = 0; m < M; m++) {
+          const uint32_t c = (w[m >> 2] >> (8 * (m & 3))) & 0xFFu;
+          const unsigned char* src = cb + (m * PT_KSUB + c) * UNIT;
+          if (DSUB == 4) {  // two sub-quantisers share a core-matrix row
+            const uint2 val = *reinterpret_cast<const uint2*>(src);
+            *reinterpret_cast<uint2*>(brow + (m >> 1) * 2048 + (m & 1) * 8) = val;
+          } else {
+#pragma unroll
+            for (int u = 0; u < UNIT / 16; u++) {
+              const uint4 val = reinterpret_cast<const uint4*>(src)[u];
+              *reinterpret_cast<uint4*>(brow + (m * (UNIT / 16) + u) * 2048) = val;
+            }
+          }
+          if (HAS_NORM) nsum += nrm[m * PT_KSUB + c];
+        }
+        // ne[b] is read by the epilogue of tile bn - 2: wait until it has released the buffer
+        mbar_wait(&sh.acc_empty[b], ((bn >> 1) & 1) ^ 1);
+        sh.ne[b][e] = valid ? nsum : INFINITY;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core proxy
+        mbar_arrive(&sh.b_full[b]);
+      }
+    }
+  } else if (warp == 8) {
+    // ======================= TMA producer (whole warp loops, one elected lane issues) =======================
+    uint32_t an = 0, cn = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const LmTile t = items[it];
+      if (t.nrows <= 0) continue;  // every role skips empty segments the same way
+      const int ab = an & 1;
+      mbar_wait(&sh.a_empty[ab], ((an >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&sh.a_full[ab], TILE);
+        bulk_g2s(a_buf + ab * TILE, a_scratch + (int64_t)t.grp * TILE, TILE, &sh.a_full[ab]);
+      }
+      __syncwarp();
+      const unsigned char* lcodes = dir.codes[t.list];
+      const int ntiles = (t.nrows + PT_N - 1) / PT_N;
+      for (int i = 0; i < ntiles; i++, cn++) {
+        const int s = cn % PT_CS;
+        mbar_wait(&sh.code_empty[s], ((cn / PT_CS) & 1) ^ 1);
+        if (elect_one()) {
+          const int n_e = min(PT_N, t.nrows - i * PT_N);
+          const uint32_t bytes = ((uint32_t)n_e * M + 15u) & ~15u;
+          mbar_arrive_expect_tx(&sh.code_full[s], bytes);
+          bulk_g2s(code_buf + s * CODE_STAGE, lcodes + (int64_t)(t.row0 + i * PT_N) * M, bytes, &sh.code_full[s]);
+        }
+        __syncwarp();
+      }
+      an++;
+    }
+  } else {
+    // ======================= MMA issuer (whole warp loops, one elected lane issues) =======================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (1 << 4), a = b = BF16 (1 << 7, 1 << 10),
+    // K-major A and B, N >> 3 at [17, 23), M >> 4 at [24, 29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PT_N >> 3) << 17) | ((uint32_t)(PT_M >> 4) << 24);
+    const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
+    uint32_t an = 0, bn = 0;
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const LmTile t = items[it];
+      if (t.nrows <= 0) continue;
+      const int ab = an & 1;
+      mbar_wait(&sh.a_full[ab], (an >> 1) & 1);
+      const int ntiles = (t.nrows + PT_N - 1) / PT_N;
+      for (int i = 0; i < ntiles; i++, bn++) {
+        const int b = bn & 1;
+        mbar_wait(&sh.b_full[b], (bn >> 1) & 1);
+        mbar_wait(&sh.acc_empty[b], ((bn >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint64_t da = lt_desc(a_base + (uint32_t)ab * TILE), db = lt_desc(b_base + (uint32_t)b * TILE);
+          const uint32_t acc = tmem_d + (uint32_t)(b * PT_N);
+#pragma unroll
+          for (int kk = 0; kk < KC / 2; kk++) {  // K = 16 per instruction: two core matrices = 4096 bytes further
+            const uint64_t adv = (uint64_t)((kk * 4096) >> 4);
+            tc_mma_bf16(acc, da + adv, db + adv, idesc, kk != 0);
+          }
+          tc_commit(&sh.b_empty[b]);
+          tc_commit(&sh.acc_full[b]);
+          if (i == ntiles - 1) tc_commit(&sh.a_empty[ab]);
+        }
+        __syncwarp();
+      }
+      an++;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(2 * PT_N) : "memory");
+  }
+}
+
+// ---- phase C: candidates -> reference arithmetic -> merge with phase A's keys ---------------------
+constexpr int RS_NT = 256;
+
+template <int METRIC>
+__global__ void __launch_bounds__(RS_NT)
+    pq_rescore_kernel(const float* __restrict__ ip_table, const int32_t* __restrict__ probe_ids,
+                      const float* __restrict__ coarse_dis, int nprobe, ListDirectory dir, int M, const float* __restrict__ T,
+                      const int* __restrict__ cand_cnt, const unsigned long long* __restrict__ cand, int cap,
+                      const unsigned long long* __restrict__ keys_a, int64_t keys_a_stride, int kprime, int NP,
+                      FilterArgs f, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(rs_smem);  // [NP]
+  float* ips = reinterpret_cast<float*>(buf + NP);                            // [M][256]
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int cnt = cand_cnt[q];
+  if (cnt > cap) return;  // overflow: the exact kernel redoes this query (pq_fallback_merge_kernel writes out)
+  const float4* ipq4 = reinterpret_cast<const float4*>(ip_table + (int64_t)q * M * PT_KSUB);
+  for (int i = tid; i < M * PT_KSUB / 4; i += RS_NT) reinterpret_cast<float4*>(ips)[i] = __ldg(ipq4 + i);
+  int n2 = 16;
+  while (n2 < kprime + cnt) n2 <<= 1;  // <= NP
+  for (int i = tid; i < n2; i += RS_NT) buf[i] = i < kprime ? keys_a[(int64_t)q * keys_a_stride + i] : kKeySentinel;
+  __syncthreads();
+  for (int i = tid; i < cnt; i += RS_NT) {
+    const unsigned long long rec = cand[(int64_t)q * cap + i];
+    const int p = (int)(rec >> 32);
+    const uint32_t pos = (uint32_t)rec;
+    const int l = probe_ids[(int64_t)q * nprobe + p];
+    float dis = coarse_dis[(int64_t)q * nprobe + p];
+    const unsigned char* code = dir.codes[l] + (int64_t)pos * M;
+    const float* Tl = METRIC == kMetricL2 ? T + (int64_t)l * M * PT_KSUB : nullptr;
+    // the reference's order: dis = dis0; dis += tab[m][code[m]], tab = T - 2 ip as ivfpq_scan_kernel builds it
+    for (int m = 0; m < M; m++) {
+      const int c = code[m];
+      const float a = ips[m * PT_KSUB + c];
+      dis += METRIC == kMetricL2 ? fmaf(-2.0f, a, __ldg(Tl + m * PT_KSUB + c)) : a;
+    }
+    const int64_t raw = dir.ids[l][pos];
+    if (raw >= 0 && dis <= f.max_score && dis >= f.min_score) buf[kprime + i] = make_key(score2ord<METRIC>(dis), (uint32_t)raw);
+  }
+  __syncthreads();
+  block_bitonic_sort(buf, n2);
+  for (int i = tid; i < kprime; i += RS_NT) out[(int64_t)q * kprime + i] = buf[i];
+}
+
+// overflowed queries: merge the exact kernel's per-group partials (sorted runs of k') into out[q]
+__global__ void __launch_bounds__(RS_NT)
+    pq_fallback_merge_kernel(const int* __restrict__ cand_cnt, int cap, const unsigned long long* __restrict__ partial,
+                             int ngroups, int kprime, int NP, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(rs_smem);
+  const int q = blockIdx.x, tid = threadIdx.x;
+  if (cand_cnt[q] <= cap) return;
+  const int n = ngroups * kprime;
+  for (int i = tid; i < NP; i += RS_NT) buf[i] = i < n ? partial[(int64_t)q * n + i] : kKeySentinel;
+  __syncthreads();
+  block_bitonic_sort(buf, NP);
+  for (int i = tid; i < kprime; i += RS_NT) out[(int64_t)q * kprime + i] = buf[i];
+}
+
+template <int M, int DSUB>
+cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* meta, const uint16_t* cb, const float* nrm,
+                              const LmTile* items, const int64_t* totals, ListDirectory dir, FilterArgs f, int metric,
+                              int* cand_cnt, unsigned long long* cand, int cap, int grid, cudaStream_t st) {
+  constexpr int D = M * DSUB;
+  const size_t base = (size_t)M * PT_KSUB * DSUB * 2 + 4 * (size_t)(D / 8) * 2048 + (size_t)PT_CS * PT_N * M;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    const size_t smem = base + (size_t)M * PT_KSUB * 4;
+    e = cudaFuncSetAttribute(pqtc_scan_kernel<M, DSUB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pqtc_scan_kernel<M, DSUB, true><<<grid, PT_NT, smem, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap);
+  } else {
+    e = cudaFuncSetAttribute(pqtc_scan_kernel<M, DSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+    if (e != cudaSuccess) return e;
+    pqtc_scan_kernel<M, DSUB, false><<<grid, PT_NT, base, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap);
+  }
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool pqtc_supported(int M, int dsub) {
+  return (M == 16 && dsub == 8) || (M == 8 && dsub == 16) || (M == 8 && dsub == 8) ||
+         (M == 16 && dsub == 4) || (M == 4 && dsub == 16) || (M == 4 && dsub == 32) || (M == 12 && dsub == 8) ||
+         (M == 4 && dsub == 8) || (M == 8 && dsub == 4);
+}
+
+size_t pqtc_pair_meta_bytes() { return sizeof(PairMeta); }
+
+cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uint16_t* cb, float* nrm, float* rmax2,
+                               cudaStream_t st) {
+  pqtc_tables_kernel<<<1, 256, 0, st>>>(pq, M, dsub, metric == kMetricL2 ? -2.0f : -1.0f, cb, nrm, rmax2);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pqtc_mask_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa, int32_t* out,
+                                    cudaStream_t st) {
+  if (npairs <= 0) return cudaSuccess;
+  pqtc_mask_probes_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, pa, out);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const float* coarse, int64_t ldc, const LmTile* items,
+                                  int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
+                                  const float* coarse_dis, const unsigned long long* bound_keys, int64_t bound_stride,
+                                  int kprime, const float* rmax2, FilterArgs f, int metric, float eps_scale,
+                                  unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, cudaStream_t st) {
+  if (max_items <= 0) return cudaSuccess;
+  if (d % 16) return cudaErrorInvalidValue;
+  if (metric == kMetricL2)
+    pq_stage_pairs_kernel<kMetricL2><<<max_items, PT_M, 0, st>>>(xq, ldq, d, coarse, ldc, items, totals, pair_j, nprobe,
+                                                                coarse_dis, bound_keys, bound_stride, kprime, rmax2,
+                                                                f.min_score, f.max_score, eps_scale, a_scratch,
+                                                                static_cast<PairMeta*>(meta), cand_cnt, cap);
+  else
+    pq_stage_pairs_kernel<kMetricIP><<<max_items, PT_M, 0, st>>>(xq, ldq, d, coarse, ldc, items, totals, pair_j, nprobe,
+                                                                coarse_dis, bound_keys, bound_stride, kprime, rmax2,
+                                                                f.min_score, f.max_score, eps_scale, a_scratch,
+                                                                static_cast<PairMeta*>(meta), cand_cnt, cap);
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* nrm,
+                             const LmTile* items, int max_items, const int64_t* totals, ListDirectory dir, int M, int dsub,
+                             FilterArgs f, int metric, int* cand_cnt, unsigned long long* cand, int cap, int num_sms,
+                             cudaStream_t st) {
+  if (max_items <= 0) return cudaSuccess;
+  const int grid = max_items < num_sms ? max_items : num_sms;
+  const PairMeta* pm = static_cast<const PairMeta*>(meta);
+#define GB_PT(MM, DS) \
+  if (M == MM && dsub == DS) return launch_scan_shape<MM, DS>(a_scratch, pm, cb, nrm, items, totals, dir, f, metric, cand_cnt, cand, cap, grid, st)
+  GB_PT(16, 8);
+  GB_PT(8, 16);
+  GB_PT(8, 8);
+  GB_PT(16, 4);
+  GB_PT(4, 16);
+  GB_PT(4, 32);
+  GB_PT(12, 8);
+  GB_PT(4, 8);
+  GB_PT(8, 4);
+#undef GB_PT
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
+                              ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,
+                              int cap, const unsigned long long* keys_a, int64_t keys_a_stride, int kprime, int metric,
+                              FilterArgs f, unsigned long long* out, cudaStream_t st) {
+  if (nq <= 0) return cudaSuccess;
+  const int NP = next_pow2(kprime + cap);
+  const size_t smem = (size_t)NP * 8 + (size_t)M * PT_KSUB * 4;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (metric == kMetricL2) {
+    e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pq_rescore_kernel<kMetricL2><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
+                                                         cap, keys_a, keys_a_stride, kprime, NP, f, out);
+  } else {
+    e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pq_rescore_kernel<kMetricIP><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
+                                                         cap, keys_a, keys_a_stride, kprime, NP, f, out);
+  }
+  note_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pq_fallback_merge(const int* cand_cnt, int cap, int nq, const unsigned long long* partial, int ngroups,
+                                     int kprime, unsigned long long* out, cudaStream_t st) {
+  if (nq <= 0) return cudaSuccess;
+  const int NP = next_pow2(ngroups * kprime < 16 ? 16 : ngroups * kprime);
+  const size_t smem = (size_t)NP * 8;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(pq_fallback_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  pq_fallback_merge_kernel<<<nq, RS_NT, smem, st>>>(cand_cnt, cap, partial, ngroups, kprime, NP, out);
+  note_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace gb

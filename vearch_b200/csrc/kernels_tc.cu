@@ -33,6 +33,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_common.cuh"
 
 namespace gb {
 
@@ -43,28 +44,7 @@ constexpr int TC_TILE_BYTES = TC_M * TC_BK * 4;          // 8 KiB per operand pa
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;        // a_hi, a_lo, b_hi, b_lo
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES;      // 64 KiB
 
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) |
-  // base_offset 0 | lbo_mode 0 | layout_type SWIZZLE_NONE (0) [61,64)
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " setp.ne.b32 p, %4, 0;\n"
-      " tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 // One 128 x 128 tile: D[i][j] = <A_i, B_j> over d columns.  arow / brow: row pointers of THIS
 // thread's row of A and B (nullptr => all zeros).  On return the accumulator sits in TMEM at
@@ -493,9 +473,6 @@ struct LwShared {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int METRIC>
 __global__ void __launch_bounds__(LW_NT, 2)
@@ -721,23 +698,7 @@ struct LtShared {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " elect.sync _|p, 0xffffffff;\n"
-      " selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 
-// descriptor of a no-swizzle K-major operand tile at shared address `addr` (LBO 2048, SBO 128): the
-// high word is constant, the low word is linear in the address
-__device__ __forceinline__ uint64_t lt_desc(uint32_t addr) {
-  return ((uint64_t)0x4008u << 32) | (uint64_t)((addr >> 4) | 0x800000u);
-}
 
 template <int METRIC>
 __global__ void __launch_bounds__(LT_NT, 2)
