@@ -74,11 +74,22 @@ int gb_index_search(gb_index *index, int nq, const float *x, int k, const char *
 int gb_index_search_device(gb_index *index, int nq, const float *x_dev, int64_t ld, int k,
                            const char *retrieval_params_json, int brute_force, float *out_scores_dev,
                            int64_t *out_ids_dev, void *stream);
+/* Same, additionally (or only: out_scores_dev / out_ids_dev may be NULL) writing the nq x k result KEYS,
+ * (order-preserving score bits << 32) | local doc id, best first, 0xFF..FF padded: what one partition
+ * contributes to the cross-partition merge (one all-gather instead of scores + ids). */
+int gb_index_search_device_keys(gb_index *index, int nq, const float *x_dev, int64_t ld, int k,
+                                const char *retrieval_params_json, int brute_force, unsigned long long *out_keys_dev,
+                                float *out_scores_dev, int64_t *out_ids_dev, void *stream);
+/* {"stage": ms, ...}: device time per stage of the searches run since the last call with timing enabled
+ * (CUDA events on the launching stream); *json_out is malloc'd, the caller frees it */
+int gb_index_stage_times(gb_index *index, char **json_out, int *out_len);
 /* device time of the dominant scan kernel(s) of the last search, ms (0 unless timing enabled) */
 void gb_index_set_scan_timing(gb_index *index, int on);
 float gb_index_last_scan_ms(gb_index *index);
 /* name of the scan kernel(s) that served the last search (bench roofline label) */
 const char *gb_index_last_scan_kernel(gb_index *index);
+/* JSON details of the path that served the last search (e.g. probes scanned exactly before the tensor-core filter) */
+const char *gb_index_last_scan_info(gb_index *index);
 
 /* ---- index-state exchange (parity tests share centroids / codebooks / lists with the oracle,
  * SURVEY.md 8c; also the substrate for Dump/Load) ---- */
@@ -136,6 +147,9 @@ int gb_kmeans_update(int device, const float *x, int64_t n, int d, int k, const 
  * nparts x nq x k, outputs nq x k with ids = (partition << 32) | local id */
 int gb_merge_partitions_device(int device, const float *dis_dev, const int64_t *ids_dev, int nparts, int nq, int k,
                                int metric, float *out_dis_dev, int64_t *out_ids_dev, void *stream);
+/* the same merge from the partitions' result keys [nparts][nq][k] (gb_index_search_device_keys) */
+int gb_merge_partition_keys_device(int device, const unsigned long long *keys_dev, int nparts, int nq, int k, int metric,
+                                   float *out_dis_dev, int64_t *out_ids_dev, void *stream);
 
 /* exact (CUDA-core fp32) or tensor-core (tcgen05 3xTF32) score matrix, host in/out: out[n][m] */
 int gb_debug_dist_matrix(int device, const float *x, int n, const float *c, int m, int d, int metric, int use_tc,

@@ -51,12 +51,17 @@ def _declare(l):
     l.gb_index_mem_bytes.argtypes = [vp, i32]
     l.gb_index_search.argtypes = [vp, i32, vp, i32, cstr, i32, vp, vp, i64, f32, f32, vp, vp]
     l.gb_index_search_device.argtypes = [vp, i32, vp, i64, i32, cstr, i32, vp, vp, vp]
+    l.gb_index_search_device_keys.argtypes = [vp, i32, vp, i64, i32, cstr, i32, vp, vp, vp, vp]
+    l.gb_index_stage_times.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    l.gb_merge_partition_keys_device.argtypes = [i32, vp, i32, i32, i32, i32, vp, vp, vp]
     l.gb_index_set_scan_timing.restype = None
     l.gb_index_set_scan_timing.argtypes = [vp, i32]
     l.gb_index_last_scan_ms.restype = f32
     l.gb_index_last_scan_ms.argtypes = [vp]
     l.gb_index_last_scan_kernel.restype = cstr
     l.gb_index_last_scan_kernel.argtypes = [vp]
+    l.gb_index_last_scan_info.restype = cstr
+    l.gb_index_last_scan_info.argtypes = [vp]
     l.gb_index_nlist.argtypes = [vp]
     l.gb_index_set_centroids.argtypes = [vp, vp, i32]
     l.gb_index_get_centroids.argtypes = [vp, vp]

@@ -239,6 +239,8 @@ Status Engine::CreateTable(const uint8_t* fb, size_t len) {
     fields_.push_back({"_id", DT_STRING, false});
   }
   values_.assign(fields_.size(), {});
+  sidx_.assign(fields_.size(), ScalarIndex());
+  for (size_t fi = 0; fi < fields_.size(); fi++) sidx_[fi].built = fields_[fi].indexed;
   size_t nvec = t.vec_len(2);
   if (nvec == 0) return Status::Make(kInvalidArgument, space_name_ + " table has no vector field");
   FbTable v = t.vec_table(2, 0);
@@ -337,12 +339,21 @@ Index* Engine::index_of(const std::string& vec_name, int* dim) {
 
 int Engine::flush_pending_locked() {
   if (pending_n_ == 0) return 0;
+  // Row i of every vector field must stay document i: a field is appended only while its store is as long as the
+  // primary one was when this flush began, so a retry after a partial failure appends exactly the missing fields,
+  // and the pending buffers are dropped only when every field has taken its rows.
+  const int64_t base = index_->store().size();
   for (auto& e : extra_) {
+    if (e.index->store().size() == base + pending_n_) continue;  // taken by an earlier, partially failed flush
+    if (e.index->store().size() != base || (int64_t)e.pending.size() != (int64_t)pending_n_ * e.dim) {
+      set_last_error("vector fields out of step (field " + e.name + ")");
+      return -1;
+    }
     if (e.index->add_vectors(e.pending.data(), pending_n_)) return -1;
-    e.pending.clear();
   }
   int rc = index_->add_vectors(pending_.data(), pending_n_);
   if (rc) return rc;
+  for (auto& e : extra_) e.pending.clear();
   pending_.clear();
   pending_n_ = 0;
   return 0;
@@ -386,7 +397,11 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
   auto it = key2docid_.find(key);
   int docid = it == key2docid_.end() ? -1 : it->second;
   if (docid != -1 && docid < max_docid_) {  // Update (engine.cc:703-710, 774-850)
-    for (auto& f : table_fields) values_[field_idx_[f.name]][docid] = f.value;
+    for (auto& f : table_fields) {
+      const int fi = field_idx_[f.name];
+      values_[fi][docid] = f.value;
+      scalar_index_put(fi, docid, f.value);
+    }
     if (has_vec) {
       if (vec_len != (size_t)dim_ * 4) return -1;
       std::vector<float> x(dim_);
@@ -414,6 +429,8 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
   for (size_t fi = 0; fi < fields_.size(); fi++) values_[fi].emplace_back();
   for (auto& f : table_fields) values_[field_idx_[f.name]][max_docid_] = f.value;
   values_[field_idx_["_id"]][max_docid_] = key;
+  for (size_t fi = 0; fi < fields_.size(); fi++)
+    if (fields_[fi].indexed) scalar_index_put((int)fi, max_docid_, values_[fi][max_docid_]);
   keys_.push_back(key);
   key2docid_[key] = max_docid_;
   pending_.resize((size_t)(pending_n_ + 1) * dim_);
@@ -429,7 +446,8 @@ int Engine::AddOrUpdate(const uint8_t* fb, size_t len) {
   if (pending_n_ >= 8192 && flush_pending_locked()) return -5;
   // auto-start indexing (engine.cc:753-761)
   if (refresh_interval_ >= 0 && indexing_state_.load() == 0 && index_status_.load() == 0 &&
-      max_docid_ - delete_num_ >= training_threshold_) {
+      max_docid_ - delete_num_ >= training_threshold_ &&
+      now_ms() - last_train_failure_ms_.load() >= kTrainRetryMs) {  // a failed training is retried after a back-off
     lk.unlock();
     BuildIndex();
   }
@@ -574,49 +592,135 @@ std::vector<std::string> split001(const std::string& s) {
 }
 }  // namespace
 
+static bool is_float_type(int dt) { return dt == DT_FLOAT || dt == DT_DOUBLE; }
+static bool is_string_type(int dt) { return dt == DT_STRING || dt == DT_STRINGARRAY; }
+// raw little-endian field bytes -> (int64 | double); false: wrong width for the type
+static bool decode_num(int dt, const std::string& v, int64_t* iv, double* fv) {
+  const size_t w = (dt == DT_INT || dt == DT_FLOAT) ? 4 : (dt == DT_BOOL ? 1 : 8);
+  if (v.size() != w) return false;
+  switch (dt) {
+    case DT_INT: {
+      int32_t x;
+      memcpy(&x, v.data(), 4);
+      *iv = x;
+      return true;
+    }
+    case DT_FLOAT: {
+      float x;
+      memcpy(&x, v.data(), 4);
+      *fv = x;
+      return true;
+    }
+    case DT_DOUBLE: memcpy(fv, v.data(), 8); return true;
+    case DT_BOOL: *iv = (uint8_t)v[0]; return true;
+    default: memcpy(iv, v.data(), 8); return true;  // DT_LONG, DT_DATE
+  }
+}
+
+void Engine::scalar_index_put(int fi, int docid, const std::string& value) {
+  if (fi >= (int)sidx_.size() || !sidx_[fi].built) return;
+  ScalarIndex& si = sidx_[fi];
+  const int dt = fields_[fi].data_type;
+  if (is_string_type(dt)) {
+    if (dt == DT_STRINGARRAY) {
+      for (const auto& e : split001(value)) {
+        auto& pl = si.postings[e];
+        if (pl.empty() || pl.back() != docid) pl.push_back(docid);
+      }
+    } else {
+      auto& pl = si.postings[value];
+      if (pl.empty() || pl.back() != docid) pl.push_back(docid);
+    }
+    return;
+  }
+  if ((int)si.ok.size() <= docid) {
+    si.ok.resize((size_t)docid + 1, 0);
+    if (is_float_type(dt)) si.f64.resize((size_t)docid + 1, 0.0);
+    else si.i64.resize((size_t)docid + 1, 0);
+  }
+  int64_t iv = 0;
+  double fv = 0;
+  si.ok[docid] = decode_num(dt, value, &iv, &fv) ? 1 : 0;
+  if (is_float_type(dt)) si.f64[docid] = fv;
+  else si.i64[docid] = iv;
+}
+
+void Engine::scalar_index_rebuild(int fi) {
+  if (fi >= (int)sidx_.size()) sidx_.resize(fields_.size());
+  ScalarIndex& si = sidx_[fi];
+  si = ScalarIndex();
+  si.built = true;
+  for (int d = 0; d < (int)values_[fi].size(); d++) scalar_index_put(fi, d, values_[fi][d]);
+}
+
 int64_t Engine::eval_filters(const std::vector<SearchRequestPB::Filter>& filters, int op, std::vector<uint8_t>* bitmap) const {
   const int n = max_docid_;
-  bitmap->assign((size_t)(n >> 3) + 1, 0);
-  std::vector<uint8_t> cur((size_t)(n >> 3) + 1);
+  const size_t nbytes = (size_t)(n >> 3) + 1;
+  bitmap->assign(nbytes, 0);
+  std::vector<uint8_t> cur(nbytes);
   bool first = true;
+  auto set_bit = [&](int d) { cur[d >> 3] |= (uint8_t)(1u << (d & 7)); };
   for (const auto& fl : filters) {
     auto it = field_idx_.find(fl.field);
     if (it == field_idx_.end() || !fields_[it->second].indexed) return 0;
     const int fi = it->second, dt = fields_[fi].data_type;
-    const bool is_str = dt == DT_STRING || dt == DT_STRINGARRAY;
+    const bool is_str = is_string_type(dt);
     if (fl.lower.empty() && (is_str || fl.upper.empty())) continue;  // Filter() returns an untouched result
+    if (fi >= (int)sidx_.size() || !sidx_[fi].built) return 0;
+    const ScalarIndex& si = sidx_[fi];
     std::fill(cur.begin(), cur.end(), 0);
     const bool neg = fl.is_union == 2;
-    std::vector<std::string> items;
-    if (is_str) items = split001(fl.lower);
-    for (int d = 0; d < n; d++) {
-      const std::string& v = values_[fi][d];
-      bool hit;
-      if (is_str) {
-        bool in = false;
-        if (dt == DT_STRINGARRAY) {
-          for (const auto& e : split001(v))
-            if (std::find(items.begin(), items.end(), e) != items.end()) in = true;
-        } else {
-          in = std::find(items.begin(), items.end(), v) != items.end();
-        }
-        hit = neg ? !in : in;
-      } else if (fl.lower == fl.upper) {
-        const int c = cmp_typed(dt, v, fl.lower);
-        hit = c != -2 && (neg ? c != 0 : c == 0);
-      } else {
-        hit = true;
-        if (!fl.lower.empty()) {
-          const int c = cmp_typed(dt, v, fl.lower);
-          hit = c != -2 && (c > 0 || (c == 0 && fl.include_lower));
-        }
-        if (hit && !fl.upper.empty()) {
-          const int c = cmp_typed(dt, v, fl.upper);
-          hit = c != -2 && (c < 0 || (c == 0 && fl.include_upper));
+    if (is_str) {
+      // In / NotIn over the inverted map; postings may hold documents whose value has changed since: re-check
+      const std::vector<std::string> items = split001(fl.lower);
+      for (const auto& item : items) {
+        auto pit = si.postings.find(item);
+        if (pit == si.postings.end()) continue;
+        for (int d : pit->second) {
+          if (d >= n) continue;
+          const std::string& v = values_[fi][d];
+          bool in;
+          if (dt == DT_STRINGARRAY) {
+            in = false;
+            for (const auto& e : split001(v))
+              if (e == item) in = true;
+          } else {
+            in = v == item;
+          }
+          if (in) set_bit(d);
         }
       }
-      if (hit) cur[d >> 3] |= (uint8_t)(1u << (d & 7));
+      if (neg) {
+        for (size_t i = 0; i < nbytes; i++) cur[i] = (uint8_t)~cur[i];
+      }
+    } else {
+      int64_t lo_i = 0, hi_i = 0;
+      double lo_f = 0, hi_f = 0;
+      const bool has_lo = !fl.lower.empty(), has_hi = !fl.upper.empty();
+      const bool lo_ok = has_lo && decode_num(dt, fl.lower, &lo_i, &lo_f);
+      const bool hi_ok = has_hi && decode_num(dt, fl.upper, &hi_i, &hi_f);
+      const bool equal = fl.lower == fl.upper;
+      const int m = std::min<int>(n, (int)si.ok.size());
+      auto scan = [&](auto* col, auto lo, auto hi) {
+        for (int d = 0; d < m; d++) {
+          if (!si.ok[d]) continue;
+          const auto v = col[d];
+          bool hit;
+          if (equal) {
+            hit = lo_ok && (neg ? v != lo : v == lo);
+          } else {
+            hit = true;
+            if (has_lo) hit = lo_ok && (v > lo || (v == lo && fl.include_lower));
+            if (hit && has_hi) hit = hi_ok && (v < hi || (v == hi && fl.include_upper));
+          }
+          if (hit) set_bit(d);
+        }
+      };
+      if (is_float_type(dt)) scan(si.f64.data(), lo_f, hi_f);
+      else scan(si.i64.data(), lo_i, hi_i);
     }
+    if (n & 7) cur[nbytes - 1] &= (uint8_t)((1u << (n & 7)) - 1u);  // no bits at or above max_docid
+    else cur[nbytes - 1] = 0;
     if (first) {
       bitmap->swap(cur);
       cur.resize(bitmap->size());
@@ -912,8 +1016,14 @@ void Engine::put_doc_fields(int docid, const FieldSel& sel, PbWriter* item) {
 // first `limit` live documents that pass the scalar filters, as one SearchResult with score-less items
 Status Engine::Query(const QueryRequestPB& req, std::string* pb_out) {
   if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
-  std::unique_lock<std::shared_mutex> wl(mu_);
-  if (pending_n_ > 0 && flush_pending_locked()) return Status::Make(kIndexError, last_error());
+  {
+    // documents accepted but not yet uploaded must be visible to GetDoc-style reads: flush under the exclusive
+    // lock, then serve the query under the shared one (filters, field reads and the per-document device reads
+    // of put_doc_fields do not block ingest or other searches)
+    std::unique_lock<std::shared_mutex> wl(mu_);
+    if (pending_n_ > 0 && flush_pending_locked()) return Status::Make(kIndexError, last_error());
+  }
+  std::shared_lock<std::shared_mutex> rl(mu_);
   std::vector<int> docids;
   auto deleted = [&](int d) { return ((del_bitmap_[d >> 3] >> (d & 7)) & 1) != 0; };
   if (!req.document_ids.empty()) {
@@ -980,7 +1090,16 @@ Status Engine::SetFieldIndexed(const std::string& field, bool indexed) {
   auto it = field_idx_.find(field);
   if (it == field_idx_.end()) return Status::Make(kInvalidArgument, "field " + field + " not found");
   fields_[it->second].indexed = indexed;
+  if (indexed) {
+    scalar_index_rebuild(it->second);  // AddFieldIndex builds the index over the documents already stored
+  } else if (it->second < (int)sidx_.size()) {
+    sidx_[it->second] = ScalarIndex();
+  }
   return Status::OK();
+}
+
+int64_t Engine::now_ms() {
+  return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // Engine::BuildIndex / Engine::Indexing (search/engine.cc:951-988, 1091-1142)
@@ -1033,6 +1152,9 @@ void Engine::indexing_loop() {
   bool train_failed = index_->train() != 0;  // e.g. fewer vectors than training_threshold
   for (auto& e : extra_) train_failed = train_failed || e.index->train() != 0;
   if (train_failed) {
+    // e.g. fewer vectors than training_threshold: remember when, so AddOrUpdate does not spawn and join a new
+    // indexing thread for every document until the threshold is reached (BuildIndex retries after a back-off)
+    last_train_failure_ms_.store(now_ms());
     indexing_state_.store(0);
     idx_cv_.notify_all();
     return;
@@ -1219,6 +1341,8 @@ int Engine::Load() {
   if (maxd && !f.read(reinterpret_cast<char*>(rows.data()), (std::streamsize)(rows.size() * 4))) return -1;
   int32_t trained;
   if (!rdv(f, &trained)) return -1;
+  for (size_t fi = 0; fi < fields_.size(); fi++)
+    if (fields_[fi].indexed) scalar_index_rebuild((int)fi);
   keys_.resize(maxd);
   int idf = field_idx_["_id"];
   for (int d = 0; d < maxd; d++) {

@@ -151,6 +151,20 @@ class Engine {
   std::vector<FieldDef> fields_;
   std::unordered_map<std::string, int> field_idx_;
   std::vector<std::vector<std::string>> values_;  // [field][docid]
+  // Scalar indexes of the fields created with is_index (table/scalar_index_manager.cc: one index per field): numeric
+  // fields keep a typed column (a filter is one pass over int64 / double values, no string handling), string fields
+  // an inverted map term -> docids (postings are append-only: an updated document is re-verified against its current
+  // value at query time).  Built at AddOrUpdate / Load / AddFieldIndex, evaluated under the SHARED table lock.
+  struct ScalarIndex {
+    bool built = false;
+    std::vector<int64_t> i64;   // DT_INT / DT_LONG / DT_DATE / DT_BOOL
+    std::vector<double> f64;    // DT_FLOAT / DT_DOUBLE
+    std::vector<uint8_t> ok;    // value present with the field type's width
+    std::unordered_map<std::string, std::vector<int>> postings;  // DT_STRING / DT_STRINGARRAY
+  };
+  std::vector<ScalarIndex> sidx_;  // [field]
+  void scalar_index_put(int fi, int docid, const std::string& value);
+  void scalar_index_rebuild(int fi);
   std::unordered_map<std::string, int> key2docid_;
   std::vector<std::string> keys_;  // docid -> _id
 
@@ -178,6 +192,9 @@ class Engine {
   bool enable_id_cache_ = false, enable_realtime_ = false;
   int slow_search_time_ = 0;
 
+  static int64_t now_ms();
+  static constexpr int64_t kTrainRetryMs = 1000;
+  std::atomic<int64_t> last_train_failure_ms_{-(int64_t)1 << 40};
   std::atomic<int> index_status_{0};    // IndexStatus: 0 UNINDEXED, 1 INDEXING, 2 INDEXED
   std::atomic<int> indexing_state_{0};  // IndexingState: 0 IDLE, 1 STARTING, 2 RUNNING, 3 STOPPING
   std::thread indexing_thread_;

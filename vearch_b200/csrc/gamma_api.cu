@@ -50,7 +50,7 @@ void* Init(const char* config_str, int len) {
   if (const char* env = getenv("GAMMA_B200_DEVICE")) device = atoi(env);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return nullptr;  // no CPU path
-  if (device < 0 || device >= ndev) device = device % ndev;
+  if (device < 0 || device >= ndev) device = ((device % ndev) + ndev) % ndev;
   return static_cast<void*>(new Engine(path, space, device));
 }
 

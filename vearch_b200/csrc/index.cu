@@ -1,4 +1,6 @@
 // Host orchestration of the hot path (see index.h).  Reference call sites are cited inline.
+#include <cuda.h>
+
 #include "index.h"
 
 #include <float.h>
@@ -74,25 +76,141 @@ void* Scratch::alloc(size_t bytes) {
   if (!var) return -1
 
 // ------------------------------------------------------------------------------------------
+// Segments are VIRTUAL address ranges of seg_rows rows; physical HBM is mapped into them in chunks as rows
+// arrive (CUDA virtual memory management: cuMemAddressReserve / cuMemCreate / cuMemMap, reached through
+// cudaGetDriverEntryPoint so the library still links only the static runtime).  A 100-document partition
+// therefore costs one 2 MiB granule, not a 1M-row segment (3 GiB at d = 768), while row addresses stay
+// stable and segment-contiguous for the kernels (MemoryRawVector grows incrementally as well,
+// vector/memory_raw_vector.cc:152-240).  Without VMM support a segment is one cudaMalloc as before.
+namespace {
+struct VmmApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+const VmmApi& vmm_api() {
+  static const VmmApi api = [] {
+    VmmApi a;
+    const char* off = getenv("GB_VMM");
+    if (off && atoi(off) == 0) return a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+    };
+    a.ok = get("cuMemAddressReserve", (void**)&a.reserve) && get("cuMemAddressFree", (void**)&a.addr_free) &&
+           get("cuMemCreate", (void**)&a.create) && get("cuMemRelease", (void**)&a.release) && get("cuMemMap", (void**)&a.map) &&
+           get("cuMemUnmap", (void**)&a.unmap) && get("cuMemSetAccess", (void**)&a.set_access) &&
+           get("cuMemGetAllocationGranularity", (void**)&a.granularity);
+    cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+}  // namespace
+
 RawStore::RawStore(int d, int seg_shift) : d_(d), dpad_((int)round_up(d, 4)), seg_shift_(seg_shift) {
   cudaMalloc(&d_segs_, sizeof(float*) * kMaxSegs);
+  cudaGetDevice(&device_);
 }
 RawStore::~RawStore() {
-  for (float* p : segs_) cudaFree(p);
+  const VmmApi& api = vmm_api();
+  for (Seg& sg : segs_) {
+    if (!sg.vmm) {
+      cudaFree(sg.base);
+      continue;
+    }
+    size_t off = 0;
+    for (auto& c : sg.chunks) {
+      api.unmap((CUdeviceptr)sg.base + off, c.second);
+      api.release(c.first);
+      off += c.second;
+    }
+    api.addr_free((CUdeviceptr)sg.base, sg.va_bytes);
+  }
   cudaFree(d_segs_);
 }
-int RawStore::ensure(int64_t n_total) {
-  while ((int64_t)segs_.size() * seg_rows() < n_total) {
-    if ((int)segs_.size() >= kMaxSegs) {
-      set_last_error("raw store: too many segments");
+int RawStore::new_segment() {
+  if ((int)segs_.size() >= kMaxSegs) {
+    set_last_error("raw store: too many segments");
+    return -1;
+  }
+  Seg sg;
+  const size_t bytes = (size_t)seg_rows() * dpad_ * 4;
+  const VmmApi& api = vmm_api();
+  if (api.ok) {
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device_;
+    size_t gran = 0;
+    if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran > 0) {
+      sg.gran = gran;
+      sg.va_bytes = (size_t)round_up((int64_t)bytes, (int64_t)gran);
+      CUdeviceptr p = 0;
+      if (api.reserve(&p, sg.va_bytes, 0, 0, 0) == CUDA_SUCCESS) {
+        sg.base = reinterpret_cast<float*>(p);
+        sg.vmm = true;
+      }
+    }
+  }
+  if (!sg.vmm) {  // no VMM: the whole segment at once
+    GB_CUDA(cudaMalloc(&sg.base, bytes));
+    GB_CUDA(cudaMemset(sg.base, 0, bytes));
+    sg.mapped = bytes;
+    phys_bytes_ += (int64_t)bytes;
+  }
+  segs_.push_back(sg);
+  GB_CUDA(cudaMemcpy(d_segs_ + segs_.size() - 1, &sg.base, sizeof(float*), cudaMemcpyHostToDevice));
+  return 0;
+}
+// physical memory behind the first `rows` rows of segment si
+int RawStore::map_rows(int si, int64_t rows) {
+  Seg& sg = segs_[si];
+  const size_t need = (size_t)rows * dpad_ * 4;
+  if (need <= sg.mapped) return 0;
+  const VmmApi& api = vmm_api();
+  while (sg.mapped < need) {
+    // geometric steps (a quarter of what is mapped, at least one granule, at most 256 MiB), never past the segment
+    size_t step = std::max(sg.gran, std::min<size_t>(sg.mapped / 4, (size_t)256 << 20));
+    step = (size_t)round_up((int64_t)std::max(step, std::min(need - sg.mapped, (size_t)256 << 20)), (int64_t)sg.gran);
+    step = std::min(step, sg.va_bytes - sg.mapped);
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device_;
+    CUmemGenericAllocationHandle hnd;
+    if (api.create(&hnd, step, &prop, 0) != CUDA_SUCCESS) {
+      set_last_error("raw store: out of device memory (cuMemCreate)");
       return -1;
     }
-    float* p = nullptr;
-    size_t bytes = (size_t)seg_rows() * dpad_ * 4;
-    GB_CUDA(cudaMalloc(&p, bytes));
-    GB_CUDA(cudaMemset(p, 0, bytes));
-    segs_.push_back(p);
-    GB_CUDA(cudaMemcpy(d_segs_ + segs_.size() - 1, &p, sizeof(float*), cudaMemcpyHostToDevice));
+    const CUdeviceptr at = (CUdeviceptr)sg.base + sg.mapped;
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (api.map(at, step, 0, hnd, 0) != CUDA_SUCCESS || api.set_access(at, step, &acc, 1) != CUDA_SUCCESS) {
+      api.release(hnd);
+      set_last_error("raw store: cuMemMap failed");
+      return -1;
+    }
+    GB_CUDA(cudaMemset(reinterpret_cast<void*>(at), 0, step));  // pad columns must read as zero
+    sg.chunks.emplace_back(hnd, step);
+    sg.mapped += step;
+    phys_bytes_ += (int64_t)step;
+  }
+  return 0;
+}
+int RawStore::ensure(int64_t n_total) {
+  while ((int64_t)segs_.size() * seg_rows() < n_total)
+    if (new_segment()) return -1;
+  for (int si = (int)(n_ >> seg_shift_); si < (int)segs_.size(); si++) {
+    const int64_t rows = std::min<int64_t>(seg_rows(), n_total - (int64_t)si * seg_rows());
+    if (rows > 0 && map_rows(si, rows)) return -1;
   }
   return 0;
 }
@@ -103,7 +221,7 @@ int RawStore::append_host(const float* x, int64_t n, cudaStream_t st) {
     int64_t vid = n_ + done;
     int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
     int64_t cnt = std::min(n - done, seg_rows() - off);
-    GB_CUDA(cudaMemcpy2DAsync(segs_[si] + off * dpad_, (size_t)dpad_ * 4, x + done * d_, (size_t)d_ * 4, (size_t)d_ * 4,
+    GB_CUDA(cudaMemcpy2DAsync(segs_[si].base + off * dpad_, (size_t)dpad_ * 4, x + done * d_, (size_t)d_ * 4, (size_t)d_ * 4,
                               (size_t)cnt, cudaMemcpyHostToDevice, st));
     done += cnt;
   }
@@ -118,7 +236,7 @@ int RawStore::append_device(const float* x, int64_t ld, int64_t n, cudaStream_t 
     int64_t vid = n_ + done;
     int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
     int64_t cnt = std::min(n - done, seg_rows() - off);
-    GB_CUDA(cudaMemcpy2DAsync(segs_[si] + off * dpad_, (size_t)dpad_ * 4, x + done * ld, (size_t)ld * 4,
+    GB_CUDA(cudaMemcpy2DAsync(segs_[si].base + off * dpad_, (size_t)dpad_ * 4, x + done * ld, (size_t)ld * 4,
                               (size_t)d_ * 4, (size_t)cnt, cudaMemcpyDeviceToDevice, st));
     done += cnt;
   }
@@ -129,14 +247,14 @@ int RawStore::append_device(const float* x, int64_t ld, int64_t n, cudaStream_t 
 int RawStore::update_host(int64_t vid, const float* x, cudaStream_t st) {
   if (vid < 0 || vid >= n_) return -1;
   int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
-  GB_CUDA(cudaMemcpyAsync(segs_[si] + off * dpad_, x, (size_t)d_ * 4, cudaMemcpyHostToDevice, st));
+  GB_CUDA(cudaMemcpyAsync(segs_[si].base + off * dpad_, x, (size_t)d_ * 4, cudaMemcpyHostToDevice, st));
   GB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 int RawStore::get_host(int64_t vid, float* out) const {
   if (vid < 0 || vid >= n_) return -1;
   int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
-  GB_CUDA(cudaMemcpy(out, segs_[si] + off * dpad_, (size_t)d_ * 4, cudaMemcpyDeviceToHost));
+  GB_CUDA(cudaMemcpy(out, segs_[si].base + off * dpad_, (size_t)d_ * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 int RawStore::get_rows_host(int64_t start, int64_t n, float* out) const {
@@ -146,21 +264,21 @@ int RawStore::get_rows_host(int64_t start, int64_t n, float* out) const {
     int64_t vid = start + done;
     int64_t si = vid >> seg_shift_, off = vid & (seg_rows() - 1);
     int64_t cnt = std::min(n - done, seg_rows() - off);
-    GB_CUDA(cudaMemcpy2D(out + done * d_, (size_t)d_ * 4, segs_[si] + off * dpad_, (size_t)dpad_ * 4, (size_t)d_ * 4,
+    GB_CUDA(cudaMemcpy2D(out + done * d_, (size_t)d_ * 4, segs_[si].base + off * dpad_, (size_t)dpad_ * 4, (size_t)d_ * 4,
                          (size_t)cnt, cudaMemcpyDeviceToHost));
     done += cnt;
   }
   return 0;
 }
 const float* RawStore::contiguous(int64_t n, Scratch& s) {
-  if (n <= seg_rows()) return segs_.empty() ? nullptr : segs_[0];
+  if (n <= seg_rows()) return segs_.empty() ? nullptr : segs_[0].base;
   float* buf = s.alloc_n<float>((size_t)n * dpad_);
   if (!buf) return nullptr;
   int64_t done = 0;
   while (done < n) {
     int64_t si = done >> seg_shift_;
     int64_t cnt = std::min(n - done, seg_rows());
-    if (cudaMemcpyAsync(buf + done * dpad_, segs_[si], (size_t)cnt * dpad_ * 4, cudaMemcpyDeviceToDevice,
+    if (cudaMemcpyAsync(buf + done * dpad_, segs_[si].base, (size_t)cnt * dpad_ * 4, cudaMemcpyDeviceToDevice,
                         s.stream()) != cudaSuccess)
       return nullptr;
     done += cnt;
@@ -375,6 +493,7 @@ void Index::quiesce() {
 }
 
 Index::~Index() {
+  drain_searches();
   {
     std::lock_guard<std::mutex> g(live_indexes().mu);
     auto& a = live_indexes().all;
@@ -430,6 +549,32 @@ void Index::big_release(void* p, cudaStream_t st) {
       b.busy = false;
     }
 }
+void Index::note_search_enqueued(cudaStream_t st) {
+  cudaEvent_t e;
+  if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  std::lock_guard<std::mutex> g(inflight_mu_);
+  if (inflight_.size() >= 64) {  // forget the ones that have completed
+    size_t w = 0;
+    for (size_t i = 0; i < inflight_.size(); i++) {
+      if (cudaEventQuery(inflight_[i]) == cudaSuccess)
+        cudaEventDestroy(inflight_[i]);
+      else
+        inflight_[w++] = inflight_[i];
+    }
+    inflight_.resize(w);
+    cudaGetLastError();  // cudaErrorNotReady from the queries is not an error
+  }
+  inflight_.push_back(e);
+}
+void Index::drain_searches() {
+  std::lock_guard<std::mutex> g(inflight_mu_);
+  for (cudaEvent_t e : inflight_) {
+    cudaEventSynchronize(e);
+    cudaEventDestroy(e);
+  }
+  inflight_.clear();
+}
 void Index::scan_timer_begin(cudaStream_t st) {
   if (!time_scan_) return;
   cudaEvent_t e0, e1;
@@ -443,6 +588,36 @@ void Index::scan_timer_end(cudaStream_t st) {
   if (!time_scan_) return;
   std::lock_guard<std::mutex> g(ev_mu_);
   if (!scan_events_.empty()) cudaEventRecord(scan_events_.back().second, st);
+}
+void Index::stage_begin(const char* name, cudaStream_t st) {
+  if (!time_scan_) return;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  std::lock_guard<std::mutex> g(ev_mu_);
+  stage_events_.push_back({name, e0, e1});
+}
+void Index::stage_end(cudaStream_t st) {
+  if (!time_scan_) return;
+  std::lock_guard<std::mutex> g(ev_mu_);
+  if (!stage_events_.empty()) cudaEventRecord(stage_events_.back().e1, st);
+}
+std::vector<std::pair<std::string, float>> Index::stage_times() {
+  std::lock_guard<std::mutex> g(ev_mu_);
+  std::vector<std::pair<std::string, float>> out;
+  for (auto& ev : stage_events_) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.e1) != cudaSuccess || cudaEventElapsedTime(&ms, ev.e0, ev.e1) != cudaSuccess) ms = 0.f;
+    cudaEventDestroy(ev.e0);
+    cudaEventDestroy(ev.e1);
+    bool found = false;
+    for (auto& o : out)
+      if (o.first == ev.name) o.second += ms, found = true;
+    if (!found) out.emplace_back(ev.name, ms);
+  }
+  stage_events_.clear();
+  return out;
 }
 float Index::last_scan_ms() {
   std::lock_guard<std::mutex> g(ev_mu_);
@@ -494,7 +669,7 @@ int Index::upload_bitmaps(const SearchContext& ctx, FilterArgs* f, Scratch& s) {
 }
 
 int Index::search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
-                         int64_t* out_ids_dev, cudaStream_t st) {
+                         int64_t* out_ids_dev, cudaStream_t st, unsigned long long* out_keys_dev) {
   if (nq <= 0) return 0;
   if (k <= 0 || k > 4096) {
     set_last_error("topK must be in [1, 4096]");
@@ -551,8 +726,13 @@ int Index::search_device(const SearchContext& ctx, int nq, const float* x_dev, i
       }
     }
   }
-  if (rc) return rc;
-  GB_CUDA(launch_decode_keys(keys, k, nq, k, metric, out_dis_dev, out_ids_dev, 0, st));
+  if (rc) {
+    note_search_enqueued(st);
+    return rc;
+  }
+  if (out_keys_dev) GB_CUDA(cudaMemcpyAsync(out_keys_dev, keys, (size_t)nq * k * 8, cudaMemcpyDeviceToDevice, st));
+  if (out_dis_dev && out_ids_dev) GB_CUDA(launch_decode_keys(keys, k, nq, k, metric, out_dis_dev, out_ids_dev, 0, st));
+  note_search_enqueued(st);
   return 0;
 }
 
@@ -897,6 +1077,7 @@ int IVFFlatIndex::set_centroids(const float* host, int nlist) {
   }
   cudaSetDevice(device_);
   std::unique_lock<std::shared_mutex> lk(mu_);
+  drain_searches();
   GB_CUDA(cudaMemset(d_centroids_, 0, (size_t)nlist_ * dpad_ * 4));
   GB_CUDA(cudaMemcpy2D(d_centroids_, (size_t)dpad_ * 4, host, (size_t)d_ * 4, (size_t)d_ * 4, nlist_,
                        cudaMemcpyHostToDevice));
@@ -922,6 +1103,7 @@ int IVFFlatIndex::train() {
     return -1;
   }
   std::unique_lock<std::shared_mutex> lk(mu_);
+  drain_searches();
   cudaStream_t st = build_stream_;
   Scratch s(st);
   const float* xt = store_->contiguous(num, s);
@@ -990,10 +1172,12 @@ int IVFFlatIndex::index_batch(const float* x, int64_t n, int64_t vid0, const uin
   GB_CUDA(cudaMemcpyAsync(d_list, h_list.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   GB_CUDA(cudaMemcpyAsync(d_pos, h_pos.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
   std::unique_lock<std::shared_mutex> lk(mu_);
+  drain_searches();  // kernels of earlier searches read lengths and base pointers at run time
   if (lists_->reserve(add, st)) return -1;
   if (append_batch(x, n, vid0, d_list, d_pos, d_assign, s)) return -1;
-  if (lists_->commit(add, st)) return -1;
+  // data (lists AND their tensor-core mirror) first, the new lengths last (realtime_mem_data.cc:292-293)
   if (type_ == "IVFFLAT" && mirror_append(x, n, d_list, d_pos, add, st)) return -1;
+  if (lists_->commit(add, st)) return -1;
   GB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
@@ -1003,11 +1187,16 @@ int IVFFlatIndex::add_pending(const uint8_t* del_bitmap) {
   if (!trained_) return 0;
   cudaSetDevice(device_);
   const int64_t BATCH = 1 << 20;
-  while (indexed_count_ < store_->size()) {
-    int64_t vid0 = indexed_count_;
-    int64_t si = vid0 >> store_->seg_shift(), off = vid0 & (store_->seg_rows() - 1);
-    int64_t n = std::min<int64_t>(std::min(store_->size() - vid0, store_->seg_rows() - off), BATCH);
-    const float* x = store_->seg((int)si) + off * dpad_;
+  for (;;) {
+    int64_t vid0 = indexed_count_, n = 0;
+    const float* x = nullptr;
+    {  // add_vectors (exclusive mu_) may append segments while we look: the segment table is read under the shared lock
+      std::shared_lock<std::shared_mutex> lk(mu_);
+      if (vid0 >= store_->size()) break;
+      int64_t si = vid0 >> store_->seg_shift(), off = vid0 & (store_->seg_rows() - 1);
+      n = std::min<int64_t>(std::min(store_->size() - vid0, store_->seg_rows() - off), BATCH);
+      x = store_->seg((int)si) + off * dpad_;
+    }
     if (index_batch(x, n, vid0, del_bitmap)) return -1;
     indexed_count_ += n;
   }
@@ -1077,6 +1266,7 @@ int IVFFlatIndex::coarse_dev(int nq, const float* xq, int nprobe, int metric, in
   int64_t ldo = round_up(nlist_, 4);
   GB_ALLOC(scores, float, (size_t)nq * ldo, s);
   GB_ALLOC(keys, unsigned long long, (size_t)nq * nprobe, s);
+  StageScope stage(this, "coarse_quantizer", st);
   if (tc_enabled() && nlist_ >= 64 && nq >= 32) {
     GB_CUDA(launch_dist_matrix_tc(xq, dpad_, nq, d_centroids_, dpad_, nlist_, dpad_, metric, scores, ldo, st));
   } else {
@@ -1115,12 +1305,13 @@ static bool tma_enabled() {  // GB_TC_MIRROR=0: never build the pre-tiled mirror
 int IVFFlatIndex::mirror_append(const float* x, int64_t n, const int32_t* d_list, const int32_t* d_pos,
                                 const std::vector<int>& add, cudaStream_t st) {
   if (!mirror_.base || mirror_.disabled || mirror_.lens.size() != (size_t)nlist_) return 0;
-  const std::vector<int>& lens = lists_->lens();  // already includes `add`
+  std::vector<int> lens = lists_->lens();  // lengths BEFORE this batch is committed
   for (int l = 0; l < nlist_; l++) {
-    if (mirror_.lens[l] + add[l] != lens[l] || lens[l] > (int64_t)mirror_.list_tiles[l] * 128) {
+    if (mirror_.lens[l] != lens[l] || (int64_t)lens[l] + add[l] > (int64_t)mirror_.list_tiles[l] * 128) {
       mirror_.lens.clear();  // stale: outgrown (or out of step); rebuilt by the next list-major search
       return 0;
     }
+    lens[l] += add[l];
   }
   GB_CUDA(launch_tc_mirror_append(x, dpad_, n, dpad_, (int)round_up(dpad_, 16), d_list, d_pos, mirror_.d_tile0, mirror_.base,
                                   mirror_.norms, st));
@@ -1456,6 +1647,7 @@ int IVFPQIndex::set_opq(const float* host_A) {
   }
   cudaSetDevice(device_);
   std::unique_lock<std::shared_mutex> lk(mu_);
+  drain_searches();
   GB_CUDA(cudaMemset(d_opq_, 0, (size_t)d_ * dpad_ * 4));
   GB_CUDA(cudaMemcpy2D(d_opq_, (size_t)dpad_ * 4, host_A, (size_t)d_ * 4, (size_t)d_ * 4, d_, cudaMemcpyHostToDevice));
   opq_trained_ = true;
@@ -1641,6 +1833,7 @@ int IVFPQIndex::rebuild_table(cudaStream_t st) {
 int IVFPQIndex::set_pq_centroids(const float* host) {
   cudaSetDevice(device_);
   std::unique_lock<std::shared_mutex> lk(mu_);
+  drain_searches();
   GB_CUDA(cudaMemcpy(d_pq_, host, (size_t)M_ * 256 * dsub_ * 4, cudaMemcpyHostToDevice));
   if (rebuild_table(build_stream_)) return -1;
   GB_CUDA(cudaStreamSynchronize(build_stream_));
@@ -1760,11 +1953,13 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   if (const char* e = getenv("GB_PQTC_PA")) pa = std::max(1, std::min(nprobe - 1, atoi(e)));
   const int cap = std::max(1024, std::min(8192, next_pow2(4 * kk)));
   const int nsm = sm_count(device_);
+  snprintf(last_scan_info_, sizeof(last_scan_info_), "{\"phase_a_probes\": %d, \"candidate_cap\": %d, \"kprime\": %d}", pa, cap, kk);
 
   // ---- phase A: exact keys of probes [0, pa) ----
   const int pgA = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)pa * nq / ((int64_t)nsm * 32)));
   const int ngA = (pa + pgA - 1) / pgA;
   GB_ALLOC(partA, unsigned long long, (size_t)nq * ngA * kk, s);
+  stage_begin("pq_phaseA_exact_scan", st);
   GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, pa, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe));
   unsigned long long* keysA = partA;
   if (ngA > 1) {
@@ -1772,6 +1967,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
     if (!keysA) return -1;
     GB_CUDA(launch_select_keys(partA, (int64_t)ngA * kk, nq, ngA * kk, kk, keysA, kk, st));
   }
+  stage_end(st);
 
   // ---- phase B: group the remaining pairs by list, stage the operand tiles, filter ----
   const int nseg = (int)std::min<int64_t>(64, std::max<int64_t>(1, (lists_->max_len() + kLmkSegRows - 1) / kLmkSegRows));
@@ -1799,6 +1995,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   unsigned char* a_scratch = big;
   void* meta = big + a_bytes;
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(big + a_bytes + meta_bytes);
+  stage_begin("pq_group_and_stage_pairs", st);
   GB_CUDA(cudaMemsetAsync(d_cand_cnt, 0, sizeof(int) * nq, st));
   GB_CUDA(launch_pqtc_mask_probes(probe_ids, npairs, nprobe, pa, d_masked, st));
   GB_CUDA(launch_lmk_group(d_masked, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
@@ -1806,8 +2003,14 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   GB_CUDA(launch_pq_stage_pairs(xq, dpad_, d_, d_centroids_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe,
                                 coarse_dis, keysA, kk, kk, d_cbnrm_ + (size_t)M_ * 256, f, metric, pqtc_eps_scale(), a_scratch,
                                 meta, d_cand_cnt, cap, st));
+  stage_end(st);
+  scan_timer_begin(st);  // the dominant kernel: the roofline in bench.py is this launch alone
+  stage_begin("pqtc_scan_kernel", st);
   GB_CUDA(launch_pqtc_scan(a_scratch, meta, d_cb16_, d_cbnrm_, d_items, (int)max_items, d_totals, dir, M_, dsub_, f, metric,
                            d_cand_cnt, cand, cap, nsm, st));
+  stage_end(st);
+  scan_timer_end(st);
+  stage_begin("pq_rescore_and_fallback", st);
 
   // ---- phase C: candidates -> reference arithmetic, merged with phase A's keys ----
   GB_CUDA(launch_pq_rescore(ip, nq, probe_ids, coarse_dis, nprobe, dir, M_, d_table_, d_cand_cnt, cand, cap, keysA, kk, kk,
@@ -1818,6 +2021,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, 32, dir, M_, d_table_, kk, metric, f, partF, st, nprobe,
                             d_cand_cnt, cap));
   GB_CUDA(launch_pq_fallback_merge(d_cand_cnt, cap, nq, partF, ngF, kk, adc_out, st));
+  stage_end(st);
   if (const char* dump = getenv("GB_PQTC_DUMP")) {  // debugging aid: candidate lists + phase A keys to a file
     std::vector<int> h(nq);
     std::vector<unsigned long long> hc((size_t)nq * cap), hk((size_t)nq * kk);
@@ -1851,8 +2055,10 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
       if (v > cap) over++;
       else tot += v, mx = std::max<long long>(mx, v);
     }
-    fprintf(stderr, "[pqtc] nq=%d k'=%d pa=%d cap=%d: candidates mean %.1f max %lld, overflowed queries %lld\n", nq, kk, pa,
-            cap, nq > over ? (double)tot / (nq - over) : 0.0, mx, over);
+    unsigned long long dc[4];
+    pqtc_debug_counters(dc, true);
+    fprintf(stderr, "[pqtc] nq=%d k'=%d pa=%d cap=%d: candidates mean %.1f max %lld, overflowed queries %lld, dbg counters %llu %llu\n",
+            nq, kk, pa, cap, nq > over ? (double)tot / (nq - over) : 0.0, mx, over, dc[0], dc[1]);
   }
   return 0;
 }
@@ -1875,26 +2081,31 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
     return -1;
   }
   GB_ALLOC(ip, float, (size_t)nq * M_ * 256, s);
-  GB_CUDA(launch_pq_ip_table(xq, dpad_, nq, d_pq_, M_, dsub_, ip, st));
+  {
+    StageScope stage(this, "pq_ip_table", st);
+    GB_CUDA(launch_pq_ip_table(xq, dpad_, nq, d_pq_, M_, dsub_, ip, st));
+  }
   unsigned long long* adc = out_keys;
   if (rerank) {
     adc = s.alloc_n<unsigned long long>((size_t)nq * kk);
     if (!adc) return -1;
   }
-  scan_timer_begin(st);
   int lm = scan_listmajor_pq(f, metric, nq, xq, kk, ip, probe_ids, coarse_dis, nprobe, adc, s);
   if (lm < 0) return -1;
   if (lm == 0) {
     last_scan_kernel_ = "pqtc_scan_kernel";
-    scan_timer_end(st);
   } else {
+    snprintf(last_scan_info_, sizeof(last_scan_info_), "{}");
     const int nsm = sm_count(device_);
     int pg = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)nprobe * nq / ((int64_t)nsm * 32)));
     int ngroups = (nprobe + pg - 1) / pg;
     GB_ALLOC(partial, unsigned long long, (size_t)nq * ngroups * kk, s);
     last_scan_kernel_ = "ivfpq_scan_kernel";
+    scan_timer_begin(st);
+    stage_begin("ivfpq_scan_kernel", st);
     GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, nprobe, pg, lists_->directory(), M_, d_table_, kk, metric, f,
                               partial, st));
+    stage_end(st);
     scan_timer_end(st);
     if (ngroups > 1) {
       GB_CUDA(launch_select_keys(partial, (int64_t)ngroups * kk, nq, ngroups * kk, kk, adc, kk, st));
@@ -1904,6 +2115,7 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
   }
   if (rerank) {
     // "for opq, rerank need raw vector" (gamma_index_ivfpq.cc:735): original queries against the raw store
+    StageScope stage(this, "rerank_kernel", st);
     GB_CUDA(launch_rerank(adc, kk, nq, raw_queries_for(xq), dpad_, dpad_, store_->d_segs(), store_->seg_shift(), dpad_, k,
                           metric, f, out_keys, st));
   }
@@ -1963,6 +2175,7 @@ Index* create_index(const std::string& type, int d, const ModelParams& mp, int d
 namespace {
 // Router merge (mergeSortedArrays, client.go:1530-1589) on device: per query, k-way merge keyed by
 // (score, later partition first).  Input scores are already sorted per partition.
+template <bool FROM_KEYS>  // FROM_KEYS: `ids` holds the partitions' result keys (score bits << 32 | local id)
 __global__ void merge_partitions_kernel(const float* __restrict__ dis, const int64_t* __restrict__ ids, int nparts,
                                         int nq, int k, int metric, float* __restrict__ out_dis,
                                         int64_t* __restrict__ out_ids) {
@@ -1976,13 +2189,21 @@ __global__ void merge_partitions_kernel(const float* __restrict__ dis, const int
     unsigned long long key = kKeySentinel, pl = 0;
     if (i < total) {
       int p = i / k, j = i - p * k;
-      int64_t id = ids[((int64_t)p * nq + q) * k + j];
-      if (id >= 0) {
-        float s = dis[((int64_t)p * nq + q) * k + j];
-        // low word: later partition first, then rank inside the partition
-        uint32_t lo = ((uint32_t)(nparts - 1 - p) << 16) | (uint32_t)j;
-        key = make_key(score2ord(s, metric), lo);
-        pl = ((unsigned long long)p << 32) | (uint32_t)id;
+      // low word: later partition first, then rank inside the partition
+      const uint32_t lo = ((uint32_t)(nparts - 1 - p) << 16) | (uint32_t)j;
+      if (FROM_KEYS) {
+        const unsigned long long pk = (unsigned long long)ids[((int64_t)p * nq + q) * k + j];
+        if (pk != kKeySentinel) {
+          key = make_key((uint32_t)(pk >> 32), lo);
+          pl = ((unsigned long long)p << 32) | (uint32_t)pk;
+        }
+      } else {
+        int64_t id = ids[((int64_t)p * nq + q) * k + j];
+        if (id >= 0) {
+          float s = dis[((int64_t)p * nq + q) * k + j];
+          key = make_key(score2ord(s, metric), lo);
+          pl = ((unsigned long long)p << 32) | (uint32_t)id;
+        }
       }
     }
     mk[i] = key;
@@ -2020,6 +2241,24 @@ __global__ void merge_partitions_kernel(const float* __restrict__ dis, const int
 }
 }  // namespace
 
+int merge_partition_keys_device(const unsigned long long* keys, int nparts, int nq, int k, int metric, float* out_dis,
+                                int64_t* out_ids, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  int NP = next_pow2(nparts * k);
+  if (nparts > 65535 || k > 65535 || NP > 8192) {
+    set_last_error("merge_partitions: nparts*k too large");
+    return -1;
+  }
+  size_t smem = (size_t)NP * 16;
+  if (smem > 48 * 1024)
+    GB_CUDA(cudaFuncSetAttribute(merge_partitions_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_partitions_kernel<true><<<nq, 256, smem, st>>>(nullptr, reinterpret_cast<const int64_t*>(keys), nparts, nq, k, metric,
+                                                       out_dis, out_ids);
+  note_launch();
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, int nq, int k, int metric, float* out_dis,
                             int64_t* out_ids, cudaStream_t st) {
   if (nq <= 0) return 0;
@@ -2030,8 +2269,8 @@ int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, in
   }
   size_t smem = (size_t)NP * 16;
   if (smem > 48 * 1024)
-    GB_CUDA(cudaFuncSetAttribute(merge_partitions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_partitions_kernel<<<nq, 256, smem, st>>>(dis, ids, nparts, nq, k, metric, out_dis, out_ids);
+    GB_CUDA(cudaFuncSetAttribute(merge_partitions_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_partitions_kernel<false><<<nq, 256, smem, st>>>(dis, ids, nparts, nq, k, metric, out_dis, out_ids);
   note_launch();
   GB_CUDA(cudaGetLastError());
   return 0;

@@ -62,7 +62,7 @@ class RawStore {
   int seg_shift() const { return seg_shift_; }
   int64_t seg_rows() const { return (int64_t)1 << seg_shift_; }
   int nsegs() const { return (int)segs_.size(); }
-  const float* seg(int i) const { return segs_[i]; }
+  const float* seg(int i) const { return segs_[i].base; }
   const float* const* d_segs() const { return d_segs_; }
   // rows: n x d floats (stride d) on host, or n x dpad (stride ld) on device
   int append_host(const float* x, int64_t n, cudaStream_t st);
@@ -72,13 +72,21 @@ class RawStore {
   int get_rows_host(int64_t start, int64_t n, float* out) const;  // n x d, stride d
   // contiguous copy of rows [0, n) (training slab, GetVectorHeader): returns device ptr, owned by `s`
   const float* contiguous(int64_t n, Scratch& s);
-  int64_t mem_bytes() const { return (int64_t)segs_.size() * seg_rows() * dpad_ * 4; }
+  int64_t mem_bytes() const { return phys_bytes_; }  // physical HBM behind the store
 
  private:
   int ensure(int64_t n_total);
-  int d_, dpad_, seg_shift_;
-  int64_t n_ = 0;
-  std::vector<float*> segs_;
+  int new_segment();
+  int map_rows(int si, int64_t rows);
+  struct Seg {
+    float* base = nullptr;
+    bool vmm = false;
+    size_t va_bytes = 0, mapped = 0, gran = 0;
+    std::vector<std::pair<unsigned long long, size_t>> chunks;  // (CUmemGenericAllocationHandle, bytes), in address order
+  };
+  int d_, dpad_, seg_shift_, device_ = 0;
+  int64_t n_ = 0, phys_bytes_ = 0;
+  std::vector<Seg> segs_;
   float** d_segs_ = nullptr;  // device array [kMaxSegs]
   static constexpr int kMaxSegs = 65536;
 };
@@ -190,8 +198,10 @@ class Index {
   int search(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
   // one H2D -> kernels -> D2H round trip on the calling thread's stream
   int search_direct(const SearchContext& ctx, int nq, const float* x, int k, float* out_dis, int64_t* out_ids);
+  // out_keys_dev (optional): the nq x k result keys, (order-preserving score bits << 32) | vid, best first,
+  // sentinel padded -- what the multi-GPU merge exchanges (one all-gather instead of scores + ids)
   int search_device(const SearchContext& ctx, int nq, const float* x_dev, int64_t ldx, int k, float* out_dis_dev,
-                    int64_t* out_ids_dev, cudaStream_t st);
+                    int64_t* out_ids_dev, cudaStream_t st, unsigned long long* out_keys_dev = nullptr);
   // forget the trained state and the index structures, keep the raw vectors (Engine::RebuildIndex ->
   // VectorManager::ReCreateVectorIndexes, search/engine.cc:991-1089): the next train() starts over
   virtual int reset_index() { return 0; }
@@ -202,8 +212,10 @@ class Index {
   // device time spent in the dominant scan kernel(s) since the last call (ms), for the bench
   // roofline: CUDA events recorded on the launching stream around the scan launches, read here.
   float last_scan_ms();
+  std::vector<std::pair<std::string, float>> stage_times();
   void set_time_scan(bool on) { time_scan_ = on; }
   const char* last_scan_kernel() const { return last_scan_kernel_; }
+  const char* last_scan_info() const { return last_scan_info_; }  // JSON details of the last scan path (bench)
 
  protected:
   // GammaFLATIndex::Search (gamma_index_flat.cc:130-370) over rows [0, nrows)
@@ -220,6 +232,14 @@ class Index {
   int64_t indexed_count_ = 0;
   bool trained_ = false;
   mutable std::shared_mutex mu_;  // searches shared, index mutation exclusive
+  // Kernels of a search keep reading the list directory (lengths, base pointers), the centroids and the raw-store
+  // segments AFTER the search call released mu_ (device-resident searches are asynchronous).  Every search leaves an
+  // event on its stream; whoever mutates those structures takes mu_ exclusively (no new search can enqueue) and then
+  // drains the events, so no kernel of an earlier search observes a directory that changes under it.
+  void note_search_enqueued(cudaStream_t st);
+  void drain_searches();
+  std::mutex inflight_mu_;
+  std::vector<cudaEvent_t> inflight_;
   std::mutex build_mu_;           // serialises train / add_pending / update_vector (one writer at a time)
 
   // Request coalescing (reference: the batching thread of its GPU index,
@@ -258,10 +278,26 @@ class Index {
   std::vector<BigBuf> big_;
   void scan_timer_begin(cudaStream_t st);
   void scan_timer_end(cudaStream_t st);
+  // per-stage device times (bench breakdown): CUDA events on the launching stream around each stage of a
+  // search while set_time_scan(true); stage_times() sums them per name since the last call
+  void stage_begin(const char* name, cudaStream_t st);
+  void stage_end(cudaStream_t st);
+  struct StageEv {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<StageEv> stage_events_;
+  struct StageScope {
+    Index* ix;
+    cudaStream_t st;
+    StageScope(Index* i, const char* name, cudaStream_t s) : ix(i), st(s) { ix->stage_begin(name, st); }
+    ~StageScope() { ix->stage_end(st); }
+  };
   std::mutex ev_mu_;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> scan_events_;
   bool time_scan_ = false;
   const char* last_scan_kernel_ = "";  // which scan path served the last search (bench roofline label)
+  char last_scan_info_[160] = "{}";
 };
 
 class FlatIndex : public Index {
@@ -437,5 +473,8 @@ Index* create_index(const std::string& type, int d, const ModelParams& mp, int d
 // in: nparts x nq x k (dis, ids) sorted per partition; out: nq x k, ids = (part << 32) | local id
 int merge_partitions_device(const float* dis, const int64_t* ids, int nparts, int nq, int k, int metric, float* out_dis,
                             int64_t* out_ids, cudaStream_t st);
+// the same merge straight from the partitions' result keys [nparts][nq][k] (Index::search_device out_keys_dev)
+int merge_partition_keys_device(const unsigned long long* keys, int nparts, int nq, int k, int metric, float* out_dis,
+                                int64_t* out_ids, cudaStream_t st);
 
 }  // namespace gb

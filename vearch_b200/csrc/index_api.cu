@@ -234,12 +234,43 @@ int gb_index_search_device(gb_index* index, int nq, const float* x_dev, int64_t 
                                     static_cast<cudaStream_t>(stream));
 }
 
+int gb_index_search_device_keys(gb_index* index, int nq, const float* x_dev, int64_t ld, int k,
+                                const char* retrieval_params_json, int brute_force, unsigned long long* out_keys_dev,
+                                float* out_scores_dev, int64_t* out_ids_dev, void* stream) {
+  IDX_OR_FAIL(index);
+  SearchContext ctx;
+  if (fill_ctx(&ctx, retrieval_params_json, brute_force, nullptr, nullptr, 0, -3.4028235e38f, 3.4028235e38f)) return -1;
+  return index->impl->search_device(ctx, nq, x_dev, ld, k, out_scores_dev, out_ids_dev, static_cast<cudaStream_t>(stream),
+                                    out_keys_dev);
+}
+
+// {"stage": ms, ...} of the searches run since the last call while scan timing was on (malloc'd, caller frees)
+int gb_index_stage_times(gb_index* index, char** json_out, int* out_len) {
+  IDX_OR_FAIL(index);
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : index->impl->stage_times()) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.6f", kv.second);
+    js += std::string(first ? "" : ", ") + "\"" + kv.first + "\": " + buf;
+    first = false;
+  }
+  js += "}";
+  char* p = static_cast<char*>(malloc(js.size() + 1));
+  if (!p) return -1;
+  memcpy(p, js.c_str(), js.size() + 1);
+  *json_out = p;
+  *out_len = (int)js.size();
+  return 0;
+}
+
 void gb_index_set_scan_timing(gb_index* index, int on) {
   if (index && index->impl) index->impl->set_time_scan(on != 0);
 }
 const char* gb_index_last_scan_kernel(gb_index* index) {
   return index && index->impl ? index->impl->last_scan_kernel() : "";
 }
+const char* gb_index_last_scan_info(gb_index* index) { return index && index->impl ? index->impl->last_scan_info() : "{}"; }
 float gb_index_last_scan_ms(gb_index* index) { return index && index->impl ? index->impl->last_scan_ms() : 0.f; }
 
 static IVFFlatIndex* as_ivf(gb_index* index) {
@@ -485,6 +516,16 @@ int gb_merge_partitions_device(int device, const float* dis_dev, const int64_t* 
   }
   return merge_partitions_device(dis_dev, ids_dev, nparts, nq, k, metric, out_dis_dev, out_ids_dev,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int gb_merge_partition_keys_device(int device, const unsigned long long* keys_dev, int nparts, int nq, int k, int metric,
+                                   float* out_dis_dev, int64_t* out_ids_dev, void* stream) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_last_error("no CUDA device");
+    return -1;
+  }
+  return merge_partition_keys_device(keys_dev, nparts, nq, k, metric, out_dis_dev, out_ids_dev,
+                                     static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -155,6 +155,7 @@ cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* prob
 
 // ---- K5 list-major: tensor-core filter + exact re-score (kernels_pqtc.cu) ---------------------------
 bool pqtc_supported(int M, int dsub);
+void pqtc_debug_counters(unsigned long long out[4], bool reset);  // GB_PQTC_DBG diagnostics
 size_t pqtc_pair_meta_bytes();
 // cb[m][c][.] = bf16(-2 pq) (L2) / bf16(-pq) (IP); nrm[m][c] = |pq[m][c]|^2; rmax2[0] = sum_m max_c nrm
 cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uint16_t* cb, float* nrm, float* rmax2,

@@ -166,6 +166,29 @@ class GammaIndex:
         _check(rc, "search_device")
         return out
 
+    def search_device_keys(self, x, k, params=None, brute_force=False, out_keys=None):
+        """Like search_device, returning only the nq x k int64 result keys (score bits << 32 | doc id, best first):
+        what a partition contributes to merge_partition_keys_device."""
+        import torch
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+        nq = x.shape[0]
+        if out_keys is None:
+            out_keys = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+        pj = json.dumps(params).encode() if params else b""
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib.lib().gb_index_search_device_keys(self._h, nq, C.c_void_p(x.data_ptr()), x.stride(0), k, pj, int(brute_force),
+                                                    C.c_void_p(out_keys.data_ptr()), None, None, C.c_void_p(st))
+        _check(rc, "search_device_keys")
+        return out_keys
+
+    def stage_times(self):
+        """{stage: ms} summed over the searches since the last call (set_scan_timing(True) first)."""
+        p, n = C.c_void_p(), C.c_int()
+        _check(_lib.lib().gb_index_stage_times(self._h, C.byref(p), C.byref(n)), "stage_times")
+        js = C.string_at(p.value, n.value).decode()
+        C.CDLL(None).free(C.c_void_p(p.value))
+        return json.loads(js)
+
     def set_scan_timing(self, on):
         _lib.lib().gb_index_set_scan_timing(self._h, int(on))
 
@@ -176,6 +199,10 @@ class GammaIndex:
     @property
     def last_scan_kernel(self):
         return _lib.lib().gb_index_last_scan_kernel(self._h).decode()
+
+    @property
+    def last_scan_info(self):
+        return json.loads(_lib.lib().gb_index_last_scan_info(self._h).decode() or "{}")
 
     # ---- index-state exchange (parity tests) -------------------------------------------
     def set_centroids(self, c):
@@ -358,6 +385,20 @@ def merge_partitions_device(dis, ids, metric):
                                                  C.c_void_p(ids.data_ptr()), nparts, nq, k, metric,
                                                  C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(st)),
            "merge_partitions_device")
+    return od, oi
+
+
+def merge_partition_keys_device(keys, metric):
+    """keys: torch CUDA int64 tensor [nparts, nq, k] of partition result keys -> merged ([nq,k] scores, [nq,k] ids with
+    ids = partition << 32 | local id) in the router's order (internal/client/client.go:1530-1609)."""
+    import torch
+    nparts, nq, k = keys.shape
+    od = torch.empty((nq, k), dtype=torch.float32, device=keys.device)
+    oi = torch.empty((nq, k), dtype=torch.int64, device=keys.device)
+    st = torch.cuda.current_stream(keys.device).cuda_stream
+    _check(_lib.lib().gb_merge_partition_keys_device(keys.device.index or 0, C.c_void_p(keys.data_ptr()), nparts, nq, k, metric,
+                                                     C.c_void_p(od.data_ptr()), C.c_void_p(oi.data_ptr()), C.c_void_p(st)),
+           "merge_partition_keys_device")
     return od, oi
 
 

@@ -72,3 +72,43 @@ def embed_like_torch(n, d, seed, device, n_clusters=4096, centers_seed=99, sigma
         x = centers[lab] + torch.randn((e - s, d), generator=g, device=device) * sigma
         out[s:e] = x / x.norm(dim=1, keepdim=True)
     return out
+
+
+# ---- a harder SIFT-shaped family ------------------------------------------------------
+# Points near a `latent`-dimensional linear manifold (x = 100 + 3 W z + noise, integer-rounded like sift_like), z from
+# `n_comp` OVERLAPPING Gaussians with Zipf weights: k-means cells cut through dense regions, true neighbours straddle
+# lists (recall rises with nprobe instead of saturating at the first probes) and list lengths are heavy-tailed.
+def _hard_model_np(d, latent, n_comp, centers_seed):
+    rng = np.random.default_rng(centers_seed)
+    W = rng.normal(0, 1, size=(d, latent)).astype(np.float32)
+    comp = (2.0 * rng.normal(0, 1, size=(n_comp, latent))).astype(np.float32)
+    w = 1.0 / np.arange(1, n_comp + 1)
+    return W, comp, (w / w.sum())
+
+
+def sift_hard(n, d=128, seed=1234, latent=16, n_comp=64, centers_seed=99):
+    W, comp, w = _hard_model_np(d, latent, n_comp, centers_seed)
+    rng = np.random.default_rng(seed)
+    lab = rng.choice(n_comp, size=n, p=w)
+    z = comp[lab] + rng.normal(0, 1, size=(n, latent)).astype(np.float32)
+    x = 100.0 + 3.0 * (z @ W.T) + 4.0 * rng.normal(0, 1, size=(n, d)).astype(np.float32)
+    return np.clip(np.rint(x), 0, 218).astype(np.float32)
+
+
+def sift_hard_torch(n, d, seed, device, latent=16, n_comp=64, centers_seed=99, chunk=1 << 20):
+    import torch
+    gc = torch.Generator(device=device)
+    gc.manual_seed(centers_seed)
+    W = torch.randn((d, latent), generator=gc, device=device)
+    comp = 2.0 * torch.randn((n_comp, latent), generator=gc, device=device)
+    w = 1.0 / torch.arange(1, n_comp + 1, device=device, dtype=torch.float32)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, d), dtype=torch.float32, device=device)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        lab = torch.multinomial(w, e - s, replacement=True, generator=g)
+        z = comp[lab] + torch.randn((e - s, latent), generator=g, device=device)
+        x = 100.0 + 3.0 * (z @ W.T) + 4.0 * torch.randn((e - s, d), generator=g, device=device)
+        out[s:e] = torch.clamp(torch.round(x), 0, 218)
+    return out
