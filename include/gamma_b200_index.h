@@ -156,6 +156,9 @@ int gb_debug_dist_matrix(int device, const float *x, int n, const float *c, int 
                          float *out);
 
 /* ---- host-logic test hooks: run the C++ wire codecs of the gamma boundary without a GPU ---- */
+/* RequestConcurrentController (search/engine.cc:47-119): op 0 threshold, 1 in-flight, 2 set threshold (<= 0: system value),
+ * 3 Acquire(value) -> 1/0, 4 Release(value) */
+int gb_debug_concurrency(int op, int value);
 int gb_debug_parse_search_request(const char *buf, int len, char **json_out, int *out_len);
 int gb_debug_roundtrip_doc(const char *buf, int len, char **out, int *out_len);
 int gb_debug_parse_table(const char *buf, int len, char **json_out, int *out_len);

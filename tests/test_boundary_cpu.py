@@ -37,6 +37,17 @@ def test_library_exports_every_declared_symbol(header):
         assert len(names) == 23
 
 
+def test_library_exports_only_the_c_abi():
+    """csrc/exports.map: the dynamic symbol table holds the 23 gamma entry points and gb_* -- no C++ symbol of the
+    implementation leaks into the process that loads the drop-in."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib()._name], capture_output=True, text=True, check=True).stdout
+    names = {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+    gamma = set(declared_symbols("gamma_api.h"))
+    extra = sorted(n for n in names if n not in gamma and not n.startswith("gb_"))
+    assert not extra, f"unexpected exported symbols: {extra[:10]}"
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():

@@ -174,6 +174,45 @@ bool Engine::IsKilled(const std::string& request_id, int partition_id) {
   return g_killed.count({request_id, partition_id}) != 0;
 }
 
+// ---- admission control (search/engine.cc:47-119) ----------------------------------------------
+static int read_proc_int(const char* path) {  // the reference popen()s `cat <path>`; same number, no shell
+  int v = -1;
+  if (FILE* fp = fopen(path, "r")) {
+    if (fscanf(fp, "%d", &v) != 1) v = -1;
+    fclose(fp);
+  }
+  return v;
+}
+RequestConcurrentController& RequestConcurrentController::GetInstance() {
+  static RequestConcurrentController instance;
+  return instance;
+}
+RequestConcurrentController::RequestConcurrentController() {
+  const int threads_max = read_proc_int("/proc/sys/kernel/threads-max");
+  const int max_map_count = read_proc_int("/proc/sys/vm/max_map_count");
+  const int pid_max = read_proc_int("/proc/sys/kernel/pid_max");
+  max_threads_ = std::min(std::min(threads_max, pid_max), max_map_count / 2);
+  const int host_threads = std::max(1u, std::thread::hardware_concurrency());
+  system_threshold_ = (int)((max_threads_ * 0.5) / (host_threads + 1));
+  if (system_threshold_ <= 0) system_threshold_ = 1;  // the reference aborts (LOG(FATAL)); a library must not
+  concurrent_threshold_ = system_threshold_;
+  if (const char* e = getenv("GAMMA_CONCURRENT_THRESHOLD")) set_threshold(atoi(e));
+}
+void RequestConcurrentController::set_threshold(int t) { concurrent_threshold_ = t > 0 ? t : system_threshold_; }
+bool RequestConcurrentController::Acquire(int req_num) {
+  const int num = cur_concurrent_num_.fetch_add(req_num);
+  return num < concurrent_threshold_;
+}
+void RequestConcurrentController::Release(int req_num) { cur_concurrent_num_.fetch_sub(req_num); }
+namespace {
+struct AdmissionGuard {  // every return path of Engine::Search releases what it acquired
+  int n;
+  bool permit;
+  explicit AdmissionGuard(int req_num) : n(req_num), permit(RequestConcurrentController::GetInstance().Acquire(req_num)) {}
+  ~AdmissionGuard() { RequestConcurrentController::GetInstance().Release(n); }
+};
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------
 Engine::Engine(const std::string& path, const std::string& space_name, int device)
     : path_(path), space_name_(space_name), device_(device) {}
@@ -742,6 +781,9 @@ int64_t Engine::eval_filters(const std::vector<SearchRequestPB::Filter>& filters
 Status Engine::Search(const SearchRequestPB& req, std::string* pb_out) {
   if (!created_table_) return Status::Make(kInvalidArgument, space_name_ + " table not created");
   if (req.req_num <= 0) return Status::Make(kInvalidArgument, space_name_ + " req_num should not less than 0");
+  // engine.cc:252-260: Status::ResourceExhausted() = kBusy + "Resource temporarily unavailable"
+  AdmissionGuard admission(req.req_num);
+  if (!admission.permit) return Status::Make(kBusy, "Resource temporarily unavailable");
   if (req.topn <= 0) return Status::Make(kInvalidArgument, "limit[topN] is zero");
   if (req.vec_fields.empty()) return Status::Make(kInvalidArgument, "no vector query");
   if (req.vec_fields.size() > 1) return SearchMulti(req, pb_out);

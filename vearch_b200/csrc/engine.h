@@ -36,6 +36,26 @@ enum StatusCode {
   kTimedOut = 7, kMemoryExceeded = 8, kCanceled = 9
 };
 
+// RequestConcurrentController (search/engine.h:197-222, search/engine.cc:47-119): process-wide admission of
+// Search requests.  Acquire adds req_num to the in-flight count and admits the request while the count BEFORE the
+// add is below the threshold ((min(threads-max, pid_max, max_map_count/2) * 0.5) / (host threads + 1), the
+// reference's rule with omp_get_max_threads() read as the host's hardware threads); a refused request still holds
+// its count until Release, exactly as the reference's call sites do (engine.cc:253-258).
+class RequestConcurrentController {
+ public:
+  static RequestConcurrentController& GetInstance();
+  bool Acquire(int req_num);
+  void Release(int req_num);
+  int threshold() const { return concurrent_threshold_; }
+  int in_flight() const { return cur_concurrent_num_.load(); }
+  void set_threshold(int t);  // test hook (gb_debug_concurrency); <= 0 restores the system-derived value
+
+ private:
+  RequestConcurrentController();
+  int system_threshold_ = 0, concurrent_threshold_ = 0, max_threads_ = 0;
+  std::atomic<int> cur_concurrent_num_{0};
+};
+
 enum DataType { DT_INT = 0, DT_LONG, DT_FLOAT, DT_DOUBLE, DT_STRING, DT_VECTOR, DT_BOOL, DT_DATE, DT_STRINGARRAY };
 
 struct DocField {

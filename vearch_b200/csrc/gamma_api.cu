@@ -211,6 +211,20 @@ static std::string to_hex(const std::string& s) {
 
 extern "C" {
 
+// admission controller introspection: op 0 = threshold, 1 = in-flight count, 2 = set threshold to `value`
+// (<= 0 restores the system-derived one), 3 = Acquire(value) -> 1 admitted / 0 refused, 4 = Release(value)
+int gb_debug_concurrency(int op, int value) {
+  auto& c = gb::RequestConcurrentController::GetInstance();
+  switch (op) {
+    case 0: return c.threshold();
+    case 1: return c.in_flight();
+    case 2: c.set_threshold(value); return c.threshold();
+    case 3: return c.Acquire(value) ? 1 : 0;
+    case 4: c.Release(value); return c.in_flight();
+  }
+  return -1;
+}
+
 int gb_debug_parse_search_request(const char* buf, int len, char** json_out, int* out_len) {
   gb::SearchRequestPB r;
   bool ok = r.parse(reinterpret_cast<const uint8_t*>(buf), (size_t)len);
