@@ -262,16 +262,24 @@ def make_roofline(idx, wl, wl_name, work, nq, k, recall_num, scan_ms, ms_per_ste
             secondary[key] = ncu[key]
     if kname == "pqtc_scan_kernel":
         # entries the tensor-core filter multiplies: probes [phase_a_probes, nprobe) of every query
-        pa = int(info.get("phase_a_probes", 1))
+        # (index.cu scan_listmajor_pq: phase A = the fewest leading probes with >= target entries, at most pa_max)
+        pa_max, target = int(info.get("phase_a_max_probes", 1)), int(info.get("phase_a_target_entries", -1))
         keys, lens = work["_keys"], work["_lens"]
-        kt = keys[:, pa:]
-        ent_tc = float(lens[kt[kt >= 0]].sum())
+        ll = np.where(keys >= 0, lens[np.maximum(keys, 0)], 0)
+        if target > 0:
+            reached = np.cumsum(ll[:, :pa_max], axis=1) >= target
+            pa_q = np.where(reached.any(axis=1), reached.argmax(axis=1) + 1, pa_max)
+        else:
+            pa_q = np.full(keys.shape[0], pa_max)
+        in_b = np.arange(keys.shape[1])[None, :] >= pa_q[:, None]
+        ent_tc = float(ll[in_b].sum())
+        info = dict(info, phase_a_probes_mean=float(pa_q.mean()))
         aflops = ent_tc * 2.0 * wl["d"]
         ach = aflops / sec / 1e12 if sec else None
         r.update({"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak if ach else None,
-                  "peak_source": tc_src, "algorithmic_flops_per_launch": aflops, "mma_kind": "kind::f16 (bf16 operands, fp32 accumulate)",
+                  "peak_source": tc_src, "algorithmic_flops_per_launch": aflops, "mma_kind": "kind::f16 (fp16 operands, power-of-two scaled; fp32 accumulate)",
                   "filter": info, "entries_filtered_on_tensor_cores": ent_tc,
-                  "note": "list-major ADC: 2*d flop per (query, entry) pair of probes >= phase_a_probes; the codes are read once per "
+                  "note": "list-major ADC: 2*d flop per (query, entry) pair of the probes behind each query's phase A; the codes are read once per "
                           "128 (query, list) pairs and decoded in shared memory, so neither HBM nor the 8(d) byte count binds it"})
     elif kname.startswith("ivf_listmajor"):
         aflops = work["entries"] * 2.0 * wl["d"]

@@ -300,3 +300,21 @@ def test_oracle_matches_known_answer_vectors():
     assert np.array_equal(d, g["ip_dis"])
     for q in range(xq.shape[0]):  # CMin reorder lists equal scores with the larger id first
         assert sorted(zip(-d[q], i[q])) == sorted(zip(-g["ip_dis"][q], g["ip_ids"][q]))
+
+
+def test_request_concurrent_controller_counts():
+    """search/engine.cc:47-69: Acquire adds req_num and admits while the count before the add is below the threshold;
+    a refused Acquire still holds its count until Release."""
+    lib = _lib.lib()
+    base = lib.gb_debug_concurrency(1, 0)
+    sys_thr = lib.gb_debug_concurrency(0, 0)
+    assert sys_thr >= 1
+    try:
+        assert lib.gb_debug_concurrency(2, base + 3) == base + 3
+        assert lib.gb_debug_concurrency(3, 2) == 1   # 0 < 3
+        assert lib.gb_debug_concurrency(3, 2) == 1   # 2 < 3
+        assert lib.gb_debug_concurrency(3, 1) == 0   # 4 >= 3: refused, but counted
+        assert lib.gb_debug_concurrency(1, 0) == base + 5
+        assert lib.gb_debug_concurrency(4, 5) == base
+    finally:
+        assert lib.gb_debug_concurrency(2, 0) == sys_thr

@@ -244,6 +244,32 @@ def test_kill_switch_and_config(tmp_path, data):
     e.close()
 
 
+def test_admission_control_refuses_with_resource_exhausted(tmp_path, data):
+    """RequestConcurrentController (search/engine.cc:47-119, :252-260): a Search arriving while the in-flight request
+    count is at the threshold fails with Status::ResourceExhausted() = code kBusy (6), "Resource busy: Resource
+    temporarily unavailable", and gives its count back; below the threshold it is admitted."""
+    db, xq = data
+    E = eng_mod()
+    e = make_engine(tmp_path, "FLAT", {"metric_type": "L2"})
+    add_all(e, db[:50])
+    api = E._api()
+    base = api.gb_debug_concurrency(1, 0)
+    assert api.gb_debug_concurrency(0, 0) >= 1  # system-derived threshold
+    try:
+        assert api.gb_debug_concurrency(2, base + 4) == base + 4
+        assert api.gb_debug_concurrency(3, 4) == 1  # four requests in flight elsewhere: admitted, threshold reached
+        with pytest.raises(E.GammaStatusError) as ei:
+            e.search(xq[:1], 3)
+        assert ei.value.code == 6 and ei.value.msg == "Resource busy: Resource temporarily unavailable"
+        assert api.gb_debug_concurrency(1, 0) == base + 4  # the refused request released its count
+        api.gb_debug_concurrency(4, 4)
+        assert len(e.search(xq[:2], 3)) == 2
+        assert api.gb_debug_concurrency(1, 0) == base
+    finally:
+        api.gb_debug_concurrency(2, 0)
+    e.close()
+
+
 def test_enable_realtime_searches_unindexed_tail(tmp_path, data):
     """table.enable_realtime: documents that are stored but not yet picked up by the indexing thread
     are searched brute-force and merged (vector_manager.cc:854-889, 971-1053)."""

@@ -799,3 +799,81 @@ def test_ivfpq_opq_rotation_train_apply_search_and_file(tmp_path):
     assert np.array_equal(d2, dg) and np.array_equal(i2, ig)
     for idx in (plain, opq, again):
         idx.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json shapes (C2: IVF-Flat d=128 nlist=1024 nprobe=32; C3: IVF-PQ d=128 M=16 nlist=4096, re-rank 400)
+# at database sizes the oracle finishes in seconds: same kernel instantiations as bench.py runs
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["query_major", "list_major"])
+@pytest.mark.parametrize("data", ["int", "float"])
+def test_baseline_shape_ivfflat_d128_nlist1024_nprobe32(path, data, monkeypatch):
+    d, n, nlist, nprobe, k = 128, 200_000, 1024, 32, 10
+    nq = 1100 if path == "list_major" else 200  # >= 32 (query, probe) pairs per list selects the list-major scan
+    if data == "int":
+        db, xq = synth.sift_like(n, d, seed=301), synth.sift_like(nq, d, seed=302)
+    else:
+        db, xq = synth.sift_like(n, d, seed=303, rounded=False), synth.sift_like(nq, d, seed=304, rounded=False)
+    if path == "query_major":
+        monkeypatch.setenv("GB_LISTMAJOR", "0")
+    idx = gi().GammaIndex("IVFFLAT", d, {"ncentroids": nlist, "nprobe": nprobe, "metric_type": "L2",
+                                         "training_threshold": nlist * 39})
+    idx.add_vectors(db)
+    idx.train()
+    idx.add_pending()
+    assert idx.indexed_count == n
+    off, codes, ids = idx.export_lists()
+    vecs = codes.view(np.float32).reshape(len(ids), -1)[:, :d]
+    cd, keys = idx.coarse_search(xq, nprobe)
+    dg, ig = idx.search_preassigned(xq, k, keys, cd)
+    want = "ivf_listmajor_tma_kernel" if path == "list_major" else "ivfflat_scan_warp_kernel"
+    assert idx.last_scan_kernel == want
+    do, io = orc.ivfflat_search_preassigned(off, vecs, ids, xq, k, keys, L2)
+    if data == "int":
+        assert_same_results(dg, ig, do, io)  # bit-equal scores
+    else:  # float data: summation order differs from the scalar loop (north-star tolerance 1e-4 relative)
+        assert_same_results(dg, ig, do, io, bit_exact=False, rtol=1e-4)
+    assert (ig == io).mean() >= 0.999
+    # the end-to-end call (own coarse quantiser) returns the same thing
+    d2, i2 = idx.search(xq, k)
+    assert np.array_equal(i2, ig)
+    idx.close()
+
+
+@pytest.mark.parametrize("data", ["int", "float"])
+def test_baseline_shape_ivfpq_d128_m16_nlist4096_rerank400(data):
+    d, n, nlist, M, nprobe, k, recall_num = 128, 200_000, 4096, 16, 32, 10, 400
+    nq = 4200  # nq * nprobe >= 32 * nlist: the tensor-core filter path of bench.py's default workload
+    if data == "int":
+        db, xq = synth.sift_like(n, d, seed=311), synth.sift_like(nq, d, seed=312)
+    else:
+        db, xq = synth.sift_like(n, d, seed=313, rounded=False), synth.sift_like(nq, d, seed=314, rounded=False)
+    idx = gi().GammaIndex("IVFPQ", d, {"ncentroids": nlist, "nprobe": nprobe, "nsubvector": M, "metric_type": "L2",
+                                       "training_threshold": nlist * 39})
+    idx.add_vectors(db)
+    idx.train()
+    idx.add_pending()
+    off, codes, ids = idx.export_lists()
+    cent, pqc, T = idx.get_centroids(), idx.get_pq_centroids(), idx.get_precomputed_table()
+    assert np.array_equal(T, orc.ivfpq_precompute_table(cent, pqc))
+    cd, keys = idx.coarse_search(xq, nprobe)
+    # ADC stage at the re-rank depth: bit-equal scores, ids equal outside boundary ties
+    dg, ig = idx.search_preassigned(xq, recall_num, keys, cd)
+    assert idx.last_scan_kernel == "pqtc_scan_kernel"
+    do, io = orc.ivfpq_search_preassigned(off, codes, ids, cent, pqc, T, xq, recall_num, keys, cd, L2)
+    assert_same_results(dg, ig, do, io)
+    # the same through the exact LUT kernel (small batch): identical answers
+    d1, i1 = idx.search_preassigned(xq[:64], recall_num, keys[:64], cd[:64])
+    assert idx.last_scan_kernel == "ivfpq_scan_kernel"
+    assert np.array_equal(d1, dg[:64]) and np.array_equal(i1, ig[:64])
+    # final answer with the exact re-rank (what bench.py times): exact L2 of the ADC candidates, best k
+    dr, ir = idx.search_preassigned(xq, k, keys, cd, params={"recall_num": recall_num})
+    agree = []
+    for q in range(0, nq, 7):
+        cand = io[q][io[q] >= 0]
+        exact = ((xq[q].astype(np.float64) - db[cand]) ** 2).sum(1)
+        order = np.lexsort((cand, exact))[:k]
+        assert np.allclose(dr[q][: len(order)], exact[order], rtol=1e-5)
+        agree.append(np.mean(ir[q][: len(order)] == cand[order]))
+    assert np.mean(agree) >= 0.999
+    idx.close()

@@ -1474,8 +1474,22 @@ int IVFFlatIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int me
   (void)coarse_dis;
   cudaStream_t st = s.stream();
   if (type_ == "IVFFLAT") {
-    int lm = scan_listmajor_dev(f, metric, nq, xq, k, probe_ids, nprobe, out_keys, s);
-    if (lm <= 0) return lm;
+    // The list-major scan selects on 3xTF32 tensor-core scores (|x|^2 + |y|^2 - 2 x.y for L2: on SIFT-like float data,
+    // |x|^2 ~ 40 d^2, the cancellation leaves ~1e-4 relative).  Its k winners are re-scored with the direct fp32 form
+    // from the raw vectors and re-sorted (rerank_kernel, k rows per query), so every distance that leaves the index is
+    // the exact-kernel value; on integer-valued data both forms are exact and nothing changes.
+    GB_ALLOC(lm_keys, unsigned long long, (size_t)nq * k, s);
+    int lm = scan_listmajor_dev(f, metric, nq, xq, k, probe_ids, nprobe, lm_keys, s);
+    if (lm < 0) return lm;
+    if (lm == 0) {
+      if ((dpad_ & 3) == 0 && k <= 8192) {
+        GB_CUDA(launch_rerank(lm_keys, k, nq, xq, dpad_, dpad_, store_->d_segs(), store_->seg_shift(), dpad_, k, metric, f,
+                              out_keys, st));
+      } else {
+        GB_CUDA(cudaMemcpyAsync(out_keys, lm_keys, (size_t)nq * k * 8, cudaMemcpyDeviceToDevice, st));
+      }
+      return 0;
+    }
   }
   int nparts = ivfflat_scan_nparts(nprobe, lists_->max_len());
   GB_ALLOC(partial, unsigned long long, (size_t)nq * nparts * k, s);
@@ -1947,20 +1961,29 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   if (mode != 2 && npairs < (int64_t)nlist_ * 32) return 1;  // < 32 queries per list on average
   cudaStream_t st = s.stream();
   ListDirectory dir = lists_->directory();
-  // phase A depth: enough probes to expect >= 4 k' entries, so its k'-th score is a usable bound
-  const int64_t avg_len = std::max<int64_t>(1, lists_->total() / std::max(1, nlist_));
-  int pa = (int)std::min<int64_t>(nprobe - 1, std::max<int64_t>(1, (4 * (int64_t)kk + avg_len - 1) / avg_len));
-  if (const char* e = getenv("GB_PQTC_PA")) pa = std::max(1, std::min(nprobe - 1, atoi(e)));
-  const int cap = std::max(1024, std::min(8192, next_pow2(4 * kk)));
+  // phase A depth, per query: the fewest leading probes whose lists hold >= 4 k' entries together (so that its k'-th
+  // exact score is a usable bound), at most pa_max.  GB_PQTC_PA=n fixes the depth at n probes for every query.
+  int pa_max = std::min(nprobe - 1, 8);
+  long long pa_target = 4 * (long long)kk;
+  if (const char* e = getenv("GB_PQTC_PA")) {
+    pa_max = std::max(1, std::min(nprobe - 1, atoi(e)));
+    pa_target = LLONG_MAX;
+  }
+  const int cap = std::max(2048, std::min(8192, next_pow2(8 * kk)));
   const int nsm = sm_count(device_);
-  snprintf(last_scan_info_, sizeof(last_scan_info_), "{\"phase_a_probes\": %d, \"candidate_cap\": %d, \"kprime\": %d}", pa, cap, kk);
+  snprintf(last_scan_info_, sizeof(last_scan_info_),
+           "{\"phase_a_max_probes\": %d, \"phase_a_target_entries\": %lld, \"candidate_cap\": %d, \"kprime\": %d}", pa_max,
+           pa_target == LLONG_MAX ? -1LL : pa_target, cap, kk);
+  GB_ALLOC(d_probes_a, int32_t, npairs, s);
+  GB_ALLOC(d_masked, int32_t, npairs, s);
+  GB_CUDA(launch_pqtc_split_probes(probe_ids, npairs, nprobe, pa_max, pa_target, dir.len, d_probes_a, d_masked, st));
 
-  // ---- phase A: exact keys of probes [0, pa) ----
-  const int pgA = (int)std::min<int64_t>(32, std::max<int64_t>(1, (int64_t)pa * nq / ((int64_t)nsm * 32)));
-  const int ngA = (pa + pgA - 1) / pgA;
+  // ---- phase A: exact keys of each query's leading probes ----
+  const int pgA = nq >= nsm * 4 ? std::min(pa_max, 32) : 1;  // one CTA per query when there are queries enough
+  const int ngA = (pa_max + pgA - 1) / pgA;
   GB_ALLOC(partA, unsigned long long, (size_t)nq * ngA * kk, s);
   stage_begin("pq_phaseA_exact_scan", st);
-  GB_CUDA(launch_ivfpq_scan(ip, nq, probe_ids, coarse_dis, pa, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe));
+  GB_CUDA(launch_ivfpq_scan(ip, nq, d_probes_a, coarse_dis, pa_max, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe));
   unsigned long long* keysA = partA;
   if (ngA > 1) {
     keysA = s.alloc_n<unsigned long long>((size_t)nq * kk);
@@ -1974,7 +1997,6 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   const int64_t max_groups = npairs / 128 + nlist_;
   const int64_t max_items = max_groups * nseg;
   if (max_items > INT32_MAX) return 1;
-  GB_ALLOC(d_masked, int32_t, npairs, s);
   GB_ALLOC(d_cnt, int32_t, nlist_, s);
   GB_ALLOC(d_start, int32_t, nlist_, s);
   GB_ALLOC(d_cursor, int32_t, nlist_, s);
@@ -1997,7 +2019,6 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(big + a_bytes + meta_bytes);
   stage_begin("pq_group_and_stage_pairs", st);
   GB_CUDA(cudaMemsetAsync(d_cand_cnt, 0, sizeof(int) * nq, st));
-  GB_CUDA(launch_pqtc_mask_probes(probe_ids, npairs, nprobe, pa, d_masked, st));
   GB_CUDA(launch_lmk_group(d_masked, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
                            d_pair_j, d_items, st));
   GB_CUDA(launch_pq_stage_pairs(xq, dpad_, d_, d_centroids_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe,
@@ -2036,7 +2057,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
     GB_CUDA(cudaMemcpy(hpj.data(), d_pair_j, hpj.size() * 8, cudaMemcpyDeviceToHost));
     GB_CUDA(cudaMemcpy(hit.data(), d_items, hit.size() * sizeof(LmTile), cudaMemcpyDeviceToHost));
     if (FILE* fp = fopen(dump, "wb")) {
-      const int hdr[8] = {nq, cap, kk, pa, (int)ht[1], (int)npairs, (int)sizeof(LmTile), (int)ht[2]};
+      const int hdr[8] = {nq, cap, kk, pa_max, (int)ht[1], (int)npairs, (int)sizeof(LmTile), (int)ht[2]};
       fwrite(hdr, 4, 8, fp);
       fwrite(h.data(), 4, h.size(), fp);
       fwrite(hc.data(), 8, hc.size(), fp);
@@ -2057,8 +2078,20 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
     }
     unsigned long long dc[4];
     pqtc_debug_counters(dc, true);
-    fprintf(stderr, "[pqtc] nq=%d k'=%d pa=%d cap=%d: candidates mean %.1f max %lld, overflowed queries %lld, dbg counters %llu %llu\n",
-            nq, kk, pa, cap, nq > over ? (double)tot / (nq - over) : 0.0, mx, over, dc[0], dc[1]);
+    int64_t ht[3];
+    GB_CUDA(cudaMemcpy(ht, d_totals, sizeof(ht), cudaMemcpyDeviceToHost));
+    std::vector<LmTile> hit((size_t)ht[1]);
+    GB_CUDA(cudaMemcpy(hit.data(), d_items, hit.size() * sizeof(LmTile), cudaMemcpyDeviceToHost));
+    long long tiles = 0, pair_rows = 0, rows = 0;
+    for (const LmTile& t : hit) {
+      tiles += (t.nrows + 127) / 128;
+      pair_rows += (long long)t.npairs * t.nrows;
+      rows += t.nrows;
+    }
+    fprintf(stderr, "[pqtc] nq=%d k'=%d pa_max=%d cap=%d: candidates mean %.1f max %lld, overflowed queries %lld, dbg counters %llu %llu; "
+            "items %lld groups %lld tiles(128x128) %lld rows decoded %lld pair-rows %lld (tile fill %.3f)\n",
+            nq, kk, pa_max, cap, nq > over ? (double)tot / (nq - over) : 0.0, mx, over, dc[0], dc[1], (long long)ht[1], (long long)ht[0],
+            tiles, rows, pair_rows, tiles ? (double)pair_rows / ((double)tiles * 128 * 128) : 0.0);
   }
   return 0;
 }

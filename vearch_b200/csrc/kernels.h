@@ -160,9 +160,10 @@ size_t pqtc_pair_meta_bytes();
 // cb[m][c][.] = bf16(-2 pq) (L2) / bf16(-pq) (IP); nrm[m][c] = |pq[m][c]|^2; rmax2[0] = sum_m max_c nrm
 cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uint16_t* cb, float* nrm, float* rmax2,
                                cudaStream_t st);
-// out[j] = probe j % nprobe < pa ? -1 : probe_ids[j]
-cudaError_t launch_pqtc_mask_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa, int32_t* out,
-                                    cudaStream_t st);
+// per query: phase A = its first P_q probes (fewest with >= target entries together, at most pa_max), phase B = the
+// rest; out_a / out_b = probe_ids with the other phase's probes set to -1
+cudaError_t launch_pqtc_split_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
+                                     const int* list_len, int32_t* out_a, int32_t* out_b, cudaStream_t st);
 // per pair group: bf16 operand tile of (x - centroid) (L2) / x (IP) rows + the pairs' filter thresholds from
 // bound_keys[q][kprime - 1] (phase A's k'-th key); queries without a bound get cand_cnt = cap + 1
 cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const float* coarse, int64_t ldc, const LmTile* items,

@@ -9,19 +9,19 @@
 // LDS wavefronts, not by HBM.  When every list is probed by dozens of queries of the same batch the
 // same numbers are a dense contraction:
 //     sum_m tab[m][code[m]] = |r_e|^2 - 2 <x - c_list, r_e>,   r_e = the entry's PQ reconstruction,
-// i.e. (query, list) pairs x decoded entries.  This file computes THAT on tcgen05 in bf16 and uses it
+// i.e. (query, list) pairs x decoded entries.  This file computes THAT on tcgen05 in fp16 (power-of-two scaled) and uses it
 // only as a FILTER; every number that leaves the pipeline is recomputed with the reference's own
 // arithmetic, so results stay bit-identical to the LUT kernel and to the oracle:
 //
 //   phase A  the exact LUT kernel scans the first `pa` probes of every query and yields k' exact
 //            keys; its k'-th score B_q is an upper bound of the query's final k'-th score;
 //   phase B  (this file) for the remaining probes: pairs grouped by list (lmk_group), per group a
-//            bf16 operand tile of (x - c_list) rows staged once (pq_stage_pairs_kernel), then a
+//            fp16 operand tile of sa * (x - c_list) rows staged once (pq_stage_pairs_kernel), then a
 //            persistent warp-specialised kernel (pqtc_scan_kernel) decodes 128 entries at a time
 //            from their codes into the second operand (codebook in shared memory, pre-scaled by -2),
 //            multiplies 128 pairs x 128 entries x d on the tensor core and compares
 //            acc + |r_e|^2 against  B_q - dis0 + eps(pair).  eps bounds |approximate - reference fp32|
-//            rigorously (bf16 rounding of both operands: 2^-7 |a||r| ; fp32 noise of both evaluations),
+//            rigorously (fp16 rounding of both operands: 2^-10 |a||r| ; fp32 noise of both evaluations),
 //            so every entry whose reference score is <= B_q passes.  Passing entries (a few per
 //            query beyond k') are appended to the query's candidate list as (probe, position);
 //   phase C  pq_rescore_kernel re-evaluates the candidates with the reference arithmetic (same
@@ -29,7 +29,7 @@
 //   A query whose candidate list overflows (no usable bound, adversarial data) is redone by the
 //   exact kernel over all its probes (flag-gated launch), so the result never depends on the filter.
 //
-// Operand layout: canonical no-swizzle K-major UMMA tiles of bf16 (8-row x 16-byte core matrices,
+// Operand layout: canonical no-swizzle K-major UMMA tiles of fp16 (8-row x 16-byte core matrices,
 // LBO 2048 = next core matrix along K, SBO 128 = next 8 rows).  With dsub = 8 a sub-quantiser's
 // centroid IS one 16-byte core-matrix row: decoding an entry is M x (LDS.128 from the codebook,
 // STS.128 into the tile), conflict-free on the store side (consecutive entries -> consecutive rows).
@@ -64,28 +64,42 @@ struct PtShared {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));  // first source -> upper half
   return r;
 }
+// power of two that brings a magnitude `mx` into [2^13, 2^14): fp16 keeps 11 significant bits there and a further
+// factor 2 (the -2 of the L2 form) still fits below 65504
+__device__ __forceinline__ float pow2_scale_for(float mx) { return mx > 0.f && mx < INFINITY ? ldexpf(1.0f, 13 - ilogbf(mx)) : 1.0f; }
 
 // ---- tables derived from the PQ codebook ---------------------------------------------------------
-// cb[m][c][0..dsub) = bf16(scale * pq[m][c][.]),  nrm[m][c] = |pq[m][c]|^2 (fp32, L2 only),
-// rmax2[0] = sum_m max_c |pq[m][c]|^2  (single CTA, M*256 threads-strided)
+// sb = power of two scaling the largest codebook component into [2^13, 2^14) (exact in fp32 and fp16);
+// cb[m][c][0..dsub) = fp16(scale * sb * pq[m][c][.]),  nrm[m][c] = |pq[m][c]|^2 (fp32, L2 only),
+// rmax2[0] = sum_m max_c |pq[m][c]|^2,  rmax2[1] = sb   (single CTA of 256 threads)
 __global__ void __launch_bounds__(256)
     pqtc_tables_kernel(const float* __restrict__ pq, int M, int dsub, float scale, uint16_t* __restrict__ cb,
                        float* __restrict__ nrm, float* __restrict__ rmax2) {
   __shared__ float s_max[256];
+  const int c = threadIdx.x;
+  float mx = 0.f;
+  for (int i = c; i < M * PT_KSUB * dsub; i += 256) mx = fmaxf(mx, fabsf(pq[i]));
+  s_max[c] = mx;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (c < off) s_max[c] = fmaxf(s_max[c], s_max[c + off]);
+    __syncthreads();
+  }
+  const float sb = pow2_scale_for(s_max[0]);
+  __syncthreads();
   float total = 0.f;
   for (int m = 0; m < M; m++) {
-    const int c = threadIdx.x;
     const float* p = pq + ((int64_t)m * PT_KSUB + c) * dsub;
     float n2 = 0.f;
     for (int j = 0; j < dsub; j++) {
       const float v = p[j];
       n2 = fmaf(v, v, n2);
-      const uint32_t b = pack_bf16x2(scale * v, 0.f);
+      const uint32_t b = pack_f16x2(scale * sb * v, 0.f);
       cb[((int64_t)m * PT_KSUB + c) * dsub + j] = (uint16_t)(b & 0xFFFFu);
     }
     nrm[m * PT_KSUB + c] = n2;
@@ -98,21 +112,41 @@ __global__ void __launch_bounds__(256)
     total += s_max[0];
     __syncthreads();
   }
-  if (threadIdx.x == 0) rmax2[0] = total;
+  if (threadIdx.x == 0) rmax2[0] = total, rmax2[1] = sb;
 }
 
-// ---- probes [0, pa) are phase A's: hide them from the grouping -----------------------------------
-__global__ void pqtc_mask_probes_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, int pa,
-                                        int32_t* __restrict__ out) {
+// ---- split the probes between phase A (exact scan -> bound) and phase B (tensor-core filter) -------------------------
+// Query q's phase A takes its first P_q probes: the fewest whose lists hold >= target entries together (so that the
+// k'-th exact score is a usable bound), at most pa_max.  out_a / out_b are copies of probe_ids with the other phase's
+// probes set to -1 ("no list", skipped by both scans).
+__global__ void pqtc_split_probes_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, int pa_max,
+                                         long long target, const int* __restrict__ list_len, int32_t* __restrict__ out_a,
+                                         int32_t* __restrict__ out_b) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= npairs) return;
-  out[j] = (int)(j % nprobe) < pa ? -1 : probe_ids[j];
+  const int64_t q = j / nprobe;
+  const int p = (int)(j - q * nprobe);
+  const int32_t* row = probe_ids + q * nprobe;
+  int P = pa_max;
+  long long cum = 0;
+  for (int i = 0; i < pa_max; i++) {
+    const int l = row[i];
+    if (l >= 0) cum += list_len[l];
+    if (cum >= target) {
+      P = i + 1;
+      break;
+    }
+  }
+  const int32_t id = row[p];
+  out_a[j] = p < P ? id : -1;
+  out_b[j] = p < P ? -1 : id;
 }
 
 // ---- per pair group: the A operand tile and the pairs' thresholds ---------------------------------
 struct PairMeta {
-  float thr;  // candidate  <=>  acc + ne <= thr
-  float lo;   // ... and acc + ne >= lo  (the other side of the score window, checked on the rare path)
+  float thr;  // candidate  <=>  acc + c * ne <= thr   (thr, lo already multiplied by c)
+  float lo;   // ... and acc + c * ne >= lo  (the other side of the score window, checked on the rare path)
+  float c;    // sa * sb: the operands' power-of-two scales (accumulator = c * (-2 <a, r>))
   int q, p;
 };
 
@@ -131,7 +165,7 @@ __global__ void __launch_bounds__(PT_M)
   const int r = threadIdx.x;
   const int kc_n = d / 8;
   unsigned char* tile = a_scratch + (int64_t)t.grp * ((int64_t)kc_n * 2048);
-  PairMeta pm{-INFINITY, INFINITY, -1, 0};
+  PairMeta pm{-INFINITY, INFINITY, 1.0f, -1, 0};
   const float* x = nullptr;
   const float* c = nullptr;
   if (r < t.npairs) {
@@ -141,10 +175,10 @@ __global__ void __launch_bounds__(PT_M)
     x = xq + (int64_t)pm.q * ldq;
     c = coarse + (int64_t)t.list * ldc;
   }
-  float na2 = 0.f, nx2 = 0.f, nc2 = 0.f;
-  for (int kc = 0; kc < kc_n; kc++) {
-    uint4 out = make_uint4(0u, 0u, 0u, 0u);
-    if (x) {
+  // pass 1: norms and the largest component of the row a = x - c (L2) / x (IP)
+  float na2 = 0.f, nx2 = 0.f, nc2 = 0.f, amax = 0.f;
+  if (x) {
+    for (int kc = 0; kc < kc_n; kc++) {
       const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + kc * 8)), x1 = __ldg(reinterpret_cast<const float4*>(x + kc * 8 + 4));
       float a[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       if (METRIC == kMetricL2) {
@@ -158,9 +192,22 @@ __global__ void __launch_bounds__(PT_M)
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; u++) na2 = fmaf(a[u], a[u], na2);
-      out.x = pack_bf16x2(a[0], a[1]), out.y = pack_bf16x2(a[2], a[3]);
-      out.z = pack_bf16x2(a[4], a[5]), out.w = pack_bf16x2(a[6], a[7]);
+      for (int u = 0; u < 8; u++) na2 = fmaf(a[u], a[u], na2), amax = fmaxf(amax, fabsf(a[u]));
+    }
+  }
+  // pass 2: the row as fp16(sa * a), sa a power of two (exact), in the canonical K-major operand layout
+  const float sa = pow2_scale_for(amax);
+  for (int kc = 0; kc < kc_n; kc++) {
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (x) {
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + kc * 8)), x1 = __ldg(reinterpret_cast<const float4*>(x + kc * 8 + 4));
+      float a[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      if (METRIC == kMetricL2) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(c + kc * 8)), c1 = __ldg(reinterpret_cast<const float4*>(c + kc * 8 + 4));
+        a[0] -= c0.x, a[1] -= c0.y, a[2] -= c0.z, a[3] -= c0.w, a[4] -= c1.x, a[5] -= c1.y, a[6] -= c1.z, a[7] -= c1.w;
+      }
+      out.x = pack_f16x2(sa * a[0], sa * a[1]), out.y = pack_f16x2(sa * a[2], sa * a[3]);
+      out.z = pack_f16x2(sa * a[4], sa * a[5]), out.w = pack_f16x2(sa * a[6], sa * a[7]);
     }
     *reinterpret_cast<uint4*>(tile + (int64_t)kc * 2048 + r * 16) = out;
   }
@@ -168,25 +215,33 @@ __global__ void __launch_bounds__(PT_M)
     const float dis0 = coarse_dis[(int64_t)pm.q * nprobe + pm.p];
     const unsigned long long bk = bound_keys[(int64_t)pm.q * bound_stride + kprime - 1];
     const float R2 = rmax2[0], R = sqrtf(R2);
+    pm.c = sa * rmax2[1];
     if (bk == kKeySentinel) {
       // phase A found fewer than k' entries: no bound -> the exact kernel redoes this query
       atomicMax(cand_cnt + pm.q, cap + 1);
     } else {
       const float B = ord2score((uint32_t)(bk >> 32), METRIC);
+      float thr, lo;
       if (METRIC == kMetricL2) {
-        // |approx - reference| <= 2^-7 (1 + 2^-9) |a| |r|  (bf16 rounding of both operands, -2 scaling exact)
-        //   + fp32 noise of the two evaluations, bounded by 2^-17 of the magnitudes that enter them
+        // |approx - reference| <= 2^-10 (1 + 2^-12) |a| |r|: fp16 rounding (unit roundoff 2^-12) of both operands of
+        //   -2 <a, r>; the power-of-two scales are exact, components below fp16's normal range are >= 2^27 times
+        //   smaller than the row's largest and fall inside the 5 % slack, as does the fp32 accumulation of the MMA
+        //   (<= 2^-15 |a| |r| for d <= 4096 even if every add truncated)
+        //   + fp32 noise of the reference evaluation, bounded by 2^-17 of the magnitudes that enter it
         const float Z = fabsf(dis0) + R2 + 2.f * (sqrtf(nx2) + sqrtf(nc2)) * R;
-        const float eps = eps_scale * (1.05f * 0.0078125f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
-        pm.thr = fminf(B, max_score) - dis0 + eps;
-        pm.lo = min_score - dis0 - eps;
+        const float eps = eps_scale * (1.05f * 0.0009765625f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
+        thr = fminf(B, max_score) - dis0 + eps;
+        lo = min_score - dis0 - eps;
       } else {
-        // score = dis0 - acc (the codebook is staged negated); better = larger
+        // score = dis0 - acc / c (the codebook is staged negated); better = larger
         const float Z = fabsf(dis0) + sqrtf(na2) * R;
-        const float eps = eps_scale * (1.05f * 0.00390625f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
-        pm.thr = dis0 - fmaxf(B, min_score) + eps;
-        pm.lo = dis0 - max_score - eps;
+        const float eps = eps_scale * (1.05f * 0.00048828125f * sqrtf(na2) * R + 7.62939453125e-6f * Z);
+        thr = dis0 - fmaxf(B, min_score) + eps;
+        lo = dis0 - max_score - eps;
       }
+      // compared against acc + c * ne; FLT_MAX keeps masked entries (ne = +inf) out even when the product overflows
+      pm.thr = fminf(thr * pm.c, FLT_MAX);
+      pm.lo = lo * pm.c;
     }
   }
   meta[(int64_t)t.grp * PT_M + r] = pm;
@@ -207,22 +262,60 @@ __device__ __forceinline__ void pt_load32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// rare path of the epilogue: the 32 columns of one pair contain at least one candidate
-__device__ __noinline__ void pt_push_hits(const uint32_t (&v)[32], const float* ne32, float thr, float lo, int q, int p,
-                                          uint32_t pos0, int* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
-                                          int cap) {
-#pragma unroll 1
-  for (int j = 0; j < 32; j++) {
-    const float s = __uint_as_float(v[j]) + ne32[j];
-    if (s <= thr && s >= lo) {
-      const int slot = atomicAdd(cand_cnt + q, 1);
-      if (slot < cap) cand[(int64_t)q * cap + slot] = ((unsigned long long)(uint32_t)p << 32) | (pos0 + (uint32_t)j);
-    }
-  }
+__device__ __forceinline__ void pt_load32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
 }
 
-// M sub-quantisers of DSUB dimensions, d = M * DSUB, DSUB in {4, 8, 16, 32}; HAS_NORM: L2 (|r|^2 term)
-template <int M, int DSUB, bool HAS_NORM>
+// rare path of the epilogue: the 32 columns of one pair contain at least one candidate.  Returns false once the
+// query's candidate list is full: the query is going to be redone by the exact kernel, so the caller stops
+// pushing for this pair (a query without a usable bound would otherwise hammer one counter with millions of
+// same-address atomics and stall the pipeline behind it).
+__device__ __noinline__ bool pt_push_hits(uint32_t taddr, const float* ne32, float c, float thr, float lo, int q, int p, uint32_t pos0,
+                                          int* __restrict__ cand_cnt, unsigned long long* __restrict__ cand, int cap, bool active) {
+  // Called by the WHOLE warp (tcgen05.ld is .sync.aligned: every lane must execute it, convergently); `active` = this
+  // lane's pair has a candidate among the 32 columns.  The columns are read from TMEM again here: handing the caller's
+  // register block over by reference would force a local-memory copy of every accumulator block in the hot loop.
+  uint32_t v[32];
+  pt_load32(taddr, v);
+  if (!active) return true;
+  if (*reinterpret_cast<volatile int*>(cand_cnt + q) > cap) return false;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const float s = fmaf(ne32[j], c, __uint_as_float(v[j]));
+    if (s <= thr && s >= lo) mask |= 1u << j;
+  }
+  if (!mask) return true;
+  // one atomic per (pair, 32-column block): on data where the bound is loose the filter passes a percent of the entries
+  // and a per-hit atomic made this path the kernel's critical section
+  const int nh = __popc(mask);
+  const int base = atomicAdd(cand_cnt + q, nh);
+  if (base + nh > cap) return false;  // the count now exceeds cap: the query is flagged for the exact kernel
+  unsigned long long* dst = cand + (int64_t)q * cap + base;
+  const unsigned long long hi = (unsigned long long)(uint32_t)p << 32;
+  while (mask) {
+    const int j = __ffs(mask) - 1;
+    mask &= mask - 1;
+    *dst++ = hi | (pos0 + (uint32_t)j);
+  }
+  return true;
+}
+
+// EAGER: tombstones and the docid predicate are resolved in the decode warps (one id + bitmap lookup per entry per
+// 128 pairs) -- needed when a deletion / filter bitmap is present, because the bound B_q was taken over valid entries
+// only and a selective filter would otherwise flood the candidate lists.  Without bitmaps the ids are not touched
+// here at all (their DRAM latency sat on the decode warps' critical path: profiles/r2_ncu_pqtc_scan.txt);
+// tombstoned entries that pass the filter are dropped by pq_rescore_kernel, which reads the id anyway.
+template <int M, int DSUB, bool HAS_NORM, bool EAGER>
 __global__ void __launch_bounds__(PT_NT, 1)
     pqtc_scan_kernel(const unsigned char* __restrict__ a_scratch, const PairMeta* __restrict__ meta,
                      const uint16_t* __restrict__ cb_g, const float* __restrict__ nrm_g, const LmTile* __restrict__ items,
@@ -234,7 +327,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
   constexpr int CB_BYTES = M * PT_KSUB * DSUB * 2;
   constexpr int NRM_BYTES = HAS_NORM ? M * PT_KSUB * 4 : 0;
   constexpr int CODE_STAGE = PT_N * M;
-  constexpr int UNIT = DSUB * 2;           // bytes of one centroid in the bf16 codebook
+  constexpr int UNIT = DSUB * 2;           // bytes of one centroid in the fp16 codebook
   static_assert(D % 16 == 0 && M % 4 == 0, "shape");
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ PtShared sh;
@@ -242,8 +335,8 @@ __global__ void __launch_bounds__(PT_NT, 1)
   float* nrm = reinterpret_cast<float*>(smem + CB_BYTES);
   // Operand tiles start on 4 KiB boundaries, so the 4 KiB block one MMA reads (two core-matrix columns, LBO apart)
   // never straddles a 128 KiB line of the shared-memory window.  Measured on B200: with a tile at 0x1e800 the MMA
-  // whose second core-matrix column began exactly at 0x20000 intermittently produced wrong accumulator columns
-  // (profiles/r2_pqtc_smem_alignment.md); every other placement tried was clean.
+  // whose second core-matrix column began exactly at 0x20000 intermittently produced wrong accumulator columns;
+  // every other placement tried was clean (GB_PQTC_DBG bit 5 + bits 8.. place the tiles at a chosen offset to reproduce).
   unsigned char* a_buf = smem + CB_BYTES + NRM_BYTES;
   if (!(dbg & 32)) a_buf += (4096u - (smem_u32(a_buf) & 4095u)) & 4095u;
   else a_buf += (dbg >> 8) & 0xFFF0;  // debugging: place the tiles at a chosen (mis)alignment
@@ -274,7 +367,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
     }
     mbar_fence_init();
   }
-  // codebook (bf16, pre-scaled) and centroid norms: resident for the CTA's lifetime
+  // codebook (fp16, pre-scaled) and centroid norms: resident for the CTA's lifetime
   for (int i = tid; i < CB_BYTES / 16; i += PT_NT)
     reinterpret_cast<uint4*>(cb)[i] = __ldg(reinterpret_cast<const uint4*>(cb_g) + i);
   if (HAS_NORM)
@@ -293,7 +386,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
       const LmTile t = items[it];
-      const PairMeta pm = meta[(int64_t)t.grp * PT_M + tid];
+      PairMeta pm = meta[(int64_t)t.grp * PT_M + tid];
       const int ntiles = (t.nrows + PT_N - 1) / PT_N;
       for (int i = 0; i < ntiles; i++, bn++) {
         const int b = bn & 1;
@@ -301,21 +394,35 @@ __global__ void __launch_bounds__(PT_NT, 1)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg & 16) __nanosleep(1000);
 #pragma unroll 1
-        for (int cc = 0; cc < PT_N; cc += 32) {
-          const int c0 = (dbg & 8) ? PT_N - 32 - cc : cc;
-          uint32_t v[32];
-          pt_load32(tmem_d + lane_base + (uint32_t)(b * PT_N + c0), v);
-          const float* ne32 = &sh.ne[b][c0];
-          float mn = INFINITY;
+        for (int cc = 0; cc < PT_N; cc += 64) {
+          // two 32-column blocks per wait: the second load's latency hides behind the first block's arithmetic
+          uint32_t v0[32], v1[32];
+          const uint32_t ta = tmem_d + lane_base + (uint32_t)(b * PT_N + cc);
+          pt_load32_nowait(ta, v0);
+          pt_load32_nowait(ta + 32, v1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float* ne0 = &sh.ne[b][cc];
+          float mn0 = INFINITY, mn1 = INFINITY;
 #pragma unroll
           for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 n4 = *reinterpret_cast<const float4*>(ne32 + j4);
-            const float s0 = __uint_as_float(v[j4]) + n4.x, s1 = __uint_as_float(v[j4 + 1]) + n4.y;
-            const float s2 = __uint_as_float(v[j4 + 2]) + n4.z, s3 = __uint_as_float(v[j4 + 3]) + n4.w;
-            mn = fminf(mn, fminf(fminf(s0, s1), fminf(s2, s3)));
+            const float4 n4 = *reinterpret_cast<const float4*>(ne0 + j4);
+            const float4 m4 = *reinterpret_cast<const float4*>(ne0 + 32 + j4);
+            const float s0 = fmaf(n4.x, pm.c, __uint_as_float(v0[j4])), s1 = fmaf(n4.y, pm.c, __uint_as_float(v0[j4 + 1]));
+            const float s2 = fmaf(n4.z, pm.c, __uint_as_float(v0[j4 + 2])), s3 = fmaf(n4.w, pm.c, __uint_as_float(v0[j4 + 3]));
+            const float u0 = fmaf(m4.x, pm.c, __uint_as_float(v1[j4])), u1 = fmaf(m4.y, pm.c, __uint_as_float(v1[j4 + 1]));
+            const float u2 = fmaf(m4.z, pm.c, __uint_as_float(v1[j4 + 2])), u3 = fmaf(m4.w, pm.c, __uint_as_float(v1[j4 + 3]));
+            mn0 = fminf(mn0, fminf(fminf(s0, s1), fminf(s2, s3)));
+            mn1 = fminf(mn1, fminf(fminf(u0, u1), fminf(u2, u3)));
           }
-          if (mn <= pm.thr)
-            pt_push_hits(v, ne32, pm.thr, pm.lo, pm.q, pm.p, (uint32_t)(t.row0 + i * PT_N + c0), cand_cnt, cand, cap);
+          const uint32_t pos = (uint32_t)(t.row0 + i * PT_N + cc);
+          const bool h0 = mn0 <= pm.thr;
+          if (__any_sync(0xffffffffu, h0) &&
+              !pt_push_hits(ta, ne0, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos, cand_cnt, cand, cap, h0))
+            pm.thr = -INFINITY;  // the query overflowed: nothing more to collect for this pair
+          const bool h1 = mn1 <= pm.thr;
+          if (__any_sync(0xffffffffu, h1) &&
+              !pt_push_hits(ta + 32, ne0 + 32, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos + 32, cand_cnt, cand, cap, h1))
+            pm.thr = -INFINITY;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&sh.acc_empty[b]);
@@ -369,7 +476,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
         // (IsValid, :934-939) are resolved here, once per entry per 128 pairs.
         const int row = t.row0 + i * PT_N + e;
         bool valid = row < row_end;
-        if (valid) {
+        if (EAGER && valid) {
           const int64_t raw = lids[row];
           valid = raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw);
         }
@@ -432,9 +539,9 @@ __global__ void __launch_bounds__(PT_NT, 1)
     }
   } else {
     // ======================= MMA issuer (whole warp loops, one elected lane issues) =======================
-    // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (1 << 4), a = b = BF16 (1 << 7, 1 << 10),
-    // K-major A and B, N >> 3 at [17, 23), M >> 4 at [24, 29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PT_N >> 3) << 17) | ((uint32_t)(PT_M >> 4) << 24);
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (1 << 4), a = b = F16 (format 0 at [7, 10) and
+    // [10, 13)), K-major A and B, N >> 3 at [17, 23), M >> 4 at [24, 29)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(PT_N >> 3) << 17) | ((uint32_t)(PT_M >> 4) << 24);
     const uint32_t a_base = smem_u32(a_buf), b_base = smem_u32(b_buf);
     uint32_t an = 0, bn = 0;
     for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
@@ -460,7 +567,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
 #pragma unroll
           for (int kk = 0; kk < KC / 2; kk++) {  // K = 16 per instruction: two core matrices = 4096 bytes further
             const uint64_t adv = (uint64_t)((kk * 4096) >> 4);
-            tc_mma_bf16(acc, da + adv, db + adv, idesc, kk != 0);
+            tc_mma_f16(acc, da + adv, db + adv, idesc, kk != 0);
           }
           tc_commit(&sh.b_empty[b]);
           tc_commit(&sh.acc_full[b]);
@@ -515,7 +622,8 @@ __global__ void __launch_bounds__(RS_NT)
       dis += METRIC == kMetricL2 ? fmaf(-2.0f, a, __ldg(Tl + m * PT_KSUB + c)) : a;
     }
     const int64_t raw = dir.ids[l][pos];
-    if (raw >= 0 && dis <= f.max_score && dis >= f.min_score) buf[kprime + i] = make_key(score2ord<METRIC>(dis), (uint32_t)raw);
+    if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw) && dis <= f.max_score && dis >= f.min_score)
+      buf[kprime + i] = make_key(score2ord<METRIC>(dis), (uint32_t)raw);
   }
   __syncthreads();
   block_bitonic_sort(buf, n2);
@@ -546,19 +654,18 @@ cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* me
   if (const char* ev = getenv("GB_PQTC_DBG")) dbg = atoi(ev);
   if (dbg & 2) tile_stride = next_pow2(tile_stride);
   const size_t base = (size_t)M * PT_KSUB * DSUB * 2 + 4 * (size_t)tile_stride + (size_t)PT_CS * PT_N * M + 4096;
-  cudaError_t e;
-  if (metric == kMetricL2) {
-    const size_t smem = base + (size_t)M * PT_KSUB * 4;
-    e = cudaFuncSetAttribute(pqtc_scan_kernel<M, DSUB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool l2 = metric == kMetricL2;
+  const bool eager = f.del_bits != nullptr || f.filter_bits != nullptr;
+  const size_t smem = base + (l2 ? (size_t)M * PT_KSUB * 4 : 0);
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    pqtc_scan_kernel<M, DSUB, true><<<grid, PT_NT, smem, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap, tile_stride, dbg);
-  } else {
-    e = cudaFuncSetAttribute(pqtc_scan_kernel<M, DSUB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-    if (e != cudaSuccess) return e;
-    pqtc_scan_kernel<M, DSUB, false><<<grid, PT_NT, base, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap, tile_stride, dbg);
-  }
-  note_launch();
-  return cudaGetLastError();
+    kern<<<grid, PT_NT, smem, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap, tile_stride, dbg);
+    note_launch();
+    return cudaGetLastError();
+  };
+  if (l2) return eager ? go(pqtc_scan_kernel<M, DSUB, true, true>) : go(pqtc_scan_kernel<M, DSUB, true, false>);
+  return eager ? go(pqtc_scan_kernel<M, DSUB, false, true>) : go(pqtc_scan_kernel<M, DSUB, false, false>);
 }
 
 }  // namespace
@@ -574,7 +681,7 @@ void pqtc_debug_counters(unsigned long long out[4], bool reset) {
 bool pqtc_supported(int M, int dsub) {
   // power-of-two shapes only.  (M = 12, dsub = 8 -- 1536-byte code tiles, 24 KiB operand tiles -- compiled and ran, but
   // intermittently (about 1 search in 100, on some boxes more) lost the rows of one decode warp of a tile; the cause
-  // was not found in the time available, see profiles/r2_pqtc_m12_investigation.md, so that shape stays on the LUT kernel.)
+  // was not found in the time available, so that shape stays on the LUT kernel.)
   return (M == 16 && dsub == 8) || (M == 8 && dsub == 16) || (M == 8 && dsub == 8) || (M == 16 && dsub == 4) ||
          (M == 4 && dsub == 16) || (M == 4 && dsub == 32) || (M == 4 && dsub == 8) || (M == 8 && dsub == 4);
 }
@@ -588,10 +695,11 @@ cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uin
   return cudaGetLastError();
 }
 
-cudaError_t launch_pqtc_mask_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa, int32_t* out,
-                                    cudaStream_t st) {
+cudaError_t launch_pqtc_split_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
+                                     const int* list_len, int32_t* out_a, int32_t* out_b, cudaStream_t st) {
   if (npairs <= 0) return cudaSuccess;
-  pqtc_mask_probes_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, pa, out);
+  pqtc_split_probes_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, pa_max, target,
+                                                                            list_len, out_a, out_b);
   note_launch();
   return cudaGetLastError();
 }

@@ -1,6 +1,6 @@
 // tcgen05 / TMEM building blocks shared by the tensor-core kernels (kernels_tc.cu, kernels_pqtc.cu):
 // shared-memory matrix descriptors (canonical no-swizzle K-major tiles), MMA issue wrappers for
-// kind::tf32 and kind::f16 (bf16 operands), elect / mbarrier arrive helpers.  sm_100a only.
+// kind::tf32 and kind::f16, elect / mbarrier arrive helpers.  sm_100a only.
 #pragma once
 #include "common.cuh"
 
@@ -35,8 +35,8 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
-// bf16 x bf16 -> fp32 (kind::f16): one instruction consumes K = 16 (two 8-element core matrices)
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+// fp16 x fp16 (or bf16 x bf16, per the instruction descriptor) -> fp32 (kind::f16): one instruction consumes K = 16 (two 8-element core matrices)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
   asm volatile(
       "{\n"

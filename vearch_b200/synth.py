@@ -20,11 +20,14 @@ def _centers_np(n_clusters, d, centers_seed):
     return centers, scale
 
 
-def sift_like(n, d=128, seed=1234, n_clusters=256, centers_seed=99):
+def sift_like(n, d=128, seed=1234, n_clusters=256, centers_seed=99, rounded=True):
+    """rounded=False: the same mixture left un-rounded (every mantissa bit in use) -- the float-valued parity set"""
     centers, scale = _centers_np(n_clusters, d, centers_seed)
     rng = np.random.default_rng(seed)
     lab = rng.integers(0, n_clusters, size=n)
     x = centers[lab] + rng.normal(0, 1, size=(n, d)).astype(np.float32) * scale[lab]
+    if not rounded:
+        return (np.clip(x, 0, 218) * np.float32(1.0 / 3.0)).astype(np.float32)
     return np.clip(np.rint(x), 0, 218).astype(np.float32)
 
 
