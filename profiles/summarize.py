@@ -94,5 +94,52 @@ def traffic(out_path):
     print(out)
 
 
+def ncu_json(out_path):
+    """profiles/r2_ncu.json: per bench workload, per dominant kernel, the counters of the committed ncu --set full
+    summaries that bench.py copies into roofline.traffic / roofline.secondary.
+        python profiles/summarize.py ncu_json profiles/r2_ncu.json"""
+    import json
+    import os
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+
+    def read(name, work_units=None):
+        t = open(os.path.join(here, name)).read()
+
+        def num(key):
+            m = re.search(re.escape(key) + r"\s+([0-9.]+)\s*(\w*)", t)
+            return (float(m.group(1)), m.group(2)) if m else (None, "")
+
+        dram = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = num(key)
+            dram += v * scale.get(u, 1.0)
+        inst = num("smsp__inst_executed.sum")[0]
+        wav, conf = num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")[0], num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")[0]
+        dur, du = num("gpu__time_duration.sum")
+        out = {"source": name, "dram_bytes": dram, "kernel_ms_under_ncu": dur * {"ms": 1.0, "us": 1e-3, "s": 1e3}.get(du, 1.0),
+               "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active")[0],
+               "lsu_pipe_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active")[0],
+               "tensor_pipe_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")[0],
+               "l2_hit_pct": num("lts__t_sector_hit_rate.pct")[0],
+               "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active")[0],
+               "shared_wavefronts": wav, "lds_bank_conflict_pct": 100.0 * conf / wav if wav else None,
+               "warp_instructions": inst}
+        if work_units:
+            out["inst_per_entry"] = inst * 32.0 / work_units[0]
+            out["inst_per_entry_unit"] = work_units[1]
+        return out
+
+    out = {"_comment": "counters per launch from the ncu --set full captures summarised in this directory; keyed by bench "
+                       "workload, then by the kernel the bench timed (a capture only speaks for its own workload)",
+           "ivfpq_10m": {"pqtc_scan_kernel": read("r2_ncu_pqtc_scan.txt", (3.939e9, "thread instructions per (query, entry) pair filtered")),
+                         "ivfpq_scan_kernel": read("r1_ncu_ivfpq_scan.txt", (3.98e9, "thread instructions per scanned code"))},
+           "ivfflat_1m": {"ivf_listmajor_tma_kernel": read("r1_ncu_ivfflat_listmajor.txt"),
+                          "ivfflat_scan_warp_kernel": read("r1_ncu_ivfflat_scan_querymajor.txt")}}
+    json.dump(out, open(out_path, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic, "ncu_json": ncu_json}[sys.argv[1]](sys.argv[2])

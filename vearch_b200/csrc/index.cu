@@ -1283,12 +1283,9 @@ int IVFFlatIndex::coarse_dev(int nq, const float* xq, int nprobe, int metric, in
 // score segment of len(list) floats, cut (list, 128 pairs, 128 rows) tiles; device side: grouped
 // GEMM on tcgen05 + segment select.
 // GB_LISTMAJOR: 0 = off, 1 = on (fused top-k epilogue when k allows), 2 = on, always the dense-score variant
-static int listmajor_mode() {
-  static int v = [] {
-    const char* e = getenv("GB_LISTMAJOR");
-    return e ? atoi(e) : 1;
-  }();
-  return v;
+static int listmajor_mode() {  // read per call: tests flip it between searches of one process
+  const char* e = getenv("GB_LISTMAJOR");
+  return e ? atoi(e) : 1;
 }
 static bool listmajor_enabled() { return listmajor_mode() != 0; }
 static bool tma_enabled() {  // GB_TC_MIRROR=0: never build the pre-tiled mirror (register-staged kernel)

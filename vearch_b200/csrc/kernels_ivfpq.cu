@@ -304,26 +304,49 @@ __global__ void __launch_bounds__(RR_NT)
   __syncthreads();
   const float4* q4 = reinterpret_cast<const float4*>(qs);
   const uint32_t seg_mask = (1u << seg_shift) - 1u;
-  for (int j = warp; j < ncand; j += RR_NT / 32) {
-    unsigned long long ck = cand_keys[(int64_t)q * ncand + j];
-    if (ck == kKeySentinel) continue;  // recall_idxi[j] < 0 (ivfpq.cc:691)
-    uint32_t vid = (uint32_t)ck;
-    const float4* row =
-        reinterpret_cast<const float4*>(raw_segments[vid >> seg_shift] + (int64_t)(vid & seg_mask) * ld_raw);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  // four candidates per warp iteration: 2 KiB of independent row loads in flight per warp (the gather is pure HBM
+  // latency: recall_num random 4d-byte rows per query)
+  constexpr int RR_U = 4;
+  for (int j0 = warp * RR_U; j0 < ncand; j0 += (RR_NT / 32) * RR_U) {
+    uint32_t vid[RR_U];
+    const float4* row[RR_U];
+    bool live[RR_U];
+#pragma unroll
+    for (int u = 0; u < RR_U; u++) {
+      const int j = j0 + u;
+      const unsigned long long ck = j < ncand ? cand_keys[(int64_t)q * ncand + j] : kKeySentinel;
+      live[u] = ck != kKeySentinel;  // recall_idxi[j] < 0 (ivfpq.cc:691)
+      vid[u] = live[u] ? (uint32_t)ck : 0u;
+      row[u] = live[u] ? reinterpret_cast<const float4*>(raw_segments[vid[u] >> seg_shift] + (int64_t)(vid[u] & seg_mask) * ld_raw)
+                       : nullptr;
+    }
+    float acc[RR_U][4];
+#pragma unroll
+    for (int u = 0; u < RR_U; u++) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
     for (int c = lane; c < (d >> 2); c += 32) {
-      float4 v = __ldg(row + c), w = q4[c];
-      if (metric == kMetricL2) {
-        float t0 = v.x - w.x, t1 = v.y - w.y, t2 = v.z - w.z, t3 = v.w - w.w;
-        a0 = fmaf(t0, t0, a0), a1 = fmaf(t1, t1, a1), a2 = fmaf(t2, t2, a2), a3 = fmaf(t3, t3, a3);
-      } else {
-        a0 = fmaf(v.x, w.x, a0), a1 = fmaf(v.y, w.y, a1), a2 = fmaf(v.z, w.z, a2), a3 = fmaf(v.w, w.w, a3);
+      const float4 w = q4[c];
+      float4 v[RR_U];
+#pragma unroll
+      for (int u = 0; u < RR_U; u++) v[u] = live[u] ? __ldg(row[u] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < RR_U; u++) {
+        if (metric == kMetricL2) {
+          const float t0 = v[u].x - w.x, t1 = v[u].y - w.y, t2 = v[u].z - w.z, t3 = v[u].w - w.w;
+          acc[u][0] = fmaf(t0, t0, acc[u][0]), acc[u][1] = fmaf(t1, t1, acc[u][1]);
+          acc[u][2] = fmaf(t2, t2, acc[u][2]), acc[u][3] = fmaf(t3, t3, acc[u][3]);
+        } else {
+          acc[u][0] = fmaf(v[u].x, w.x, acc[u][0]), acc[u][1] = fmaf(v[u].y, w.y, acc[u][1]);
+          acc[u][2] = fmaf(v[u].z, w.z, acc[u][2]), acc[u][3] = fmaf(v[u].w, w.w, acc[u][3]);
+        }
       }
     }
-    float dis = (a0 + a1) + (a2 + a3);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) dis += __shfl_xor_sync(0xffffffffu, dis, off);
-    if (lane == 0 && dis <= f.max_score && dis >= f.min_score) buf[j] = make_key(score2ord(dis, metric), vid);
+    for (int u = 0; u < RR_U; u++) {
+      float dis = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) dis += __shfl_xor_sync(0xffffffffu, dis, off);
+      if (lane == 0 && live[u] && dis <= f.max_score && dis >= f.min_score) buf[j0 + u] = make_key(score2ord(dis, metric), vid[u]);
+    }
   }
   __syncthreads();
   block_bitonic_sort(buf, NP);
@@ -453,7 +476,7 @@ cudaError_t launch_rerank(const unsigned long long* cand_keys, int ncand, int nq
                           FilterArgs f, unsigned long long* out_keys, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   if (ncand <= 0 || ncand > 8192 || (d & 3)) return cudaErrorInvalidValue;
-  int NP = next_pow2(ncand);
+  int NP = next_pow2(ncand < 2 ? 2 : ncand);  // >= 16 bytes of keys: the query row behind them is read as float4
   size_t smem = (size_t)NP * 8 + (size_t)d * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -601,8 +601,18 @@ __global__ void __launch_bounds__(RS_NT)
   const int q = blockIdx.x, tid = threadIdx.x;
   const int cnt = cand_cnt[q];
   if (cnt > cap) return;  // overflow: the exact kernel redoes this query (pq_fallback_merge_kernel writes out)
-  const float4* ipq4 = reinterpret_cast<const float4*>(ip_table + (int64_t)q * M * PT_KSUB);
-  for (int i = tid; i < M * PT_KSUB / 4; i += RS_NT) reinterpret_cast<float4*>(ips)[i] = __ldg(ipq4 + i);
+  if (cnt == 0) {  // nothing passed the filter: phase A's keys are the answer (common when the bound is tight)
+    for (int i = tid; i < kprime; i += RS_NT) out[(int64_t)q * kprime + i] = keys_a[(int64_t)q * keys_a_stride + i];
+    return;
+  }
+  // a handful of candidates (the usual case) read the query's inner-product table straight from L2; staging the
+  // 4 M bytes-per-sub-quantiser table in shared memory pays only for long candidate lists
+  const float* ipq = ip_table + (int64_t)q * M * PT_KSUB;
+  const bool staged = cnt > 64;
+  if (staged) {
+    const float4* ipq4 = reinterpret_cast<const float4*>(ipq);
+    for (int i = tid; i < M * PT_KSUB / 4; i += RS_NT) reinterpret_cast<float4*>(ips)[i] = __ldg(ipq4 + i);
+  }
   int n2 = 16;
   while (n2 < kprime + cnt) n2 <<= 1;  // <= NP
   for (int i = tid; i < n2; i += RS_NT) buf[i] = i < kprime ? keys_a[(int64_t)q * keys_a_stride + i] : kKeySentinel;
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(RS_NT)
     // the reference's order: dis = dis0; dis += tab[m][code[m]], tab = T - 2 ip as ivfpq_scan_kernel builds it
     for (int m = 0; m < M; m++) {
       const int c = code[m];
-      const float a = ips[m * PT_KSUB + c];
+      const float a = staged ? ips[m * PT_KSUB + c] : __ldg(ipq + m * PT_KSUB + c);
       dis += METRIC == kMetricL2 ? fmaf(-2.0f, a, __ldg(Tl + m * PT_KSUB + c)) : a;
     }
     const int64_t raw = dir.ids[l][pos];
