@@ -21,10 +21,12 @@ nlist=4096 N=10M nq=10k (BASELINE.json configs[2]); other configs via --workload
 Multi-GPU (N > 1), one Vearch partition per rank/GPU; every query goes to every partition; the per-rank
 result keys are all-gathered over NCCL (one collective) and merged on device in the router's order
 (internal/client/client.go:1530-1609).
-  --scaling weak   (default) a fixed partition per GPU: 10M vectors each (12.5M at N=8 = BASELINE configs[4],
-                   100M vectors over 8 partitions); the database grows with N, ideal = constant global queries/s.
-                   `partition_queries_per_s` (= value x N) and `scan_entries_per_s` are the aggregate-work figures.
+  --scaling weak   (default) a fixed partition per GPU (10M vectors each); the database grows with N, ideal = constant
+                   global queries/s.  `partition_queries_per_s` (= value x N) and `scan_entries_per_s` are the
+                   aggregate-work figures.
   --scaling strong a fixed database (--n-total, default the workload's N) split over the ranks.
+The default run also carries, under `secondary`, BASELINE configs[4] measured the strong way at the same N: the 100M-vector
+IVF-PQ database split over the N ranks (N=1 holds it all, N=8 holds 12.5M per GPU), plus C1/C2/C4 at N=1.
 """
 import argparse
 import json
@@ -53,7 +55,7 @@ WORKLOADS = {
                        nq=10_000, scaling="strong",
                        desc="IVF-PQ d=128 N=100M split over the ranks' partitions (BASELINE configs[4])"),
 }
-CONFIGS4_PER_GPU = 12_500_000  # BASELINE configs[4]: 100M vectors over 8 partitions
+CONFIGS4_TOTAL = 100_000_000  # BASELINE configs[4]: 100M vectors over the ranks' partitions (12.5M per GPU at N=8)
 
 
 def parse_args():
@@ -261,8 +263,8 @@ def make_roofline(idx, wl, wl_name, work, nq, k, recall_num, scan_ms, ms_per_ste
         if key in ncu:
             secondary[key] = ncu[key]
     if kname == "pqtc_scan_kernel":
-        # entries the tensor-core filter multiplies: probes [phase_a_probes, nprobe) of every query
-        # (index.cu scan_listmajor_pq: phase A = the fewest leading probes with >= target entries, at most pa_max)
+        # entries the tensor-core filter multiplies: the probes behind each query's phase A (index.cu scan_listmajor_pq:
+        # phase A = the fewest leading probes, in full, whose lists hold >= target entries, at most pa_max)
         pa_max, target = int(info.get("phase_a_max_probes", 1)), int(info.get("phase_a_target_entries", -1))
         keys, lens = work["_keys"], work["_lens"]
         ll = np.where(keys >= 0, lens[np.maximum(keys, 0)], 0)
@@ -273,7 +275,7 @@ def make_roofline(idx, wl, wl_name, work, nq, k, recall_num, scan_ms, ms_per_ste
             pa_q = np.full(keys.shape[0], pa_max)
         in_b = np.arange(keys.shape[1])[None, :] >= pa_q[:, None]
         ent_tc = float(ll[in_b].sum())
-        info = dict(info, phase_a_probes_mean=float(pa_q.mean()))
+        info = dict(info, phase_a_probes_mean=float(pa_q.mean()), phase_a_entries_scanned=float(ll[~in_b].sum()))
         aflops = ent_tc * 2.0 * wl["d"]
         ach = aflops / sec / 1e12 if sec else None
         r.update({"bound": "tensor", "achieved": ach, "peak": tc_peak, "unit": "TFLOP/s", "frac": ach / tc_peak if ach else None,
@@ -607,10 +609,7 @@ def main():
         n_total_cfg = args.n_total or wl["n"]
         n_rank = args.n or n_total_cfg // nparts
     else:
-        n_rank = args.n or wl["n"]
-        if wl_name == "ivfpq_10m" and nparts == 8 and not args.n:
-            n_rank = CONFIGS4_PER_GPU
-            desc_wl["desc"] = "IVF-PQ d=128 N=100M sharded across 8 partitions on 8 GPUs (BASELINE configs[4]), 12.5M per GPU"
+        n_rank = args.n or wl["n"]  # the same partition per GPU at every N: per-GPU work is fixed, ideal = constant queries/s
     wl = desc_wl
 
     # =============================================================================================
@@ -626,8 +625,19 @@ def main():
     res = measure(args, wl_name, wl, n_rank, rank, world, local, use_dist, family, args.steps, args.warmup, primary=True)
     if res is None:
         return 0
+    default_shape = not (args.n or args.nq or args.nprobe or args.dataset or args.n_total)
+    want_c5 = wl_name == "ivfpq_10m" and default_shape and not args.no_secondary and scaling == "weak"
     if rank != 0:
         res["idx"].close()
+        del res
+        if want_c5:  # every rank holds its share of the 100M database
+            try:
+                torch.cuda.empty_cache()
+                w5 = WORKLOADS["ivfpq_100m"]
+                r5 = measure(args, "ivfpq_100m", w5, CONFIGS4_TOTAL // world, rank, world, local, use_dist, w5["data"], 3, 3, primary=False)
+                r5["idx"].close()
+            except Exception as e:
+                print(f"rank {rank}: configs[4] secondary failed: {e!r}", file=sys.stderr)
         if use_dist:
             dist.barrier()
             dist.destroy_process_group()
@@ -636,7 +646,6 @@ def main():
     idx, nq, k, nprobe, recall_num = res["idx"], res["nq"], res["k"], res["nprobe"], res["recall_num"]
     ms_per_step = res["ms_per_step"]
     value = nq / (ms_per_step / 1000)  # global queries/s on the world-partition database
-    default_shape = not (args.n or args.nq or args.nprobe or args.dataset or args.n_total)
     roofline = make_roofline(idx, wl, wl_name, res["work"], nq, k, recall_num, res["scan_avg"], ms_per_step, default_shape)
 
     # ---- CPU baseline on this box's host cores (bounded sample) ---------------------------------
@@ -681,9 +690,28 @@ def main():
     idx.close()
     del res
 
+    sec = []
+    # ---- BASELINE configs[4], strong scaling: the 100M database split over this run's ranks ----
+    if want_c5:
+        try:
+            torch.cuda.empty_cache()
+            w5 = WORKLOADS["ivfpq_100m"]
+            r5 = measure(args, "ivfpq_100m", w5, CONFIGS4_TOTAL // world, rank, world, local, use_dist, w5["data"], 3, 3, primary=False)
+            v5 = r5["nq"] / (r5["ms_per_step"] / 1000)
+            pr = r5["per_rank"]
+            sec.append({"workload": w5["desc"], "scaling": "strong", "metric": metric_string(w5, r5["n_total"], r5["nq"]),
+                        "n_gpus": world, "n_per_gpu": CONFIGS4_TOTAL // world, "n_total": r5["n_total"], "value": v5,
+                        "unit": "queries/s", "ms_per_step": r5["ms_per_step"], "steps": 3, "warmup": 3, "e2e_value": r5["cabi_qps"] or r5["e2e_qps"],
+                        "recall@10_1nn": r5["r1"], "recall@10": r5["r10"], "nprobe": r5["nprobe"], "recall_num": r5["recall_num"],
+                        "gpu_launches": r5["launches"], "stages_ms": r5["stages"],
+                        "per_rank_scan_kernel_ms_min_max": [float(pr[:, 1].min()), float(pr[:, 1].max())],
+                        "build_seconds": r5["build"]})
+            r5["idx"].close()
+            del r5
+        except Exception as e:
+            sec.append({"workload": "ivfpq_100m", "error": repr(e)[:300]})
     # ---- quick lines for the other single-GPU BASELINE configs (driver-run record of C1 / C2 / C4) ----
     if world == 1 and wl_name == "ivfpq_10m" and default_shape and not args.no_secondary:
-        sec = []
         for name in ("flat_100k", "ivfflat_1m", "ivfflat_768"):
             try:
                 w2 = WORKLOADS[name]
@@ -701,6 +729,7 @@ def main():
                 del r2
             except Exception as e:  # a secondary line must never take the primary one down
                 sec.append({"workload": name, "error": repr(e)[:300]})
+    if sec:
         line["secondary"] = sec
 
     print(json.dumps(line))

@@ -244,6 +244,42 @@ def test_kill_switch_and_config(tmp_path, data):
     e.close()
 
 
+def test_reference_written_flatbuffers_drive_the_engine(tmp_path):
+    """Boundary pin: gamma_api.Table / gamma_api.Doc buffers written by the REFERENCE's own flatc-generated
+    builders (tests/golden/make_fb_golden.cc, compiled against /root/reference's vendored flatbuffers + idl/fbs-gen/c) go
+    through CreateTable / AddOrUpdateDoc / GetDocByID / Search exactly as the Go partition server would send them --
+    including the Go SDK's habit of writing `value` with CreateString (sdk/go/gamma/doc.go:28-42)."""
+    import json as _json
+    import os
+    E = eng_mod()
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fb")
+    meta = _json.load(open(os.path.join(gold, "official.json")))
+    e = E.GammaEngine(str(tmp_path / "fbref"), space_name="ts_space")
+    e.create_table_raw(open(os.path.join(gold, "table_official_full.fb"), "rb").read(), "emb", 64)
+    # a second CreateTable must be refused like the reference does (engine.cc: "table is created")
+    with pytest.raises(E.GammaStatusError):
+        e.create_table_raw(open(os.path.join(gold, "table_official_minimal.fb"), "rb").read(), "emb", 64)
+    exp = {f["name"]: bytes.fromhex(f["value_hex"]) for f in meta["doc_official_bytes.fb"]["fields"]}
+    assert e.add_doc_raw(open(os.path.join(gold, "doc_official_bytes.fb"), "rb").read()) == 0
+    assert e.status()["doc_num"] == 1
+    # the same document again, `value` written as a flatbuffers string: an update of the same _id, not a second doc
+    assert e.add_doc_raw(open(os.path.join(gold, "doc_official_gostring.fb"), "rb").read()) == 0
+    assert e.status()["doc_num"] == 1
+    rc, doc = e.get_doc_by_id("doc-00042")
+    assert rc == 0
+    for name in ("_id", "price", "tag", "emb", "img"):
+        assert doc[name][0] == exp[name], name
+    emb = np.frombuffer(exp["emb"], np.float32)
+    res = e.search(emb[None, :], 1, is_brute_search=1)
+    assert res[0]["items"][0]["fields"]["_id"] == b"doc-00042" and res[0]["items"][0]["score"] == 0.0
+    # the second vector field of the table (FLAT, inner product) is searchable too
+    img = np.frombuffer(exp["img"], np.float32)
+    req = wire.encode_search_request("img", img[None, :], 1, is_brute_search=1)
+    r2 = wire.decode_search_response(e.search_raw(req))
+    assert r2[0]["items"][0]["fields"]["_id"] == b"doc-00042" and abs(r2[0]["items"][0]["score"] - float(img @ img)) < 1e-3
+    e.close()
+
+
 def test_admission_control_refuses_with_resource_exhausted(tmp_path, data):
     """RequestConcurrentController (search/engine.cc:47-119, :252-260): a Search arriving while the in-flight request
     count is at the threshold fails with Status::ResourceExhausted() = code kBusy (6), "Resource busy: Resource

@@ -1953,34 +1953,39 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
                                   unsigned long long* adc_out, Scratch& s) {
   const int mode = pqtc_mode();
   if (!mode || !tc_enabled() || !d_cb16_ || !pqtc_supported(M_, dsub_) || dpad_ != d_) return 1;
-  if (kk > 2048 || nprobe < 2) return 1;
+  if (kk > 2048 || nprobe < 2 || nprobe > 65535 || nq > 65535) return 1;  // (query, probe) travel as 16-bit fields of a candidate record
   const int64_t npairs = (int64_t)nq * nprobe;
   if (mode != 2 && npairs < (int64_t)nlist_ * 32) return 1;  // < 32 queries per list on average
   cudaStream_t st = s.stream();
   ListDirectory dir = lists_->directory();
-  // phase A depth, per query: the fewest leading probes whose lists hold >= 4 k' entries together (so that its k'-th
-  // exact score is a usable bound), at most pa_max.  GB_PQTC_PA=n fixes the depth at n probes for every query.
+  // phase A, per query: its first probes in full -- the fewest whose lists hold >= 4 k' entries together (so that its
+  // k'-th exact score is a tight bound B_q), at most pa_max; phase B filters the other probes.  GB_PQTC_PA=n: the
+  // first n probes of every query; GB_PQTC_TARGET=t: t k' entries instead of 4 k'.
   int pa_max = std::min(nprobe - 1, 8);
   long long pa_target = 4 * (long long)kk;
   if (const char* e = getenv("GB_PQTC_PA")) {
     pa_max = std::max(1, std::min(nprobe - 1, atoi(e)));
     pa_target = LLONG_MAX;
   }
+  if (const char* e = getenv("GB_PQTC_TARGET")) pa_target = std::max(1LL, atoll(e)) * kk;
   const int cap = std::max(2048, std::min(8192, next_pow2(8 * kk)));
   const int nsm = sm_count(device_);
   snprintf(last_scan_info_, sizeof(last_scan_info_),
            "{\"phase_a_max_probes\": %d, \"phase_a_target_entries\": %lld, \"candidate_cap\": %d, \"kprime\": %d}", pa_max,
            pa_target == LLONG_MAX ? -1LL : pa_target, cap, kk);
   GB_ALLOC(d_probes_a, int32_t, npairs, s);
-  GB_ALLOC(d_masked, int32_t, npairs, s);
-  GB_CUDA(launch_pqtc_split_probes(probe_ids, npairs, nprobe, pa_max, pa_target, dir.len, d_probes_a, d_masked, st));
+  GB_ALLOC(d_probes_b, int32_t, npairs, s);
+  GB_ALLOC(d_row_limit, int, npairs, s);
+  GB_CUDA(launch_pqtc_plan_phase_a(probe_ids, npairs, nprobe, pa_max, pa_target, dir.len, d_probes_a, d_probes_b, d_row_limit,
+                                   st));
 
   // ---- phase A: exact keys of each query's leading probes ----
   const int pgA = nq >= nsm * 4 ? std::min(pa_max, 32) : 1;  // one CTA per query when there are queries enough
   const int ngA = (pa_max + pgA - 1) / pgA;
   GB_ALLOC(partA, unsigned long long, (size_t)nq * ngA * kk, s);
   stage_begin("pq_phaseA_exact_scan", st);
-  GB_CUDA(launch_ivfpq_scan(ip, nq, d_probes_a, coarse_dis, pa_max, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe));
+  GB_CUDA(launch_ivfpq_scan(ip, nq, d_probes_a, coarse_dis, pa_max, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe,
+                            nullptr, 0, d_row_limit));
   unsigned long long* keysA = partA;
   if (ngA > 1) {
     keysA = s.alloc_n<unsigned long long>((size_t)nq * kk);
@@ -2016,11 +2021,11 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(big + a_bytes + meta_bytes);
   stage_begin("pq_group_and_stage_pairs", st);
   GB_CUDA(cudaMemsetAsync(d_cand_cnt, 0, sizeof(int) * nq, st));
-  GB_CUDA(launch_lmk_group(d_masked, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
+  GB_CUDA(launch_lmk_group(d_probes_b, npairs, dir, nseg, d_cnt, d_start, d_cursor, d_item_start, d_grp_start, d_totals,
                            d_pair_j, d_items, st));
   GB_CUDA(launch_pq_stage_pairs(xq, dpad_, d_, d_centroids_, dpad_, d_items, (int)max_items, d_totals, d_pair_j, nprobe,
                                 coarse_dis, keysA, kk, kk, d_cbnrm_ + (size_t)M_ * 256, f, metric, pqtc_eps_scale(), a_scratch,
-                                meta, d_cand_cnt, cap, st));
+                                meta, d_cand_cnt, cap, d_row_limit, st));
   stage_end(st);
   scan_timer_begin(st);  // the dominant kernel: the roofline in bench.py is this launch alone
   stage_begin("pqtc_scan_kernel", st);
@@ -2032,7 +2037,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
 
   // ---- phase C: candidates -> reference arithmetic, merged with phase A's keys ----
   GB_CUDA(launch_pq_rescore(ip, nq, probe_ids, coarse_dis, nprobe, dir, M_, d_table_, d_cand_cnt, cand, cap, keysA, kk, kk,
-                            metric, f, adc_out, st));
+                            metric, d_row_limit, f, adc_out, st));
   // queries whose candidate list overflowed (or that had no bound): exact kernel over all probes, flag-gated
   const int ngF = (nprobe + 31) / 32;
   GB_ALLOC(partF, unsigned long long, (size_t)nq * ngF * kk, s);

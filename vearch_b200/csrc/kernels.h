@@ -151,7 +151,7 @@ cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nli
 cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis,
                               int nprobe, int pg, ListDirectory dir, int M, const float* T, int k, int metric,
                               FilterArgs f, unsigned long long* partial, cudaStream_t st, int ld_probe = 0,
-                              const int* gate_cnt = nullptr, int gate_cap = 0);
+                              const int* gate_cnt = nullptr, int gate_cap = 0, const int* row_limit = nullptr);
 
 // ---- K5 list-major: tensor-core filter + exact re-score (kernels_pqtc.cu) ---------------------------
 bool pqtc_supported(int M, int dsub);
@@ -160,17 +160,18 @@ size_t pqtc_pair_meta_bytes();
 // cb[m][c][.] = bf16(-2 pq) (L2) / bf16(-pq) (IP); nrm[m][c] = |pq[m][c]|^2; rmax2[0] = sum_m max_c nrm
 cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uint16_t* cb, float* nrm, float* rmax2,
                                cudaStream_t st);
-// per query: phase A = its first P_q probes (fewest with >= target entries together, at most pa_max), phase B = the
-// rest; out_a / out_b = probe_ids with the other phase's probes set to -1
-cudaError_t launch_pqtc_split_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
-                                     const int* list_len, int32_t* out_a, int32_t* out_b, cudaStream_t st);
+// phase A's plan: per query its first P_q probes in full (fewest with >= target entries together, at most pa_max);
+// probes_a / probes_b = probe_ids with the other phase's probes set to -1, row_limit[q][p] = rows phase A scores exactly
+cudaError_t launch_pqtc_plan_phase_a(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
+                                     const int* list_len, int32_t* probes_a, int32_t* probes_b, int* row_limit,
+                                     cudaStream_t st);
 // per pair group: bf16 operand tile of (x - centroid) (L2) / x (IP) rows + the pairs' filter thresholds from
 // bound_keys[q][kprime - 1] (phase A's k'-th key); queries without a bound get cand_cnt = cap + 1
 cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const float* coarse, int64_t ldc, const LmTile* items,
                                   int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
                                   const float* coarse_dis, const unsigned long long* bound_keys, int64_t bound_stride,
                                   int kprime, const float* rmax2, FilterArgs f, int metric, float eps_scale,
-                                  unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, cudaStream_t st);
+                                  unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, const int* row_limit, cudaStream_t st);
 // persistent kernel, one CTA per SM: candidates (probe << 32 | position) appended to cand[q][cap]
 cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* nrm,
                              const LmTile* items, int max_items, const int64_t* totals, ListDirectory dir, int M, int dsub,
@@ -180,7 +181,7 @@ cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, c
 cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                               ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,
                               int cap, const unsigned long long* keys_a, int64_t keys_a_stride, int kprime, int metric,
-                              FilterArgs f, unsigned long long* out, cudaStream_t st);
+                              const int* row_limit, FilterArgs f, unsigned long long* out, cudaStream_t st);
 // queries with cand_cnt > cap: out[q] = best kprime of partial[q][ngroups][kprime]
 cudaError_t launch_pq_fallback_merge(const int* cand_cnt, int cap, int nq, const unsigned long long* partial, int ngroups,
                                      int kprime, unsigned long long* out, cudaStream_t st);

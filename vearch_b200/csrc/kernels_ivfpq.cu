@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(PQ_NT)
     ivfpq_scan_kernel(const float* __restrict__ ip_table, const int32_t* __restrict__ probe_ids,
                       const float* __restrict__ coarse_dis, int nprobe, int ld_probe, int pg, ListDirectory dir, int M,
                       const float* __restrict__ T, int tile_e, int k, int KP, int SORTN, FilterArgs f,
-                      const int* __restrict__ gate_cnt, int gate_cap, unsigned long long* __restrict__ partial) {
+                      const int* __restrict__ gate_cnt, int gate_cap, const int* __restrict__ row_limit,
+                      unsigned long long* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tile_bytes = tile_e * M;
   // the LUT sits at the start of the dynamic window: its shared address is a link-time constant, so
@@ -162,6 +163,8 @@ __global__ void __launch_bounds__(PQ_NT)
     for (int i = 0; i < np; i++) {
       int l = probe_ids[(int64_t)q * ld_probe + p0 + i];
       int len = (l >= 0 && l < dir.nlist) ? dir.len[l] : 0;  // key < 0: "not enough centroids" (ivfpq.cc:640)
+      // phase A of the tensor-core filter scans only a prefix of its lists (kernels_pqtc.cu)
+      if (row_limit) len = min(len, row_limit[(int64_t)q * ld_probe + p0 + i]);
       g_list[i] = l;
       g_len[i] = len;
       g_dis0[i] = coarse_dis[(int64_t)q * ld_probe + p0 + i];
@@ -399,7 +402,7 @@ void pq_cq_geometry(int k, int tile_e, int* KP, int* SORTN) {
 template <int METRIC, int MW>
 cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                           int ld_probe, int pg, ListDirectory dir, int M, const float* T, int k, FilterArgs f,
-                          const int* gate_cnt, int gate_cap, unsigned long long* partial, cudaStream_t st) {
+                          const int* gate_cnt, int gate_cap, const int* row_limit, unsigned long long* partial, cudaStream_t st) {
   int tile_e = pq_tile_entries(M);
   int KP, SORTN;
   pq_cq_geometry(k, tile_e, &KP, &SORTN);
@@ -411,7 +414,7 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
   int ngroups = (nprobe + pg - 1) / pg;
   dim3 grid(ngroups, nq);
   ivfpq_scan_kernel<METRIC, MW><<<grid, PQ_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T,
-                                                          tile_e, k, KP, SORTN, f, gate_cnt, gate_cap, partial);
+                                                          tile_e, k, KP, SORTN, f, gate_cnt, gate_cap, row_limit, partial);
                                                           note_launch();
   return cudaGetLastError();
 }
@@ -419,10 +422,10 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
 template <int METRIC>
 cudaError_t launch_scan_m(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                           int ld_probe, int pg, ListDirectory dir, int M, const float* T, int k, FilterArgs f,
-                          const int* gate_cnt, int gate_cap, unsigned long long* partial, cudaStream_t st) {
+                          const int* gate_cnt, int gate_cap, const int* row_limit, unsigned long long* partial, cudaStream_t st) {
 #define GB_SCAN(MW) \
   return launch_scan_t<METRIC, MW>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, \
-                                   gate_cap, partial, st)
+                                   gate_cap, row_limit, partial, st)
   switch (M) {
     case 8: GB_SCAN(2);
     case 16: GB_SCAN(4);
@@ -460,15 +463,15 @@ cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nli
 cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis,
                               int nprobe, int pg, ListDirectory dir, int M, const float* T, int k, int metric,
                               FilterArgs f, unsigned long long* partial, cudaStream_t st, int ld_probe,
-                              const int* gate_cnt, int gate_cap) {
+                              const int* gate_cnt, int gate_cap, const int* row_limit) {
   if (nq <= 0 || nprobe <= 0) return cudaSuccess;
   if (ld_probe <= 0) ld_probe = nprobe;
   if (k <= 0 || k > 4096 || nq > 65535 || pg < 1 || pg > PQ_MAX_PG) return cudaErrorInvalidValue;
   if (metric == kMetricL2) {
     if (!T) return cudaErrorInvalidValue;
-    return launch_scan_m<kMetricL2>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, partial, st);
+    return launch_scan_m<kMetricL2>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, partial, st);
   }
-  return launch_scan_m<kMetricIP>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, partial, st);
+  return launch_scan_m<kMetricIP>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, partial, st);
 }
 
 cudaError_t launch_rerank(const unsigned long long* cand_keys, int ncand, int nq, const float* xq, int64_t ldq, int d,

@@ -50,7 +50,9 @@ namespace {
 
 constexpr int PT_M = 128;          // pairs per group  (MMA M, TMEM lanes)
 constexpr int PT_N = 128;          // entries per tile (MMA N, accumulator columns)
-constexpr int PT_NT = 320;         // warps 0-3 epilogue, 4-7 decode, 8 TMA producer, 9 MMA issuer
+constexpr int PT_NT = 352;         // warps 0-3 epilogue, 4-7 decode, 8 TMA producer, 9 MMA issuer, 10 candidate drain
+constexpr int PT_RQ = 512;         // records of the CTA's candidate queue (shared memory)
+constexpr unsigned long long kRecEmpty = ~0ull;
 constexpr int PT_CS = 4;           // code stages
 constexpr int PT_KSUB = 256;
 
@@ -60,8 +62,13 @@ struct PtShared {
   uint64_t code_full[PT_CS], code_empty[PT_CS];
   uint64_t b_full[2], b_empty[2], a_full[2], a_empty[2], acc_full[2], acc_empty[2];
   alignas(16) float ne[2][PT_N];  // |r_e|^2 of the tile's entries, +inf = can never be returned
-  uint32_t tag[2][PT_N];          // debugging (GB_PQTC_DBG & 128): tile counter written with each decoded row
   uint32_t tmem_base;
+  // candidate queue: the epilogue warps append (query, probe, position) records with shared-memory atomics and move on;
+  // the drain warp turns them into the global per-query lists.  A global atomicAdd-with-return costs ~1 us of latency:
+  // issued from the epilogue it stalled the whole pipeline as soon as a loose bound let a percent of the entries through.
+  unsigned int q_head, q_tail;
+  int q_done;
+  unsigned long long q_rec[PT_RQ];  // (q << 48 | p << 32 | pos), kRecEmpty = free slot
 };
 
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
@@ -115,13 +122,15 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) rmax2[0] = total, rmax2[1] = sb;
 }
 
-// ---- split the probes between phase A (exact scan -> bound) and phase B (tensor-core filter) -------------------------
-// Query q's phase A takes its first P_q probes: the fewest whose lists hold >= target entries together (so that the
-// k'-th exact score is a usable bound), at most pa_max.  out_a / out_b are copies of probe_ids with the other phase's
-// probes set to -1 ("no list", skipped by both scans).
-__global__ void pqtc_split_probes_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, int pa_max,
-                                         long long target, const int* __restrict__ list_len, int32_t* __restrict__ out_a,
-                                         int32_t* __restrict__ out_b) {
+// ---- phase A's plan ---------------------------------------------------------------------------------------------------
+// Query q's phase A scans its first P_q probes IN FULL: the fewest whose lists hold >= target entries together, at most
+// pa_max.  probes_a / probes_b = probe_ids with the other phase's probes set to -1 ("no list", skipped by both scans);
+// row_limit[q][p] = rows of probe p phase A scores exactly (the whole list, or 0).  A tight bound matters far more than
+// a cheap phase A: bounding from a 3 200-row PREFIX of the nearest list instead of the whole list was measured at
+// 60x the candidates and a 2.8x slower filter kernel at C3, 4x slower at 100 M vectors (profiles/README.md, r2 notes).
+__global__ void pqtc_plan_phase_a_kernel(const int32_t* __restrict__ probe_ids, int64_t npairs, int nprobe, int pa_max,
+                                         long long target, const int* __restrict__ list_len, int32_t* __restrict__ probes_a,
+                                         int32_t* __restrict__ probes_b, int* __restrict__ row_limit) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= npairs) return;
   const int64_t q = j / nprobe;
@@ -138,8 +147,10 @@ __global__ void pqtc_split_probes_kernel(const int32_t* __restrict__ probe_ids, 
     }
   }
   const int32_t id = row[p];
-  out_a[j] = p < P ? id : -1;
-  out_b[j] = p < P ? -1 : id;
+  const bool in_a = p < P;
+  probes_a[j] = in_a ? id : -1;
+  probes_b[j] = in_a ? -1 : id;
+  row_limit[j] = in_a && id >= 0 ? list_len[id] : 0;
 }
 
 // ---- per pair group: the A operand tile and the pairs' thresholds ---------------------------------
@@ -148,6 +159,7 @@ struct PairMeta {
   float lo;   // ... and acc + c * ne >= lo  (the other side of the score window, checked on the rare path)
   float c;    // sa * sb: the operands' power-of-two scales (accumulator = c * (-2 <a, r>))
   int q, p;
+  int lim;    // rows [0, lim) of this pair's list were scored exactly by phase A: never candidates
 };
 
 template <int METRIC>
@@ -158,14 +170,14 @@ __global__ void __launch_bounds__(PT_M)
                           const unsigned long long* __restrict__ bound_keys, int64_t bound_stride, int kprime,
                           const float* __restrict__ rmax2, float min_score, float max_score, float eps_scale,
                           unsigned char* __restrict__ a_scratch, PairMeta* __restrict__ meta, int* __restrict__ cand_cnt,
-                          int cap) {
+                          int cap, const int* __restrict__ row_limit) {
   if ((int64_t)blockIdx.x >= totals[1]) return;
   const LmTile t = items[blockIdx.x];
   if (t.seg != 0) return;  // one staging per pair group: the first item of the group owns the slot
   const int r = threadIdx.x;
   const int kc_n = d / 8;
   unsigned char* tile = a_scratch + (int64_t)t.grp * ((int64_t)kc_n * 2048);
-  PairMeta pm{-INFINITY, INFINITY, 1.0f, -1, 0};
+  PairMeta pm{-INFINITY, INFINITY, 1.0f, -1, 0, 0};
   const float* x = nullptr;
   const float* c = nullptr;
   if (r < t.npairs) {
@@ -213,6 +225,7 @@ __global__ void __launch_bounds__(PT_M)
   }
   if (x) {
     const float dis0 = coarse_dis[(int64_t)pm.q * nprobe + pm.p];
+    pm.lim = row_limit ? row_limit[(int64_t)pm.q * nprobe + pm.p] : 0;
     const unsigned long long bk = bound_keys[(int64_t)pm.q * bound_stride + kprime - 1];
     const float R2 = rmax2[0], R = sqrtf(R2);
     pm.c = sa * rmax2[1];
@@ -275,39 +288,37 @@ __device__ __forceinline__ void pt_load32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "memory");
 }
 
-// rare path of the epilogue: the 32 columns of one pair contain at least one candidate.  Returns false once the
-// query's candidate list is full: the query is going to be redone by the exact kernel, so the caller stops
-// pushing for this pair (a query without a usable bound would otherwise hammer one counter with millions of
-// same-address atomics and stall the pipeline behind it).
-__device__ __noinline__ bool pt_push_hits(uint32_t taddr, const float* ne32, float c, float thr, float lo, int q, int p, uint32_t pos0,
-                                          int* __restrict__ cand_cnt, unsigned long long* __restrict__ cand, int cap, bool active) {
-  // Called by the WHOLE warp (tcgen05.ld is .sync.aligned: every lane must execute it, convergently); `active` = this
-  // lane's pair has a candidate among the 32 columns.  The columns are read from TMEM again here: handing the caller's
-  // register block over by reference would force a local-memory copy of every accumulator block in the hot loop.
+// rare path of the epilogue: the 32 columns of one pair contain at least one candidate.
+// Called by the WHOLE warp (tcgen05.ld is .sync.aligned: every lane must execute it, convergently); `active` = this
+// lane's pair has a candidate among the 32 columns.  The columns are read from TMEM again here: handing the caller's
+// register block over by reference would force a local-memory copy of every accumulator block in the hot loop.
+__device__ __noinline__ void pt_push_hits(uint32_t taddr, const float* ne32, float c, float thr, float lo, int q, int p, uint32_t pos0,
+                                          int lim, PtShared* sh, bool active) {
   uint32_t v[32];
   pt_load32(taddr, v);
-  if (!active) return true;
-  if (*reinterpret_cast<volatile int*>(cand_cnt + q) > cap) return false;
   uint32_t mask = 0;
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
-    const float s = fmaf(ne32[j], c, __uint_as_float(v[j]));
-    if (s <= thr && s >= lo) mask |= 1u << j;
+    for (int j = 0; j < 32; j++) {
+      const float s = fmaf(ne32[j], c, __uint_as_float(v[j]));
+      if (s <= thr && s >= lo) mask |= 1u << j;
+    }
+    // rows phase A has scored exactly stay out
+    if ((int)pos0 < lim) mask = (int)pos0 + 32 <= lim ? 0u : mask & ~((1u << (lim - (int)pos0)) - 1u);
   }
-  if (!mask) return true;
-  // one atomic per (pair, 32-column block): on data where the bound is loose the filter passes a percent of the entries
-  // and a per-hit atomic made this path the kernel's critical section
-  const int nh = __popc(mask);
-  const int base = atomicAdd(cand_cnt + q, nh);
-  if (base + nh > cap) return false;  // the count now exceeds cap: the query is flagged for the exact kernel
-  unsigned long long* dst = cand + (int64_t)q * cap + base;
-  const unsigned long long hi = (unsigned long long)(uint32_t)p << 32;
-  while (mask) {
-    const int j = __ffs(mask) - 1;
-    mask &= mask - 1;
-    *dst++ = hi | (pos0 + (uint32_t)j);
+  if (mask) {
+    unsigned int idx = atomicAdd(&sh->q_head, (unsigned int)__popc(mask));
+    const unsigned long long hi = ((unsigned long long)(uint32_t)q << 48) | ((unsigned long long)(uint32_t)p << 32);
+    while (mask) {
+      const int j = __ffs(mask) - 1;
+      mask &= mask - 1;
+      // the slot's previous occupant (idx - PT_RQ) has been consumed once the tail has passed it
+      while (idx - *reinterpret_cast<volatile unsigned int*>(&sh->q_tail) >= (unsigned int)PT_RQ) __nanosleep(32);
+      *reinterpret_cast<volatile unsigned long long*>(&sh->q_rec[idx % PT_RQ]) = hi | (unsigned long long)(pos0 + (uint32_t)j);
+      idx++;
+    }
   }
-  return true;
+  __syncwarp();
 }
 
 // EAGER: tombstones and the docid predicate are resolved in the decode warps (one id + bitmap lookup per entry per
@@ -366,7 +377,9 @@ __global__ void __launch_bounds__(PT_NT, 1)
       mbar_init(&sh.acc_empty[b], PT_M);    // every epilogue thread
     }
     mbar_fence_init();
+    sh.q_head = 0, sh.q_tail = 0, sh.q_done = 0;
   }
+  for (int i = tid; i < PT_RQ; i += PT_NT) sh.q_rec[i] = kRecEmpty;
   // codebook (fp16, pre-scaled) and centroid norms: resident for the CTA's lifetime
   for (int i = tid; i < CB_BYTES / 16; i += PT_NT)
     reinterpret_cast<uint4*>(cb)[i] = __ldg(reinterpret_cast<const uint4*>(cb_g) + i);
@@ -415,18 +428,19 @@ __global__ void __launch_bounds__(PT_NT, 1)
             mn1 = fminf(mn1, fminf(fminf(u0, u1), fminf(u2, u3)));
           }
           const uint32_t pos = (uint32_t)(t.row0 + i * PT_N + cc);
-          const bool h0 = mn0 <= pm.thr;
-          if (__any_sync(0xffffffffu, h0) &&
-              !pt_push_hits(ta, ne0, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos, cand_cnt, cand, cap, h0))
-            pm.thr = -INFINITY;  // the query overflowed: nothing more to collect for this pair
-          const bool h1 = mn1 <= pm.thr;
-          if (__any_sync(0xffffffffu, h1) &&
-              !pt_push_hits(ta + 32, ne0 + 32, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos + 32, cand_cnt, cand, cap, h1))
-            pm.thr = -INFINITY;
+          const bool h0 = mn0 <= pm.thr, h1 = mn1 <= pm.thr;
+          if (__any_sync(0xffffffffu, h0)) pt_push_hits(ta, ne0, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos, pm.lim, &sh, h0);
+          if (__any_sync(0xffffffffu, h1))
+            pt_push_hits(ta + 32, ne0 + 32, pm.c, pm.thr, pm.lo, pm.q, pm.p, pos + 32, pm.lim, &sh, h1);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&sh.acc_empty[b]);
       }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      __threadfence_block();
+      atomicAdd(&sh.q_done, 1);  // this warp's records are all in the queue
     }
   } else if (warp < 8) {
     // ======================= decode: thread = entry of the tile =======================
@@ -504,7 +518,6 @@ __global__ void __launch_bounds__(PT_NT, 1)
         // ne[b] is read by the epilogue of tile bn - 2: wait until it has released the buffer
         mbar_wait(&sh.acc_empty[b], ((bn >> 1) & 1) ^ 1);
         sh.ne[b][e] = valid ? nsum : INFINITY;
-        if (dbg & 128) sh.tag[b][e] = bn;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core proxy
         mbar_arrive(&sh.b_full[b]);
       }
@@ -537,6 +550,42 @@ __global__ void __launch_bounds__(PT_NT, 1)
       }
       an++;
     }
+  } else if (warp == 10) {
+    // ======================= candidate drain: shared queue -> global per-query lists =======================
+    const int lane = tid & 31;
+    unsigned int t = 0;
+    for (;;) {
+      unsigned long long r[4];
+      int n = 0;
+      bool open = true;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        r[u] = *reinterpret_cast<volatile unsigned long long*>(&sh.q_rec[(t + (unsigned)(lane + 32 * u)) % PT_RQ]);
+        const unsigned int m = __ballot_sync(0xffffffffu, r[u] != kRecEmpty);
+        if (open) {  // records are consumed as a contiguous prefix, so the tail stays a single counter
+          if (m == 0xffffffffu) n += 32;
+          else n += __ffs(~m) - 1, open = false;
+        }
+      }
+      if (n == 0) {
+        if (*reinterpret_cast<volatile int*>(&sh.q_done) == 4 && *reinterpret_cast<volatile unsigned int*>(&sh.q_head) == t) break;
+        __nanosleep(64);
+        continue;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (lane + 32 * u < n) {
+          const int q = (int)(r[u] >> 48), p = (int)((r[u] >> 32) & 0xFFFFu);
+          const int slot = atomicAdd(cand_cnt + q, 1);  // a count above cap flags the query for the exact kernel
+          if (slot < cap) cand[(int64_t)q * cap + slot] = ((unsigned long long)(uint32_t)p << 32) | (r[u] & 0xFFFFFFFFull);
+          *reinterpret_cast<volatile unsigned long long*>(&sh.q_rec[(t + (unsigned)(lane + 32 * u)) % PT_RQ]) = kRecEmpty;
+        }
+      }
+      __threadfence_block();
+      __syncwarp();
+      t += (unsigned int)n;
+      if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&sh.q_tail) = t;
+    }
   } else {
     // ======================= MMA issuer (whole warp loops, one elected lane issues) =======================
     // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (1 << 4), a = b = F16 (format 0 at [7, 10) and
@@ -555,12 +604,6 @@ __global__ void __launch_bounds__(PT_NT, 1)
         mbar_wait(&sh.b_full[b], (bn >> 1) & 1);
         mbar_wait(&sh.acc_empty[b], ((bn >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg & 128) {  // every row of the stage must carry this tile's tag by now
-          const int lane = tid & 31;
-          int stale = 0;
-          for (int u = 0; u < 4; u++) stale += sh.tag[b][lane + 32 * u] != bn;
-          if (stale) atomicAdd(&g_pqtc_dbg[1], (unsigned long long)stale);
-        }
         if (elect_one()) {
           const uint64_t da = lt_desc(a_base + (uint32_t)(ab * tile_stride)), db = lt_desc(b_base + (uint32_t)(b * tile_stride));
           const uint32_t acc = tmem_d + (uint32_t)(b * PT_N);
@@ -594,7 +637,7 @@ __global__ void __launch_bounds__(RS_NT)
                       const float* __restrict__ coarse_dis, int nprobe, ListDirectory dir, int M, const float* __restrict__ T,
                       const int* __restrict__ cand_cnt, const unsigned long long* __restrict__ cand, int cap,
                       const unsigned long long* __restrict__ keys_a, int64_t keys_a_stride, int kprime, int NP,
-                      FilterArgs f, unsigned long long* __restrict__ out) {
+                      const int* __restrict__ row_limit, FilterArgs f, unsigned long long* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(rs_smem);  // [NP]
   float* ips = reinterpret_cast<float*>(buf + NP);                            // [M][256]
@@ -613,9 +656,16 @@ __global__ void __launch_bounds__(RS_NT)
     const float4* ipq4 = reinterpret_cast<const float4*>(ipq);
     for (int i = tid; i < M * PT_KSUB / 4; i += RS_NT) reinterpret_cast<float4*>(ips)[i] = __ldg(ipq4 + i);
   }
-  int n2 = 16;
-  while (n2 < kprime + cnt) n2 <<= 1;  // <= NP
-  for (int i = tid; i < n2; i += RS_NT) buf[i] = i < kprime ? keys_a[(int64_t)q * keys_a_stride + i] : kKeySentinel;
+  // CandQueue layout: buf[0, KP) = the current best (phase A's keys, sentinel padded), buf[KP, KP + cnt) = candidates;
+  // its flush keeps the k' best -- a bitonic sort of the occupied prefix when short, an MSB radix select (linear in the
+  // fill) when a loose bound let thousands of candidates through
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_tau;
+  int KP = 16;
+  while (KP < kprime) KP <<= 1;
+  CandQueue cq{buf, &s_cnt, &s_tau, kprime, KP, NP};
+  for (int i = tid; i < KP; i += RS_NT) buf[i] = i < kprime ? keys_a[(int64_t)q * keys_a_stride + i] : kKeySentinel;
+  if (tid == 0) s_cnt = cnt, s_tau = kKeySentinel;
   __syncthreads();
   for (int i = tid; i < cnt; i += RS_NT) {
     const unsigned long long rec = cand[(int64_t)q * cap + i];
@@ -632,11 +682,12 @@ __global__ void __launch_bounds__(RS_NT)
       dis += METRIC == kMetricL2 ? fmaf(-2.0f, a, __ldg(Tl + m * PT_KSUB + c)) : a;
     }
     const int64_t raw = dir.ids[l][pos];
-    if (raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw) && dis <= f.max_score && dis >= f.min_score)
-      buf[kprime + i] = make_key(score2ord<METRIC>(dis), (uint32_t)raw);
+    // positions below row_limit were scored exactly by phase A: they are in keys_a already (or lost there for good)
+    const bool ok = (int)pos >= row_limit[(int64_t)q * nprobe + p] && raw >= 0 && ctx_is_valid(f.del_bits, f.filter_bits, (uint32_t)raw) && dis <= f.max_score && dis >= f.min_score;
+    buf[KP + i] = ok ? make_key(score2ord<METRIC>(dis), (uint32_t)raw) : kKeySentinel;
   }
   __syncthreads();
-  block_bitonic_sort(buf, n2);
+  cq.flush(true);
   for (int i = tid; i < kprime; i += RS_NT) out[(int64_t)q * kprime + i] = buf[i];
 }
 
@@ -705,11 +756,12 @@ cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uin
   return cudaGetLastError();
 }
 
-cudaError_t launch_pqtc_split_probes(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
-                                     const int* list_len, int32_t* out_a, int32_t* out_b, cudaStream_t st) {
+cudaError_t launch_pqtc_plan_phase_a(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
+                                     const int* list_len, int32_t* probes_a, int32_t* probes_b, int* row_limit,
+                                     cudaStream_t st) {
   if (npairs <= 0) return cudaSuccess;
-  pqtc_split_probes_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, pa_max, target,
-                                                                            list_len, out_a, out_b);
+  pqtc_plan_phase_a_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(probe_ids, npairs, nprobe, pa_max, target,
+                                                                            list_len, probes_a, probes_b, row_limit);
   note_launch();
   return cudaGetLastError();
 }
@@ -718,19 +770,20 @@ cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const flo
                                   int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
                                   const float* coarse_dis, const unsigned long long* bound_keys, int64_t bound_stride,
                                   int kprime, const float* rmax2, FilterArgs f, int metric, float eps_scale,
-                                  unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, cudaStream_t st) {
+                                  unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, const int* row_limit,
+                                  cudaStream_t st) {
   if (max_items <= 0) return cudaSuccess;
   if (d % 16) return cudaErrorInvalidValue;
   if (metric == kMetricL2)
     pq_stage_pairs_kernel<kMetricL2><<<max_items, PT_M, 0, st>>>(xq, ldq, d, coarse, ldc, items, totals, pair_j, nprobe,
                                                                 coarse_dis, bound_keys, bound_stride, kprime, rmax2,
                                                                 f.min_score, f.max_score, eps_scale, a_scratch,
-                                                                static_cast<PairMeta*>(meta), cand_cnt, cap);
+                                                                static_cast<PairMeta*>(meta), cand_cnt, cap, row_limit);
   else
     pq_stage_pairs_kernel<kMetricIP><<<max_items, PT_M, 0, st>>>(xq, ldq, d, coarse, ldc, items, totals, pair_j, nprobe,
                                                                 coarse_dis, bound_keys, bound_stride, kprime, rmax2,
                                                                 f.min_score, f.max_score, eps_scale, a_scratch,
-                                                                static_cast<PairMeta*>(meta), cand_cnt, cap);
+                                                                static_cast<PairMeta*>(meta), cand_cnt, cap, row_limit);
   note_launch();
   return cudaGetLastError();
 }
@@ -759,9 +812,9 @@ cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, c
 cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                               ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,
                               int cap, const unsigned long long* keys_a, int64_t keys_a_stride, int kprime, int metric,
-                              FilterArgs f, unsigned long long* out, cudaStream_t st) {
+                              const int* row_limit, FilterArgs f, unsigned long long* out, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
-  const int NP = next_pow2(kprime + cap);
+  const int NP = next_pow2(next_pow2(kprime < 16 ? 16 : kprime) + cap);  // CandQueue: KP best + cap candidates
   const size_t smem = (size_t)NP * 8 + (size_t)M * PT_KSUB * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   cudaError_t e;
@@ -769,12 +822,12 @@ cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* prob
     e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_rescore_kernel<kMetricL2><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
-                                                         cap, keys_a, keys_a_stride, kprime, NP, f, out);
+                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, out);
   } else {
     e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_rescore_kernel<kMetricIP><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
-                                                         cap, keys_a, keys_a_stride, kprime, NP, f, out);
+                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, out);
   }
   note_launch();
   return cudaGetLastError();

@@ -116,6 +116,11 @@ class GammaEngine:
         tb = wire.build_table(name, list(fields), vectors, indexes, refresh_interval=refresh_interval, **kw)
         _status(_api().CreateTable(self._h, tb, len(tb)))
 
+    def create_table_raw(self, table_bytes, vec_name, dim):
+        """CreateTable with caller-supplied gamma_api.Table flatbuffer bytes (fixtures written by the reference's builders)"""
+        self.vec_name, self.dim = vec_name, dim
+        _status(_api().CreateTable(self._h, table_bytes, len(table_bytes)))
+
     def add_doc(self, key, vector, extra_fields=()):
         v = np.ascontiguousarray(vector, np.float32).tobytes()
         fields = [("_id", key.encode() if isinstance(key, str) else key, wire.DT_STRING)]
