@@ -877,3 +877,37 @@ def test_baseline_shape_ivfpq_d128_m16_nlist4096_rerank400(data):
         agree.append(np.mean(ir[q][: len(order)] == cand[order]))
     assert np.mean(agree) >= 0.999
     idx.close()
+
+
+def test_ivfpq_filter_follows_appends_and_codebook_changes():
+    """The tensor-core filter streams a cached |r_e|^2 per list entry next to the codes.  The cache must follow the
+    lists (vectors appended between two searches) and the codebook (set_pq_centroids): answers stay those of the oracle."""
+    d, M, n, nq, nlist, nprobe, kk = 64, 8, 30000, 700, 16, 6, 50
+    rng = np.random.default_rng(401)
+    centers = rng.normal(0, 1, (32, d)).astype(np.float32)
+    gen = lambda m: (centers[rng.integers(0, 32, m)] + 0.4 * rng.normal(0, 1, (m, d))).astype(np.float32)  # noqa: E731
+    db, xq = gen(n), gen(nq)
+    cent, _, _ = orc.kmeans(db[:4000], nlist, niter=5)
+    a = orc.assign(cent, db, L2)
+    pqc = orc.pq_train(db[:6000] - cent[a[:6000]], M, niter=4)
+    idx = gi().GammaIndex("IVFPQ", d, {"ncentroids": nlist, "nprobe": nprobe, "nsubvector": M, "metric_type": "L2"})
+    idx.set_centroids(cent)
+    idx.set_pq_centroids(pqc)
+    idx.add_vectors(db[:20000])
+    idx.add_pending()
+    T = orc.ivfpq_precompute_table(cent, pqc)
+    cd, keys = orc.coarse_search(cent, xq, nprobe, L2)
+
+    def check(pq_now, T_now):
+        off, codes, ids = idx.export_lists()
+        dg, ig = idx.search_preassigned(xq, kk, keys, cd)
+        assert idx.last_scan_kernel == "pqtc_scan_kernel"
+        do, io = orc.ivfpq_search_preassigned(off, codes, ids, cent, pq_now, T_now, xq, kk, keys, cd, L2)
+        assert_same_results(dg, ig, do, io)
+
+    check(pqc, T)
+    idx.add_vectors(db[20000:])   # lists grow: the cache is rebuilt by the next search
+    idx.add_pending()
+    check(pqc, T)
+    check(pqc, T)                 # and reused when nothing changed
+    idx.close()

@@ -190,11 +190,15 @@ struct CandQueue {
 
   static constexpr int kSelectMin = 1024;
 
-  // Radix-select flush.  Finds the byte prefix P (most significant bytes first) such that exactly
-  // k valid keys are <= P|11..1, compacts those keys to buf[0, k) in place (unordered), pads
-  // buf[k, KP) with sentinels and sets tau = P|11..1.  That tau is >= the true k-th best key and
-  // < every discarded key, so the "key < tau" admission test stays exact.  Keys are unique
-  // (one vid appears once per query), which bounds the loop at 8 byte passes.
+  // Radix-select flush.  Finds the shortest byte prefix P (most significant bytes first) such that
+  // between k and KP valid keys are <= P|11..1, compacts those keys to buf[0, kept) in place
+  // (unordered), pads buf[kept, KP) with sentinels and sets tau = P|11..1.  That tau is >= the true
+  // k-th best key and < every discarded key, so the "key < tau" admission test never loses a top-k
+  // key; the up to KP - k extra keys ride along until the final sort drops them.  Stopping as soon as
+  // the selected bin fits the slack (instead of descending until exactly k remain) saves most of the
+  // 8 byte passes when scores share their leading bytes: with k = 400 the flushes were 40 % of a
+  // one-list scan (phase A of the tensor-core filter).  Keys are unique (one vid appears once per
+  // query), which bounds the loop at 8 passes.
   __device__ __forceinline__ void flush_select(int c, bool final_sort) {
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_prefix;
@@ -252,7 +256,8 @@ struct CandQueue {
             if (before < need && need <= before + h[j]) {
               s_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
               s_need = need - before;
-              s_done = (h[j] == need - before) ? 1 : 0;
+              // keeping the whole bin leaves k - (need - before) + h[j] keys: done when that fits KP
+              s_done = (h[j] - (need - before) <= KP - k) ? 1 : 0;
             }
             before += h[j];
           }

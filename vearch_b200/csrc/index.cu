@@ -287,7 +287,8 @@ const float* RawStore::contiguous(int64_t n, Scratch& s) {
 }
 
 // ------------------------------------------------------------------------------------------
-IvfLists::IvfLists(int nlist, int code_bytes) : nlist_(nlist), code_bytes_(code_bytes) {
+static std::atomic<uint64_t> g_lists_uid{1};
+IvfLists::IvfLists(int nlist, int code_bytes) : nlist_(nlist), code_bytes_(code_bytes), uid_(g_lists_uid.fetch_add(1)) {
   h_data_.assign(nlist, nullptr);
   h_ids_.assign(nlist, nullptr);
   h_len_.assign(nlist, 0);
@@ -1814,6 +1815,8 @@ IVFPQIndex::~IVFPQIndex() {
   cudaFree(d_table_);
   cudaFree(d_cb16_);
   cudaFree(d_cbnrm_);
+  if (pqn_.base) cudaFree(pqn_.base);
+  if (pqn_.d_off) cudaFree(pqn_.d_off);
 }
 int IVFPQIndex::training_threshold() const {
   // gamma_index_ivfpq.cc:139-144: default max(nlist*200, 256); Indexing() clamps like IVFFLAT (:304-329)
@@ -1829,6 +1832,7 @@ int64_t IVFPQIndex::index_mem_bytes() const {
          (d_table_ ? (int64_t)nlist_ * M_ * 256 * 4 : 0);
 }
 int IVFPQIndex::rebuild_table(cudaStream_t st) {
+  pq_gen_++;  // the per-entry norm cache belongs to the previous codebook
   // tables of the tensor-core filter (kernels_pqtc.cu): bf16 codebook pre-scaled by -2 (L2) / -1 (IP),
   // centroid norms, and the bound on |r| its error margin uses
   if (pqtc_supported(M_, dsub_)) {
@@ -1933,6 +1937,41 @@ int IVFPQIndex::encode_host(const float* x, int64_t n, const int64_t* assign, ui
   return 0;
 }
 
+// Cache of |r_e|^2 per list entry for the tensor-core filter.  Searches hold mu_ shared, appends hold it exclusively and
+// drain in-flight searches before the lists change, so whenever the key (list set, lengths, codebook generation) differs
+// from the cached one no kernel is reading the cache; the rebuild (one pass over the codes) is serialised by pqn_mu_ and
+// synchronised before other streams may use it.
+int IVFPQIndex::ensure_pq_norms(cudaStream_t st) {
+  std::lock_guard<std::mutex> g(pqn_mu_);
+  const std::vector<int>& lens = lists_->lens();
+  if (pqn_.base && pqn_.lists_uid == lists_->uid() && pqn_.pq_gen == pq_gen_ && pqn_.lens == lens) return 0;
+  std::vector<int64_t> off((size_t)nlist_ + 1, 0);
+  for (int l = 0; l < nlist_; l++) off[l + 1] = off[l] + round_up(lens[l], 32);
+  const size_t total = (size_t)off[nlist_] + 128;  // a tile's 16-byte rounded tail may run past the last entry
+  if (total > pqn_.cap) {
+    if (pqn_.base) {
+      cudaDeviceSynchronize();
+      cudaFree(pqn_.base);
+      pqn_.base = nullptr;
+    }
+    const size_t cap = total + total / 4;
+    if (cudaMalloc(&pqn_.base, cap * 4) != cudaSuccess) {
+      cudaGetLastError();
+      pqn_.cap = 0;
+      return 1;  // no room: the caller scans with the exact kernel
+    }
+    pqn_.cap = cap;
+  }
+  if (!pqn_.d_off) GB_CUDA(cudaMalloc(&pqn_.d_off, sizeof(int64_t) * ((size_t)nlist_ + 1)));
+  GB_CUDA(cudaMemcpyAsync(pqn_.d_off, off.data(), sizeof(int64_t) * ((size_t)nlist_ + 1), cudaMemcpyHostToDevice, st));
+  GB_CUDA(launch_pq_entry_norms(lists_->directory(), nlist_, lists_->max_len(), M_, d_cbnrm_, pqn_.d_off, pqn_.base, st));
+  GB_CUDA(cudaStreamSynchronize(st));
+  pqn_.lens = lens;
+  pqn_.lists_uid = lists_->uid();
+  pqn_.pq_gen = pq_gen_;
+  return 0;
+}
+
 // GB_PQTC=0: never use the tensor-core filter (exact LUT kernel for every probe); GB_PQTC=2: use it
 // whenever the shape allows, whatever the batch size (tests)
 static int pqtc_mode() {  // read per call: tests flip it between searches of one process
@@ -1956,6 +1995,10 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   if (kk > 2048 || nprobe < 2 || nprobe > 65535 || nq > 65535) return 1;  // (query, probe) travel as 16-bit fields of a candidate record
   const int64_t npairs = (int64_t)nq * nprobe;
   if (mode != 2 && npairs < (int64_t)nlist_ * 32) return 1;  // < 32 queries per list on average
+  if (metric == kMetricL2) {
+    const int nr = ensure_pq_norms(s.stream());
+    if (nr) return nr;
+  }
   cudaStream_t st = s.stream();
   ListDirectory dir = lists_->directory();
   // phase A, per query: its first probes in full -- the fewest whose lists hold >= 4 k' entries together (so that its
@@ -2029,7 +2072,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   stage_end(st);
   scan_timer_begin(st);  // the dominant kernel: the roofline in bench.py is this launch alone
   stage_begin("pqtc_scan_kernel", st);
-  GB_CUDA(launch_pqtc_scan(a_scratch, meta, d_cb16_, d_cbnrm_, d_items, (int)max_items, d_totals, dir, M_, dsub_, f, metric,
+  GB_CUDA(launch_pqtc_scan(a_scratch, meta, d_cb16_, pqn_.base, pqn_.d_off, d_items, (int)max_items, d_totals, dir, M_, dsub_, f, metric,
                            d_cand_cnt, cand, cap, nsm, st));
   stage_end(st);
   scan_timer_end(st);

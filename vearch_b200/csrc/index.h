@@ -11,6 +11,7 @@
 
 #include <condition_variable>
 #include <memory>
+#include <atomic>
 #include <mutex>
 #include <thread>
 #include <shared_mutex>
@@ -102,6 +103,7 @@ class IvfLists {
   int max_len() const { return max_len_; }
   int64_t total() const { return total_; }
   const std::vector<int>& lens() const { return h_len_; }
+  uint64_t uid() const { return uid_; }  // distinguishes list sets (reset_index builds a new one)
   ListDirectory directory() const;
   // make room for add[l] more entries in every list; grows by copy (x1.5) when needed
   int reserve(const std::vector<int>& add, cudaStream_t st);
@@ -127,6 +129,7 @@ class IvfLists {
  private:
   void* slab_alloc(size_t bytes);
   int nlist_, code_bytes_;
+  uint64_t uid_;
   std::vector<void*> h_data_;
   std::vector<int64_t*> h_ids_;
   std::vector<int> h_len_, h_cap_;
@@ -455,7 +458,19 @@ class IVFPQIndex : public IVFFlatIndex {
   float* d_pq_ = nullptr;     // [M][256][dsub]
   float* d_table_ = nullptr;  // [nlist][M][256] (L2 only)
   uint16_t* d_cb16_ = nullptr;  // [M][256][dsub] bf16, pre-scaled (tensor-core filter)
-  float* d_cbnrm_ = nullptr;    // [M][256] |pq|^2, then rmax2
+  float* d_cbnrm_ = nullptr;    // [M][256] |pq|^2, then rmax2, sb
+  // |r_e|^2 of every list entry (L2), flat with 32-entry aligned list segments: built by the first list-major search
+  // after the lists or the codebook changed (lists are append-only: same list set + same lengths = same content)
+  struct PqNormCache {
+    float* base = nullptr;
+    int64_t* d_off = nullptr;
+    size_t cap = 0;
+    std::vector<int> lens;
+    uint64_t lists_uid = 0, pq_gen = 0;
+  } pqn_;
+  std::mutex pqn_mu_;
+  uint64_t pq_gen_ = 1;
+  int ensure_pq_norms(cudaStream_t st);
   float* d_opq_ = nullptr;    // [d][dpad] rows of the OPQ rotation A (y = A x); nullptr: no OPQ
   bool opq_trained_ = false;
 

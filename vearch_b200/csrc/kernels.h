@@ -173,10 +173,13 @@ cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const flo
                                   int kprime, const float* rmax2, FilterArgs f, int metric, float eps_scale,
                                   unsigned char* a_scratch, void* meta, int* cand_cnt, int cap, const int* row_limit, cudaStream_t st);
 // persistent kernel, one CTA per SM: candidates (probe << 32 | position) appended to cand[q][cap]
-cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* nrm,
+cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* pqnorm, const int64_t* pqnorm_off,
                              const LmTile* items, int max_items, const int64_t* totals, ListDirectory dir, int M, int dsub,
                              FilterArgs f, int metric, int* cand_cnt, unsigned long long* cand, int cap, int num_sms,
                              cudaStream_t st);
+// |r_e|^2 of every list entry: out[off[l] + pos] (L2; cached beside the lists, streamed to the filter kernel with the codes)
+cudaError_t launch_pq_entry_norms(ListDirectory dir, int nlist, int max_len, int M, const float* nrm, const int64_t* off,
+                                  float* out, cudaStream_t st);
 // out[q][kprime] = best kprime of keys_a[q] + the re-scored candidates (queries with cand_cnt > cap untouched)
 cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                               ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,

@@ -329,21 +329,25 @@ __device__ __noinline__ void pt_push_hits(uint32_t taddr, const float* ne32, flo
 template <int M, int DSUB, bool HAS_NORM, bool EAGER>
 __global__ void __launch_bounds__(PT_NT, 1)
     pqtc_scan_kernel(const unsigned char* __restrict__ a_scratch, const PairMeta* __restrict__ meta,
-                     const uint16_t* __restrict__ cb_g, const float* __restrict__ nrm_g, const LmTile* __restrict__ items,
+                     const uint16_t* __restrict__ cb_g, const float* __restrict__ pqnorm,
+                     const int64_t* __restrict__ pqnorm_off, const LmTile* __restrict__ items,
                      const int64_t* __restrict__ totals, ListDirectory dir, FilterArgs f, int* __restrict__ cand_cnt,
                      unsigned long long* __restrict__ cand, int cap, int tile_stride, int dbg) {
   constexpr int D = M * DSUB;
   constexpr int KC = D / 8;                // core matrices along K
   constexpr int TILE = KC * 2048;          // one 128-row operand tile, bytes
   constexpr int CB_BYTES = M * PT_KSUB * DSUB * 2;
-  constexpr int NRM_BYTES = HAS_NORM ? M * PT_KSUB * 4 : 0;
+  // |r_e|^2 of every list entry is cached in HBM beside the lists (IVFPQIndex::ensure_pq_norms) and arrives with the
+  // codes: 512 bytes per tile by TMA instead of 16 table gathers per entry in the decode warps (a sixth of the kernel's
+  // shared-memory wavefronts, profiles/r2_ncu_pqtc_scan.txt)
+  constexpr int NRM_BYTES = HAS_NORM ? PT_CS * PT_N * 4 : 0;
   constexpr int CODE_STAGE = PT_N * M;
   constexpr int UNIT = DSUB * 2;           // bytes of one centroid in the fp16 codebook
   static_assert(D % 16 == 0 && M % 4 == 0, "shape");
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ PtShared sh;
   unsigned char* cb = smem;
-  float* nrm = reinterpret_cast<float*>(smem + CB_BYTES);
+  float* nstage = reinterpret_cast<float*>(smem + CB_BYTES);  // [PT_CS][PT_N] norms of the staged tiles
   // Operand tiles start on 4 KiB boundaries, so the 4 KiB block one MMA reads (two core-matrix columns, LBO apart)
   // never straddles a 128 KiB line of the shared-memory window.  Measured on B200: with a tile at 0x1e800 the MMA
   // whose second core-matrix column began exactly at 0x20000 intermittently produced wrong accumulator columns;
@@ -383,9 +387,6 @@ __global__ void __launch_bounds__(PT_NT, 1)
   // codebook (fp16, pre-scaled) and centroid norms: resident for the CTA's lifetime
   for (int i = tid; i < CB_BYTES / 16; i += PT_NT)
     reinterpret_cast<uint4*>(cb)[i] = __ldg(reinterpret_cast<const uint4*>(cb_g) + i);
-  if (HAS_NORM)
-    for (int i = tid; i < NRM_BYTES / 16; i += PT_NT)
-      reinterpret_cast<float4*>(nrm)[i] = __ldg(reinterpret_cast<const float4*>(nrm_g) + i);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -484,6 +485,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
             if (bad) atomicAdd(&g_pqtc_dbg[0], 1ull);
           }
         }
+        const float nstaged = HAS_NORM ? nstage[s * PT_N + e] : 0.f;
         mbar_arrive(&sh.code_empty[s]);
         // entries past the end of the segment decode whatever bytes the stage holds: finite values,
         // masked by ne = +inf.  Tombstones (gamma_index_ivfpq.h:930) and the docid predicate
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
         mbar_wait(&sh.b_empty[b], ((bn >> 1) & 1) ^ 1);
         if (dbg & 1) __nanosleep(3000);
         unsigned char* brow = b_buf + b * tile_stride + e * 16;
-        float nsum = 0.f;
+        const float nsum = nstaged;
 #pragma unroll
         for (int m = 0; m < M; m++) {
           const uint32_t c = (w[m >> 2] >> (8 * (m & 3))) & 0xFFu;
@@ -513,7 +515,6 @@ __global__ void __launch_bounds__(PT_NT, 1)
               *reinterpret_cast<uint4*>(brow + (m * (UNIT / 16) + u) * 2048) = val;
             }
           }
-          if (HAS_NORM) nsum += nrm[m * PT_KSUB + c];
         }
         // ne[b] is read by the epilogue of tile bn - 2: wait until it has released the buffer
         mbar_wait(&sh.acc_empty[b], ((bn >> 1) & 1) ^ 1);
@@ -536,6 +537,7 @@ __global__ void __launch_bounds__(PT_NT, 1)
       }
       __syncwarp();
       const unsigned char* lcodes = dir.codes[t.list];
+      const float* lnorms = HAS_NORM ? pqnorm + pqnorm_off[t.list] : nullptr;  // list segments start 128-byte aligned
       const int ntiles = (t.nrows + PT_N - 1) / PT_N;
       for (int i = 0; i < ntiles; i++, cn++) {
         const int s = cn % PT_CS;
@@ -543,8 +545,10 @@ __global__ void __launch_bounds__(PT_NT, 1)
         if (elect_one()) {
           const int n_e = min(PT_N, t.nrows - i * PT_N);
           const uint32_t bytes = ((uint32_t)n_e * M + 15u) & ~15u;
-          mbar_arrive_expect_tx(&sh.code_full[s], bytes);
+          const uint32_t nbytes = HAS_NORM ? ((uint32_t)n_e * 4u + 15u) & ~15u : 0u;
+          mbar_arrive_expect_tx(&sh.code_full[s], bytes + nbytes);
           bulk_g2s(code_buf + s * CODE_STAGE, lcodes + (int64_t)(t.row0 + i * PT_N) * M, bytes, &sh.code_full[s]);
+          if (HAS_NORM) bulk_g2s(nstage + s * PT_N, lnorms + (t.row0 + i * PT_N), nbytes, &sh.code_full[s]);
         }
         __syncwarp();
       }
@@ -707,7 +711,8 @@ __global__ void __launch_bounds__(RS_NT)
 }
 
 template <int M, int DSUB>
-cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* meta, const uint16_t* cb, const float* nrm,
+cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* meta, const uint16_t* cb, const float* pqnorm,
+                              const int64_t* pqnorm_off,
                               const LmTile* items, const int64_t* totals, ListDirectory dir, FilterArgs f, int metric,
                               int* cand_cnt, unsigned long long* cand, int cap, int grid, cudaStream_t st) {
   constexpr int D = M * DSUB;
@@ -717,11 +722,12 @@ cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* me
   const size_t base = (size_t)M * PT_KSUB * DSUB * 2 + 4 * (size_t)tile_stride + (size_t)PT_CS * PT_N * M + 4096;
   const bool l2 = metric == kMetricL2;
   const bool eager = f.del_bits != nullptr || f.filter_bits != nullptr;
-  const size_t smem = base + (l2 ? (size_t)M * PT_KSUB * 4 : 0);
+  if (l2 && (!pqnorm || !pqnorm_off)) return cudaErrorInvalidValue;
+  const size_t smem = base + (l2 ? (size_t)PT_CS * PT_N * 4 : 0);
   auto go = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, PT_NT, smem, st>>>(a_scratch, meta, cb, nrm, items, totals, dir, f, cand_cnt, cand, cap, tile_stride, dbg);
+    kern<<<grid, PT_NT, smem, st>>>(a_scratch, meta, cb, pqnorm, pqnorm_off, items, totals, dir, f, cand_cnt, cand, cap, tile_stride, dbg);
     note_launch();
     return cudaGetLastError();
   };
@@ -730,6 +736,43 @@ cudaError_t launch_scan_shape(const unsigned char* a_scratch, const PairMeta* me
 }
 
 }  // namespace
+
+// ---- |r_e|^2 of every list entry (L2): out[off[l] + pos] = sum_m nrm[m][code[m]] ------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+    pq_entry_norms_kernel(ListDirectory dir, int M, const float* __restrict__ nrm, const int64_t* __restrict__ off,
+                          float* __restrict__ out) {
+  extern __shared__ float s_nrm[];  // [M][256]
+  const int l = blockIdx.y;
+  const int len = dir.len[l];
+  const int row0 = blockIdx.x * 1024;
+  if (row0 >= len) return;
+  for (int i = threadIdx.x; i < M * PT_KSUB; i += 256) s_nrm[i] = nrm[i];
+  __syncthreads();
+  const unsigned char* codes = dir.codes[l];
+  float* dst = out + off[l];
+  for (int r = row0 + threadIdx.x; r < min(len, row0 + 1024); r += 256) {
+    const unsigned char* c = codes + (int64_t)r * M;
+    float sum = 0.f;
+    for (int m = 0; m < M; m++) sum += s_nrm[m * PT_KSUB + c[m]];
+    dst[r] = sum;
+  }
+}
+}  // namespace
+
+cudaError_t launch_pq_entry_norms(ListDirectory dir, int nlist, int max_len, int M, const float* nrm, const int64_t* off,
+                                  float* out, cudaStream_t st) {
+  if (nlist <= 0 || max_len <= 0) return cudaSuccess;
+  const size_t smem = (size_t)M * PT_KSUB * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(pq_entry_norms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid((unsigned)((max_len + 1023) / 1024), (unsigned)nlist);
+  pq_entry_norms_kernel<<<grid, 256, smem, st>>>(dir, M, nrm, off, out);
+  note_launch();
+  return cudaGetLastError();
+}
 
 void pqtc_debug_counters(unsigned long long out[4], bool reset) {
   cudaMemcpyFromSymbol(out, g_pqtc_dbg, sizeof(unsigned long long) * 4);
@@ -788,7 +831,8 @@ cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const flo
   return cudaGetLastError();
 }
 
-cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* nrm,
+cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, const uint16_t* cb, const float* pqnorm,
+                             const int64_t* pqnorm_off,
                              const LmTile* items, int max_items, const int64_t* totals, ListDirectory dir, int M, int dsub,
                              FilterArgs f, int metric, int* cand_cnt, unsigned long long* cand, int cap, int num_sms,
                              cudaStream_t st) {
@@ -796,7 +840,7 @@ cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, c
   const int grid = max_items < num_sms ? max_items : num_sms;
   const PairMeta* pm = static_cast<const PairMeta*>(meta);
 #define GB_PT(MM, DS) \
-  if (M == MM && dsub == DS) return launch_scan_shape<MM, DS>(a_scratch, pm, cb, nrm, items, totals, dir, f, metric, cand_cnt, cand, cap, grid, st)
+  if (M == MM && dsub == DS) return launch_scan_shape<MM, DS>(a_scratch, pm, cb, pqnorm, pqnorm_off, items, totals, dir, f, metric, cand_cnt, cand, cap, grid, st)
   GB_PT(16, 8);
   GB_PT(8, 16);
   GB_PT(8, 8);

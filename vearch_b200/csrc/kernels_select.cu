@@ -112,6 +112,7 @@ __global__ void split_keys_kernel(const unsigned long long* __restrict__ keys, i
 
 void select_geometry(int k, int m, int* KP, int* SORTN) {
   *KP = next_pow2(k < 16 ? 16 : k);
+  if (*KP - k < k / 4 && *KP < 4096) *KP *= 2;  // slack for the radix-select flush to stop early (common.cuh)
   int per_round = SEL_NT * SEL_ITEMS;
   *SORTN = next_pow2(*KP + (m < per_round ? m : per_round));  // single-round inputs never flush mid-way
 }
