@@ -911,3 +911,52 @@ def test_ivfpq_filter_follows_appends_and_codebook_changes():
     check(pqc, T)
     check(pqc, T)                 # and reused when nothing changed
     idx.close()
+
+
+def test_ivfpq_filter_survives_concurrent_adds_and_searches():
+    """Big-batch IVF-PQ searches (tensor-core filter, per-entry norm cache) from two threads while a third keeps adding
+    vectors: every search sees a consistent index -- with exact re-rank each probe vector finds itself at distance 0 --
+    and the norm cache is rebuilt between searches without tearing (appends drain in-flight searches first)."""
+    import threading
+    d, M, nlist, n0 = 64, 8, 8, 12000
+    db = synth.sift_like(n0 + 4000, d, seed=61)
+    # distinct rows only: a duplicate would make "finds itself" ambiguous
+    db = np.unique(db, axis=0)
+    n0 = min(n0, len(db) - 4000)
+    cent, _, _ = orc.kmeans(db[:3000], nlist, niter=4)
+    a = orc.assign(cent, db[:6000], L2)
+    pqc = orc.pq_train(db[:6000] - cent[a], M, niter=4)
+    idx = gi().GammaIndex("IVFPQ", d, {"ncentroids": nlist, "nprobe": nlist, "nsubvector": M, "metric_type": "L2"})
+    idx.set_centroids(cent)
+    idx.set_pq_centroids(pqc)
+    idx.add_vectors(db[:n0])
+    idx.add_pending()
+    errs, stop = [], threading.Event()
+
+    def searcher(seed):
+        rng = np.random.default_rng(seed)
+        try:
+            while not stop.is_set():
+                pick = rng.integers(0, n0, 400)
+                dg, ig = idx.search(db[pick], 1, params={"nprobe": nlist, "recall_num": 100})
+                assert idx.last_scan_kernel == "pqtc_scan_kernel"
+                assert (dg[:, 0] == 0).all() and (ig[:, 0] == pick).all()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=searcher, args=(s,)) for s in (1, 2)]
+    for t in ts:
+        t.start()
+    try:
+        for b in range(n0, n0 + 4000, 250):
+            idx.add_vectors(db[b:b + 250])
+            idx.add_pending()
+    finally:
+        stop.set()
+        for t in ts:
+            t.join()
+    assert not errs, errs[:1]
+    pick = np.arange(n0 + 3000, n0 + 3400)
+    dg, ig = idx.search(db[pick], 1, params={"nprobe": nlist, "recall_num": 100})
+    assert (dg[:, 0] == 0).all() and (ig[:, 0] == pick).all()
+    idx.close()

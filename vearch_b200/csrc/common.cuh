@@ -168,10 +168,11 @@ struct CandQueue {
   // all threads; must be preceded by a __syncthreads() after the last push.  Small buffers are
   // sorted (bitonic, occupied prefix only); big ones go through an MSB radix select, whose cost is
   // linear in the fill.  final_sort: leave buf[0, KP) sorted ascending (the kernel's result).
-  __device__ __forceinline__ void flush(bool final_sort = false) {
+  // exact: leave exactly the k best in buf[0, k) (no slack keys) -- for a final flush whose caller does not sort
+  __device__ __forceinline__ void flush(bool final_sort = false, bool exact = false) {
     int c = *cnt;
     if (KP + c > kSelectMin) {
-      flush_select(c, final_sort);
+      flush_select(c, final_sort, exact);
       return;
     }
     // only the occupied prefix needs sorting: everything behind it is (made) sentinel
@@ -188,7 +189,9 @@ struct CandQueue {
     __syncthreads();
   }
 
-  static constexpr int kSelectMin = 1024;
+  // above this fill the flush is a radix select (linear in the fill) instead of a bitonic sort: a 1 Ki-key sort per
+  // flush was 40 % of the instructions of a one-list scan with k = 400 (profiles/r2_ncu_ivfpq_scan_phaseA.txt)
+  static constexpr int kSelectMin = 512;
 
   // Radix-select flush.  Finds the shortest byte prefix P (most significant bytes first) such that
   // between k and KP valid keys are <= P|11..1, compacts those keys to buf[0, kept) in place
@@ -199,7 +202,7 @@ struct CandQueue {
   // 8 byte passes when scores share their leading bytes: with k = 400 the flushes were 40 % of a
   // one-list scan (phase A of the tensor-core filter).  Keys are unique (one vid appears once per
   // query), which bounds the loop at 8 passes.
-  __device__ __forceinline__ void flush_select(int c, bool final_sort) {
+  __device__ __forceinline__ void flush_select(int c, bool final_sort, bool exact = false) {
     __shared__ int s_hist[256];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_need, s_done, s_valid, s_pos;
@@ -257,7 +260,7 @@ struct CandQueue {
               s_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
               s_need = need - before;
               // keeping the whole bin leaves k - (need - before) + h[j] keys: done when that fits KP
-              s_done = (h[j] - (need - before) <= KP - k) ? 1 : 0;
+              s_done = (h[j] - (need - before) <= (exact ? 0 : KP - k)) ? 1 : 0;
             }
             before += h[j];
           }

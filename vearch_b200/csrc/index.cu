@@ -1989,7 +1989,7 @@ static float pqtc_eps_scale() {
 // the batch / shape does not qualify (caller runs the exact kernel over all probes).
 int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const float* xq, int kk, const float* ip,
                                   const int32_t* probe_ids, const float* coarse_dis, int nprobe,
-                                  unsigned long long* adc_out, Scratch& s) {
+                                  unsigned long long* adc_out, bool need_sorted, Scratch& s) {
   const int mode = pqtc_mode();
   if (!mode || !tc_enabled() || !d_cb16_ || !pqtc_supported(M_, dsub_) || dpad_ != d_) return 1;
   if (kk > 2048 || nprobe < 2 || nprobe > 65535 || nq > 65535) return 1;  // (query, probe) travel as 16-bit fields of a candidate record
@@ -2027,8 +2027,10 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
   const int ngA = (pa_max + pgA - 1) / pgA;
   GB_ALLOC(partA, unsigned long long, (size_t)nq * ngA * kk, s);
   stage_begin("pq_phaseA_exact_scan", st);
+  // one group per query: its k' best come back unordered with the largest (the bound) in slot k' - 1 -- nobody needs
+  // them sorted (launch_select_keys below, used when the probes were split over groups, sorts anyway)
   GB_CUDA(launch_ivfpq_scan(ip, nq, d_probes_a, coarse_dis, pa_max, pgA, dir, M_, d_table_, kk, metric, f, partA, st, nprobe,
-                            nullptr, 0, d_row_limit));
+                            nullptr, 0, d_row_limit, /*sorted_out=*/ngA > 1));
   unsigned long long* keysA = partA;
   if (ngA > 1) {
     keysA = s.alloc_n<unsigned long long>((size_t)nq * kk);
@@ -2080,7 +2082,7 @@ int IVFPQIndex::scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const
 
   // ---- phase C: candidates -> reference arithmetic, merged with phase A's keys ----
   GB_CUDA(launch_pq_rescore(ip, nq, probe_ids, coarse_dis, nprobe, dir, M_, d_table_, d_cand_cnt, cand, cap, keysA, kk, kk,
-                            metric, d_row_limit, f, adc_out, st));
+                            metric, d_row_limit, f, need_sorted, adc_out, st));
   // queries whose candidate list overflowed (or that had no bound): exact kernel over all probes, flag-gated
   const int ngF = (nprobe + 31) / 32;
   GB_ALLOC(partF, unsigned long long, (size_t)nq * ngF * kk, s);
@@ -2168,7 +2170,8 @@ int IVFPQIndex::scan_dev(const SearchContext& ctx, const FilterArgs& f, int metr
     adc = s.alloc_n<unsigned long long>((size_t)nq * kk);
     if (!adc) return -1;
   }
-  int lm = scan_listmajor_pq(f, metric, nq, xq, kk, ip, probe_ids, coarse_dis, nprobe, adc, s);
+  // the exact re-rank takes its candidates in any order; without it the ADC keys are the result and must be sorted
+  int lm = scan_listmajor_pq(f, metric, nq, xq, kk, ip, probe_ids, coarse_dis, nprobe, adc, !rerank, s);
   if (lm < 0) return -1;
   if (lm == 0) {
     last_scan_kernel_ = "pqtc_scan_kernel";

@@ -449,7 +449,7 @@ class IVFPQIndex : public IVFFlatIndex {
   // list-major scan through the tensor-core filter (kernels_pqtc.cu); 1 = not applicable
   int scan_listmajor_pq(const FilterArgs& f, int metric, int nq, const float* xq, int kk, const float* ip,
                         const int32_t* probe_ids, const float* coarse_dis, int nprobe, unsigned long long* adc_out,
-                        Scratch& s);
+                        bool need_sorted, Scratch& s);
 
   const float* train_transform(const float* xt, int64_t n, Scratch& s) override;
   const float* transform_dev(const float* x, int64_t n, Scratch& s) override;

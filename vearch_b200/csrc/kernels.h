@@ -151,7 +151,8 @@ cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nli
 cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis,
                               int nprobe, int pg, ListDirectory dir, int M, const float* T, int k, int metric,
                               FilterArgs f, unsigned long long* partial, cudaStream_t st, int ld_probe = 0,
-                              const int* gate_cnt = nullptr, int gate_cap = 0, const int* row_limit = nullptr);
+                              const int* gate_cnt = nullptr, int gate_cap = 0, const int* row_limit = nullptr,
+                              bool sorted_out = true);  // false: partial[..][k - 1] = the largest key, the others in any order
 
 // ---- K5 list-major: tensor-core filter + exact re-score (kernels_pqtc.cu) ---------------------------
 bool pqtc_supported(int M, int dsub);
@@ -184,7 +185,7 @@ cudaError_t launch_pq_entry_norms(ListDirectory dir, int nlist, int max_len, int
 cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                               ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,
                               int cap, const unsigned long long* keys_a, int64_t keys_a_stride, int kprime, int metric,
-                              const int* row_limit, FilterArgs f, unsigned long long* out, cudaStream_t st);
+                              const int* row_limit, FilterArgs f, bool sorted_out, unsigned long long* out, cudaStream_t st);
 // queries with cand_cnt > cap: out[q] = best kprime of partial[q][ngroups][kprime]
 cudaError_t launch_pq_fallback_merge(const int* cand_cnt, int cap, int nq, const unsigned long long* partial, int ngroups,
                                      int kprime, unsigned long long* out, cudaStream_t st);

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(PQ_NT)
     ivfpq_scan_kernel(const float* __restrict__ ip_table, const int32_t* __restrict__ probe_ids,
                       const float* __restrict__ coarse_dis, int nprobe, int ld_probe, int pg, ListDirectory dir, int M,
                       const float* __restrict__ T, int tile_e, int k, int KP, int SORTN, FilterArgs f,
-                      const int* __restrict__ gate_cnt, int gate_cap, const int* __restrict__ row_limit,
+                      const int* __restrict__ gate_cnt, int gate_cap, const int* __restrict__ row_limit, int sorted_out,
                       unsigned long long* __restrict__ partial) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tile_bytes = tile_e * M;
@@ -286,7 +286,38 @@ __global__ void __launch_bounds__(PQ_NT)
     }
   }
   __syncthreads();
-  cq.flush(true);
+  if (sorted_out) {
+    cq.flush(true);
+  } else {
+    // The caller wants the k best and their bound, not their order (phase A of the tensor-core filter): exact radix
+    // select, no sort; the largest key -- the sentinel when fewer than k entries qualified -- goes to slot k - 1.
+    cq.flush(false, true);
+    __shared__ unsigned long long s_wmax[PQ_NT / 32];
+    __shared__ int s_wpos[PQ_NT / 32];
+    unsigned long long mx = 0;
+    int pos = -1;
+    for (int i = tid; i < k; i += PQ_NT) {
+      const unsigned long long v = buf[i];
+      if (pos < 0 || v > mx) mx = v, pos = i;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long om = __shfl_xor_sync(0xffffffffu, mx, off);
+      const int op = __shfl_xor_sync(0xffffffffu, pos, off);
+      if (op >= 0 && (pos < 0 || om > mx || (om == mx && op > pos))) mx = om, pos = op;
+    }
+    if ((tid & 31) == 0) s_wmax[tid >> 5] = mx, s_wpos[tid >> 5] = pos;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < PQ_NT / 32; w++)
+        if (s_wpos[w] >= 0 && (pos < 0 || s_wmax[w] > mx || (s_wmax[w] == mx && s_wpos[w] > pos))) mx = s_wmax[w], pos = s_wpos[w];
+      if (pos >= 0 && pos != k - 1) {
+        buf[pos] = buf[k - 1];
+        buf[k - 1] = mx;
+      }
+    }
+    __syncthreads();
+  }
   for (int i = tid; i < k; i += PQ_NT) out[i] = buf[i];
 }
 
@@ -402,7 +433,8 @@ void pq_cq_geometry(int k, int tile_e, int* KP, int* SORTN) {
 template <int METRIC, int MW>
 cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                           int ld_probe, int pg, ListDirectory dir, int M, const float* T, int k, FilterArgs f,
-                          const int* gate_cnt, int gate_cap, const int* row_limit, unsigned long long* partial, cudaStream_t st) {
+                          const int* gate_cnt, int gate_cap, const int* row_limit, int sorted_out, unsigned long long* partial,
+                          cudaStream_t st) {
   int tile_e = pq_tile_entries(M);
   int KP, SORTN;
   pq_cq_geometry(k, tile_e, &KP, &SORTN);
@@ -414,7 +446,7 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
   int ngroups = (nprobe + pg - 1) / pg;
   dim3 grid(ngroups, nq);
   ivfpq_scan_kernel<METRIC, MW><<<grid, PQ_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T,
-                                                          tile_e, k, KP, SORTN, f, gate_cnt, gate_cap, row_limit, partial);
+                                                          tile_e, k, KP, SORTN, f, gate_cnt, gate_cap, row_limit, sorted_out, partial);
                                                           note_launch();
   return cudaGetLastError();
 }
@@ -422,10 +454,11 @@ cudaError_t launch_scan_t(const float* ip_table, int nq, const int32_t* probe_id
 template <int METRIC>
 cudaError_t launch_scan_m(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                           int ld_probe, int pg, ListDirectory dir, int M, const float* T, int k, FilterArgs f,
-                          const int* gate_cnt, int gate_cap, const int* row_limit, unsigned long long* partial, cudaStream_t st) {
+                          const int* gate_cnt, int gate_cap, const int* row_limit, int sorted_out, unsigned long long* partial,
+                          cudaStream_t st) {
 #define GB_SCAN(MW) \
   return launch_scan_t<METRIC, MW>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, \
-                                   gate_cap, row_limit, partial, st)
+                                   gate_cap, row_limit, sorted_out, partial, st)
   switch (M) {
     case 8: GB_SCAN(2);
     case 16: GB_SCAN(4);
@@ -463,15 +496,15 @@ cudaError_t launch_pq_precompute_table(const float* coarse, int64_t ldc, int nli
 cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis,
                               int nprobe, int pg, ListDirectory dir, int M, const float* T, int k, int metric,
                               FilterArgs f, unsigned long long* partial, cudaStream_t st, int ld_probe,
-                              const int* gate_cnt, int gate_cap, const int* row_limit) {
+                              const int* gate_cnt, int gate_cap, const int* row_limit, bool sorted_out) {
   if (nq <= 0 || nprobe <= 0) return cudaSuccess;
   if (ld_probe <= 0) ld_probe = nprobe;
   if (k <= 0 || k > 4096 || nq > 65535 || pg < 1 || pg > PQ_MAX_PG) return cudaErrorInvalidValue;
   if (metric == kMetricL2) {
     if (!T) return cudaErrorInvalidValue;
-    return launch_scan_m<kMetricL2>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, partial, st);
+    return launch_scan_m<kMetricL2>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, sorted_out ? 1 : 0, partial, st);
   }
-  return launch_scan_m<kMetricIP>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, partial, st);
+  return launch_scan_m<kMetricIP>(ip_table, nq, probe_ids, coarse_dis, nprobe, ld_probe, pg, dir, M, T, k, f, gate_cnt, gate_cap, row_limit, sorted_out ? 1 : 0, partial, st);
 }
 
 cudaError_t launch_rerank(const unsigned long long* cand_keys, int ncand, int nq, const float* xq, int64_t ldq, int d,

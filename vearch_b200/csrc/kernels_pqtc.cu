@@ -641,14 +641,14 @@ __global__ void __launch_bounds__(RS_NT)
                       const float* __restrict__ coarse_dis, int nprobe, ListDirectory dir, int M, const float* __restrict__ T,
                       const int* __restrict__ cand_cnt, const unsigned long long* __restrict__ cand, int cap,
                       const unsigned long long* __restrict__ keys_a, int64_t keys_a_stride, int kprime, int NP,
-                      const int* __restrict__ row_limit, FilterArgs f, unsigned long long* __restrict__ out) {
+                      const int* __restrict__ row_limit, FilterArgs f, int sorted_out, unsigned long long* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char rs_smem[];
   unsigned long long* buf = reinterpret_cast<unsigned long long*>(rs_smem);  // [NP]
   float* ips = reinterpret_cast<float*>(buf + NP);                            // [M][256]
   const int q = blockIdx.x, tid = threadIdx.x;
   const int cnt = cand_cnt[q];
   if (cnt > cap) return;  // overflow: the exact kernel redoes this query (pq_fallback_merge_kernel writes out)
-  if (cnt == 0) {  // nothing passed the filter: phase A's keys are the answer (common when the bound is tight)
+  if (cnt == 0 && !sorted_out) {  // nothing passed the filter: phase A's (unordered) keys are the answer -- the usual case
     for (int i = tid; i < kprime; i += RS_NT) out[(int64_t)q * kprime + i] = keys_a[(int64_t)q * keys_a_stride + i];
     return;
   }
@@ -856,7 +856,7 @@ cudaError_t launch_pqtc_scan(const unsigned char* a_scratch, const void* meta, c
 cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* probe_ids, const float* coarse_dis, int nprobe,
                               ListDirectory dir, int M, const float* T, const int* cand_cnt, const unsigned long long* cand,
                               int cap, const unsigned long long* keys_a, int64_t keys_a_stride, int kprime, int metric,
-                              const int* row_limit, FilterArgs f, unsigned long long* out, cudaStream_t st) {
+                              const int* row_limit, FilterArgs f, bool sorted_out, unsigned long long* out, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   const int NP = next_pow2(next_pow2(kprime < 16 ? 16 : kprime) + cap);  // CandQueue: KP best + cap candidates
   const size_t smem = (size_t)NP * 8 + (size_t)M * PT_KSUB * 4;
@@ -866,12 +866,12 @@ cudaError_t launch_pq_rescore(const float* ip_table, int nq, const int32_t* prob
     e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_rescore_kernel<kMetricL2><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
-                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, out);
+                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, sorted_out ? 1 : 0, out);
   } else {
     e = cudaFuncSetAttribute(pq_rescore_kernel<kMetricIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     pq_rescore_kernel<kMetricIP><<<nq, RS_NT, smem, st>>>(ip_table, probe_ids, coarse_dis, nprobe, dir, M, T, cand_cnt, cand,
-                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, out);
+                                                         cap, keys_a, keys_a_stride, kprime, NP, row_limit, f, sorted_out ? 1 : 0, out);
   }
   note_launch();
   return cudaGetLastError();
