@@ -94,6 +94,10 @@ class ClockSampler:
         self.uuid = uuid
         self.proc = None
         self.lines = []
+        self.first = 0
+
+    def mark(self):
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -112,6 +116,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)  # let the sample that covers the end of the window arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -119,7 +124,7 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 7:
                 continue
@@ -369,6 +374,12 @@ def measure(args, wl_name, wl, n_rank, rank, world, local, use_dist, family, ste
     k = args.k
     nprobe = args.nprobe or wl["nprobe"]
     recall_num = args.recall_num if args.recall_num >= 0 else (400 if wl["type"] == "IVFPQ" else 0)
+    sampler = None
+    if primary:  # nvidia-smi needs a second or two before its first sample: started ahead of the index build
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        sampler = ClockSampler(uuid)
+        sampler.start()
     idx, params, build = build_index(wl, n_rank, rank, local, family)
     if wl["type"] != "FLAT":
         nprobe = min(nprobe, params["ncentroids"])
@@ -465,12 +476,8 @@ def measure(args, wl_name, wl, n_rank, rank, world, local, use_dist, family, ste
             dist.barrier()
             torch.cuda.synchronize()
 
-    sampler = None
-    if primary:
-        uuid = str(torch.cuda.get_device_properties(local).uuid)
-        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
-        sampler = ClockSampler(uuid)
-        sampler.start()  # nvidia-smi needs ~1 s before its first sample: covers warm-up + both timed regions
+    if sampler:
+        sampler.mark()  # samples from here on: warm-up + both timed regions
 
     # ---- device-resident timing ----------------------------------------------------------------
     for b in range(warmup):
