@@ -228,6 +228,8 @@ struct CandQueue {
         } else {
           match = (key >> (shift + 8)) == prefix;
         }
+        // (a warp-aggregated add via __match_any_sync was measured slower than the plain shared atomics: phase A
+        // 0.77 -> 0.87 ms, coarse select +0.04 ms)
         if (match) atomicAdd(&s_hist[(int)(key >> shift) & 255], 1);
       }
       if (shift == 56) {
