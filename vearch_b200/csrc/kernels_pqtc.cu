@@ -13,8 +13,9 @@
 // only as a FILTER; every number that leaves the pipeline is recomputed with the reference's own
 // arithmetic, so results stay bit-identical to the LUT kernel and to the oracle:
 //
-//   phase A  the exact LUT kernel scans the first `pa` probes of every query and yields k' exact
-//            keys; its k'-th score B_q is an upper bound of the query's final k'-th score;
+//   phase A  the exact LUT kernel scans each query's leading probes in full (the fewest whose lists hold
+//            >= 4 k' entries, pqtc_plan_phase_a_kernel) and yields k' exact keys, unordered, the largest --
+//            B_q, an upper bound of the query's final k'-th score -- in slot k' - 1;
 //   phase B  (this file) for the remaining probes: pairs grouped by list (lmk_group), per group a
 //            fp16 operand tile of sa * (x - c_list) rows staged once (pq_stage_pairs_kernel), then a
 //            persistent warp-specialised kernel (pqtc_scan_kernel) decodes 128 entries at a time
@@ -22,8 +23,10 @@
 //            multiplies 128 pairs x 128 entries x d on the tensor core and compares
 //            acc + |r_e|^2 against  B_q - dis0 + eps(pair).  eps bounds |approximate - reference fp32|
 //            rigorously (fp16 rounding of both operands: 2^-10 |a||r| ; fp32 noise of both evaluations),
-//            so every entry whose reference score is <= B_q passes.  Passing entries (a few per
-//            query beyond k') are appended to the query's candidate list as (probe, position);
+//            so every entry whose reference score is <= B_q passes.  |r_e|^2 comes from a per-entry cache
+//            in HBM (pq_entry_norms_kernel), streamed with the codes.  Passing entries (a few per query)
+//            go through a shared-memory queue to a drain warp that appends (probe, position) to the
+//            query's candidate list, so no global atomic sits in the epilogue;
 //   phase C  pq_rescore_kernel re-evaluates the candidates with the reference arithmetic (same
 //            fmaf / add order as the LUT kernel), merges them with phase A's keys and keeps k'.
 //   A query whose candidate list overflows (no usable bound, adversarial data) is redone by the
