@@ -431,7 +431,7 @@ def test_ivfpq_train_on_device_recall():
                                       (128, 8, "float"), (32, 4, "float"), (96, 12, "float")])
 def test_ivfpq_listmajor_tensor_core_filter_matches_oracle(metric, d, M, data):
     """Many queries per list => the IVF-PQ scan runs list-major (kernels_pqtc.cu): exact LUT scan of the
-    first probes -> per-query bound -> bf16 tcgen05 FILTER over the other probes -> candidates re-scored
+    first probes -> per-query bound -> fp16 tcgen05 FILTER over the other probes -> candidates re-scored
     with the reference arithmetic.  The filter must never lose an entry: ADC scores bit-equal to the
     oracle and ids equal (tie-aware) on float data (every mantissa bit in use) as on integer data, at
     k = 10 and at re-rank depth 400, with tombstones, deletion bitmap, missing probes, score window."""

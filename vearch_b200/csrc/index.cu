@@ -1833,7 +1833,7 @@ int64_t IVFPQIndex::index_mem_bytes() const {
 }
 int IVFPQIndex::rebuild_table(cudaStream_t st) {
   pq_gen_++;  // the per-entry norm cache belongs to the previous codebook
-  // tables of the tensor-core filter (kernels_pqtc.cu): bf16 codebook pre-scaled by -2 (L2) / -1 (IP),
+  // tables of the tensor-core filter (kernels_pqtc.cu): fp16 codebook pre-scaled by -2 sb (L2) / -sb (IP), sb a power of two,
   // centroid norms, and the bound on |r| its error margin uses
   if (pqtc_supported(M_, dsub_)) {
     if (!d_cb16_) GB_CUDA(cudaMalloc(&d_cb16_, (size_t)M_ * 256 * dsub_ * 2));

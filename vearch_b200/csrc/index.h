@@ -457,7 +457,7 @@ class IVFPQIndex : public IVFFlatIndex {
   int M_, dsub_;
   float* d_pq_ = nullptr;     // [M][256][dsub]
   float* d_table_ = nullptr;  // [nlist][M][256] (L2 only)
-  uint16_t* d_cb16_ = nullptr;  // [M][256][dsub] bf16, pre-scaled (tensor-core filter)
+  uint16_t* d_cb16_ = nullptr;  // [M][256][dsub] fp16, pre-scaled (tensor-core filter)
   float* d_cbnrm_ = nullptr;    // [M][256] |pq|^2, then rmax2, sb
   // |r_e|^2 of every list entry (L2), flat with 32-entry aligned list segments: built by the first list-major search
   // after the lists or the codebook changed (lists are append-only: same list set + same lengths = same content)

@@ -158,7 +158,7 @@ cudaError_t launch_ivfpq_scan(const float* ip_table, int nq, const int32_t* prob
 bool pqtc_supported(int M, int dsub);
 void pqtc_debug_counters(unsigned long long out[4], bool reset);  // GB_PQTC_DBG diagnostics
 size_t pqtc_pair_meta_bytes();
-// cb[m][c][.] = bf16(-2 pq) (L2) / bf16(-pq) (IP); nrm[m][c] = |pq[m][c]|^2; rmax2[0] = sum_m max_c nrm
+// cb[m][c][.] = fp16(-2 sb pq) (L2) / fp16(-sb pq) (IP), sb = rmax2[1] a power of two; nrm[m][c] = |pq[m][c]|^2; rmax2[0] = sum_m max_c nrm
 cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uint16_t* cb, float* nrm, float* rmax2,
                                cudaStream_t st);
 // phase A's plan: per query its first P_q probes in full (fewest with >= target entries together, at most pa_max);
@@ -166,7 +166,7 @@ cudaError_t launch_pqtc_tables(const float* pq, int M, int dsub, int metric, uin
 cudaError_t launch_pqtc_plan_phase_a(const int32_t* probe_ids, int64_t npairs, int nprobe, int pa_max, long long target,
                                      const int* list_len, int32_t* probes_a, int32_t* probes_b, int* row_limit,
                                      cudaStream_t st);
-// per pair group: bf16 operand tile of (x - centroid) (L2) / x (IP) rows + the pairs' filter thresholds from
+// per pair group: fp16 operand tile (rows scaled by their own power of two) of (x - centroid) (L2) / x (IP) rows + the pairs' filter thresholds from
 // bound_keys[q][kprime - 1] (phase A's k'-th key); queries without a bound get cand_cnt = cap + 1
 cudaError_t launch_pq_stage_pairs(const float* xq, int64_t ldq, int d, const float* coarse, int64_t ldc, const LmTile* items,
                                   int max_items, const int64_t* totals, const int64_t* pair_j, int nprobe,
