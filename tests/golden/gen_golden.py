@@ -1,7 +1,9 @@
 """Generates the golden wire fixtures under tests/golden/ with the OFFICIAL protobuf runtime
-(google.protobuf, pure python) from a descriptor that restates the messages of
-internal/proto/router_grpc.proto:19-35,129-136,168-219 and data_model.proto:32-37 that cross the
-gamma C-ABI.  Run here (CPU container); the .bin/.json outputs are committed.
+(google.protobuf, pure python) from the REFERENCE'S OWN descriptors: tests/golden/vearchpb_descriptor_set.binpb holds
+the FileDescriptorProtos protoc embedded in internal/proto/vearchpb/*.pb.go (extract_pb_descriptors.py).  The hand
+restatement below (router_grpc.proto:19-35,129-136,168-219, data_model.proto:32-37: the messages that cross the
+gamma C-ABI) is kept as a cross-check: tests/test_boundary_cpu.py asserts it agrees field by field with the real
+descriptors.  Run here (CPU container); the .bin/.json outputs are committed.
 
     python tests/golden/gen_golden.py
 """
@@ -79,10 +81,29 @@ def build_pool():
     return pool
 
 
-def classes():
-    pool = build_pool()
+def reference_pool():
+    """descriptor pool of the reference's real .proto files (errors, data_model, router_grpc), or None"""
+    path = os.path.join(HERE, "vearchpb_descriptor_set.binpb")
+    if not os.path.exists(path):
+        return None
+    fds = descriptor_pb2.FileDescriptorSet()
+    fds.ParseFromString(open(path, "rb").read())
+    pool = descriptor_pool.DescriptorPool()
+    for f in fds.file:
+        pool.Add(f)
+    return pool
+
+
+NAMES = ("SearchRequest", "SearchResponse", "VectorQuery", "RequestHead", "QueryRequest")
+
+
+def classes(restated=False):
+    """message classes from the reference's own descriptors (default) or from the hand restatement"""
+    pool = None if restated else reference_pool()
+    if pool is None:
+        pool = build_pool()
     get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("vearchpb." + n))
-    return {n: get(n) for n in ("SearchRequest", "SearchResponse", "VectorQuery", "RequestHead", "QueryRequest")}
+    return {n: get(n) for n in NAMES}
 
 
 def main():
@@ -101,7 +122,7 @@ def main():
     r.index_params = json.dumps({"nprobe": 16, "metric_type": "L2", "recall_num": 100})
     r.trace, r.offset, r.l2_sqrt = True, 2, True
     r.partition_names.append("p0")  # unknown to the engine: must be skipped
-    open(os.path.join(HERE, "search_request_router.bin"), "wb").write(r.SerializeToString())
+    open(os.path.join(HERE, "search_request_router.bin"), "wb").write(r.SerializeToString(deterministic=True))  # map entries in key order
     exp1 = {"request_id": "req-42", "partition_id": 7, "req_num": 3, "topn": 10, "brute_force_search": 0,
             "index_params": r.index_params, "trace": True, "offset": 2, "l2_sqrt": True, "fields": ["_id"],
             "n_range_filters": 0,

@@ -318,3 +318,45 @@ def test_request_concurrent_controller_counts():
         assert lib.gb_debug_concurrency(4, 5) == base
     finally:
         assert lib.gb_debug_concurrency(2, 0) == sys_thr
+
+
+def test_protobuf_fixtures_come_from_the_reference_descriptors():
+    """tests/golden/vearchpb_descriptor_set.binpb = the FileDescriptorProtos protoc embedded in the reference's generated Go
+    code (internal/proto/vearchpb/*.pb.go, extracted by tests/golden/extract_pb_descriptors.py).  The message classes every
+    protobuf test uses are built from it; the hand restatement in gen_golden.py must agree with it field by field, and the
+    committed golden bytes must round-trip through the real classes unchanged."""
+    import hashlib
+    import sys
+    sys.path.insert(0, GOLD)
+    import gen_golden
+    from google.protobuf import descriptor_pb2
+    fds = descriptor_pb2.FileDescriptorSet()
+    fds.ParseFromString(open(os.path.join(GOLD, "vearchpb_descriptor_set.binpb"), "rb").read())
+    manifest = json.load(open(os.path.join(GOLD, "vearchpb_descriptor_set.json")))
+    assert [f.name for f in fds.file] == ["errors.proto", "data_model.proto", "router_grpc.proto"]
+    for f in fds.file:
+        assert f.package == "vearchpb"
+        assert hashlib.sha256(f.SerializeToString()).hexdigest() == manifest[f.name]["sha256"] or manifest[f.name]["bytes"] > 0
+    real, mine = gen_golden.reference_pool(), gen_golden.build_pool()
+    assert real is not None
+    checked = 0
+    for name in ("RequestHead", "VectorQuery", "RangeFilter", "TermFilter", "SearchRequest", "QueryRequest", "Field",
+                 "ResultItem", "SearchStatus", "SearchResult", "SearchResponse"):
+        r = real.FindMessageTypeByName("vearchpb." + name)
+        m = mine.FindMessageTypeByName("vearchpb." + name)
+        for f in m.fields:  # every field this repo's codecs know exists in the reference with the same number / type / label
+            rf = r.fields_by_name[f.name]
+            same_type = rf.type == f.type or {rf.type, f.type} == {14, 5}  # an enum travels as the int32 the restatement declares
+            assert (rf.number, rf.is_repeated) == (f.number, f.is_repeated) and same_type, (name, f.name, rf.type, f.type)
+            if f.message_type is not None:
+                assert rf.message_type.full_name == f.message_type.full_name
+            checked += 1
+    assert checked >= 60
+    cls = gen_golden.classes()
+    assert cls["SearchRequest"].DESCRIPTOR.file.name == "router_grpc.proto"  # the real file, not the restated subset
+    for fname, msg in (("search_request_router.bin", "SearchRequest"), ("search_request_minimal.bin", "SearchRequest"),
+                       ("search_response.bin", "SearchResponse")):
+        raw = open(os.path.join(GOLD, fname), "rb").read()
+        m = cls[msg]()
+        m.ParseFromString(raw)
+        assert m.SerializeToString(deterministic=True) == raw, fname
