@@ -960,3 +960,4 @@ def test_ivfpq_filter_survives_concurrent_adds_and_searches():
     dg, ig = idx.search(db[pick], 1, params={"nprobe": nlist, "recall_num": 100})
     assert (dg[:, 0] == 0).all() and (ig[:, 0] == pick).all()
     idx.close()
+
